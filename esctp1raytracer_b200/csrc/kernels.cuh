@@ -1,0 +1,553 @@
+// kernels.cuh — device kernels of the render path (see sweep.cuh for the sweeps).
+//
+//   build_origin_table   per (point O, triangle): the 48-byte filter row
+//   primary_kernel       raygen (camera.h:31-34) + closest hit (main.cpp:176-192)
+//   light_step_kernel    per pixel, per light: finish light k-1 (main.cpp:772-788),
+//                        set up the shadow ray of light k (main.cpp:740-770)
+//   list_prefix / list_scatter   group shadow rays by light vertex
+//   shadow_kernel        first in-order occluder (main.cpp:314-329)
+//   quantise_kernel      clamp + int(x*255) -> packed u8 RGB (main.cpp:679-684)
+//   assemble_bands_kernel  rank 0: band-packed rank buffers -> one frame
+#pragma once
+#include "sweep.cuh"
+
+namespace trk {
+
+using strict::f3;
+
+struct Cam {
+    float o[3], llc[3], hor[3], ver[3];
+};
+
+// local pixel k (row-major over the PPM rows this rank renders) -> (w, h)
+struct Bands {
+    int W, H, band_rows, band_index, band_count, n_px;
+    __host__ __device__ __forceinline__ void map(int k, int &w, int &h) const {
+        const int lr = k / W;
+        w = k - lr * W;
+        int pr = lr;
+        if (band_count > 1) {
+            const int lb = lr / band_rows;
+            pr = (band_index + lb * band_count) * band_rows + (lr - lb * band_rows);
+        }
+        h = H - 1 - pr; // PPM row 0 is h = H-1 (main.cpp:662)
+    }
+};
+
+// main.cpp:709-710 + camera.h:31-34, strict
+__device__ __forceinline__ f3 primary_dir(const Cam &c, int W, int H, int w, int h) {
+    const float s = __fdiv_rn((float)w, (float)(W - 1));
+    const float tt = __fdiv_rn((float)h, (float)(H - 1));
+    const f3 o = strict::ld(c.o), llc = strict::ld(c.llc), hor = strict::ld(c.hor), ver = strict::ld(c.ver);
+    return strict::normalize(strict::sub(strict::add(strict::add(llc, strict::mul(hor, s)), strict::mul(ver, tt)), o));
+}
+
+// ---------------------------------------------------------------------------------
+// Filter rows for lines through O (see sweep.cuh).  Computed in FP64 from the float
+// vertices, rounded once.  lmax bounds the length of any ray segment that will be
+// swept against this table (0 for the eye table: rays start AT O).
+//
+// Margin: the reference evaluates u' (etc.) as float dot/cross products of
+// tvec = orig - v0, dir, edges: absolute error <= ~8 eps |tvec||dir||edge|, with
+// |tvec| <= lmax + |a|.  Our own evaluation adds <= ~4 eps |a||edge|, and the
+// shadow ray's float direction misses O by <= ~3 eps len.  All are bounded by
+// K = CK eps * max|edge| * (lmax + |a| + |b| + |c|) with CK = 64.
+// If O is within the same noise of the triangle's plane the side s is undefined
+// (e.g. a light vertex against its own light's faces): the row is made
+// "always candidate" and the pair is always decided by the strict path.
+__global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tris, int n_pad, double ox, double oy,
+                                   double oz, double lmax, float4 *__restrict__ table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    float4 rb, rc, rd;
+    if (i >= n_tris) { // padding rows: never candidate
+        rb = rc = rd = make_float4(0.f, 0.f, 0.f, -1.f);
+    } else {
+        const float *p = tri_verts + 9 * (size_t)i;
+        const double v0x = p[0], v0y = p[1], v0z = p[2];
+        const double e1x = (double)p[3] - v0x, e1y = (double)p[4] - v0y, e1z = (double)p[5] - v0z;
+        const double e2x = (double)p[6] - v0x, e2y = (double)p[7] - v0y, e2z = (double)p[8] - v0z;
+        const double ax = v0x - ox, ay = v0y - oy, az = v0z - oz;
+        // B = a x e2, C = e1 x a, Nn = e2 x e1, D = Nn - B - C
+        const double Bx = ay * e2z - az * e2y, By = az * e2x - ax * e2z, Bz = ax * e2y - ay * e2x;
+        const double Cx = e1y * az - e1z * ay, Cy = e1z * ax - e1x * az, Cz = e1x * ay - e1y * ax;
+        const double Nx = e2y * e1z - e2z * e1y, Ny = e2z * e1x - e2x * e1z, Nz = e2x * e1y - e2y * e1x;
+        const double Dx = Nx - Bx - Cx, Dy = Ny - By - Cy, Dz = Nz - Bz - Cz;
+        const double tprime = e2x * Cx + e2y * Cy + e2z * Cz; // e2 . (tvec x e1), tvec = -a
+        const double la = sqrt(ax * ax + ay * ay + az * az);
+        const double lb = sqrt((ax + e1x) * (ax + e1x) + (ay + e1y) * (ay + e1y) + (az + e1z) * (az + e1z));
+        const double lc = sqrt((ax + e2x) * (ax + e2x) + (ay + e2y) * (ay + e2y) + (az + e2z) * (az + e2z));
+        const double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
+        const double l3 = sqrt((e2x - e1x) * (e2x - e1x) + (e2y - e1y) * (e2y - e1y) + (e2z - e1z) * (e2z - e1z));
+        const double emax = fmax(l1, fmax(l2, l3));
+        const double reach = lmax + la + lb + lc;
+        const double eps = (double)TRC_EPS;
+        const double K = (double)sweep::CK * eps * emax * reach;
+        const double tau = (double)sweep::CK * eps * l1 * l2 * reach;
+        if (!(fabs(tprime) > tau)) { // side of the plane undefined (or NaN): always candidate
+            rb = rc = rd = make_float4(0.f, 0.f, 0.f, 1.f);
+        } else {
+            const double s = tprime > 0 ? 1.0 : -1.0;
+            // round K up a little so the float row never under-states it
+            const float Kf = (float)(K * 1.0000002) + 1e-37f;
+            rb = make_float4((float)(s * Bx), (float)(s * By), (float)(s * Bz), Kf);
+            rc = make_float4((float)(s * Cx), (float)(s * Cy), (float)(s * Cz), Kf);
+            rd = make_float4((float)(s * Dx), (float)(s * Dy), (float)(s * Dz), Kf);
+        }
+    }
+    table[3 * (size_t)i] = rb;
+    table[3 * (size_t)i + 1] = rc;
+    table[3 * (size_t)i + 2] = rd;
+}
+
+// ---------------------------------------------------------------------------------
+struct PrimaryParams {
+    Cam cam;
+    Bands bands;
+    const float4 *table; // eye table
+    int n_tiles, n_tris;
+    const float *tri_verts;
+    const float4 *spheres;
+    int n_spheres;
+    int *hit_tri;
+    float *hit_t, *hit_v;
+    sweep::Counters *counters;
+    int *work;
+    int n_blocks;
+};
+
+template <int R, bool EXHAUSTIVE>
+__global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const PrimaryParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        sweep::fence_barrier_init();
+    }
+    __syncthreads();
+    unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0;
+    unsigned long long tests = 0, hits = 0;
+    for (;;) {
+        if (tid == 0) sm.blk = atomicAdd(p.work, 1);
+        __syncthreads();
+        const int blk = sm.blk;
+        if (blk >= p.n_blocks) break;
+        const int base = blk * (sweep::THREADS * R);
+        float ex[R], ey[R], ez[R];
+        unsigned valid = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int k = base + r * sweep::THREADS + tid;
+            if (k < p.bands.n_px) valid |= 1u << r;
+            k = min(k, p.bands.n_px - 1);
+            int w, h;
+            p.bands.map(k, w, h);
+            const f3 d = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
+            ex[r] = d.x, ey[r] = d.y, ez[r] = d.z;
+            sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
+            sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
+            sm.t[r][tid] = FLT_MAX; // main.cpp:715-717
+            sm.v[r][tid] = 0.f;
+            sm.tri[r][tid] = -1;
+        }
+        unsigned done = 0;
+        unsigned swept = 0;
+        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, p.n_tiles, p.tri_verts, ex, ey, ez, valid, done, gtile,
+                                                 n_strict, swept, n_miss);
+        n_swept += swept;
+        tests += (unsigned long long)__popc(valid) * p.n_tris;
+        // extension: analytic spheres after all triangles, strict, in order
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!((valid >> r) & 1u)) continue;
+            float t = sm.t[r][tid], v = sm.v[r][tid];
+            int tri = sm.tri[r][tid];
+            if (p.n_spheres > 0) {
+                const f3 o = strict::ld(p.cam.o);
+                const f3 d = strict::mk(ex[r], ey[r], ez[r]);
+                for (int s = 0; s < p.n_spheres; ++s)
+                    if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
+            }
+            const int k = base + r * sweep::THREADS + tid;
+            p.hit_tri[k] = tri;
+            p.hit_t[k] = t;
+            p.hit_v[k] = v;
+            hits += tri >= 0;
+        }
+        __syncthreads(); // slots are rewritten by the next block
+    }
+    atomicAdd(&p.counters->tests_primary, tests);
+    atomicAdd(&p.counters->n_hits, hits);
+    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
+    if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
+}
+
+// ---------------------------------------------------------------------------------
+struct LightInfo {              // device arrays describing the lights
+    const int *light_vbase;     // [L+1] prefix sum of F_l: index of light l's first vertex/table
+    const float *light_verts;   // [V*3] light.vertex[faceID] positions (main.cpp:749)
+};
+
+struct PixelState {
+    int *hit_tri;
+    float *hit_t, *hit_v;
+    float *carry_t;       // the `t` variable of scan_row across lights (main.cpp:715, 764, occlusion's t2)
+    float *nrm;           // [3][n_px]
+    float *accum;         // [3][n_px]
+    float *ro, *rd, *re;  // [3][n_px] shadow ray origin, strict unit dir, filter dir
+    float *rt;            // [n_px] tmax in, t after occlusion() out
+    int *rj;              // [n_px] light-vertex slot within the current light, -1 none
+    int *occ;             // [n_px] first in-order occluder, -1 none
+};
+
+struct LightStepParams {
+    Cam cam;
+    Bands bands;
+    PixelState px;
+    LightInfo li;
+    int k, L, n_tris;
+    const float *tri_verts, *tri_normals;
+    const int *tri_geom, *geom_has_normals;
+    const float *geom_material, *sphere_material;
+    const float4 *spheres;
+    int rng_mode;
+    uint32_t seed;
+    const int *faceid; // [n_px*L] local pixel order (explicit / mt19937 modes)
+    double lmax;
+    int *seg_count;    // [F_k] histogram of rays per light vertex
+    sweep::Counters *counters;
+    int *dbg_occ;      // [n_px*L] or null
+};
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+// counter-based faceID: uniform in [0,F), keyed by (seed, image index, light)
+__host__ __device__ __forceinline__ int hash_faceid(uint32_t seed, uint32_t image_index, uint32_t light, uint32_t F) {
+    uint32_t h = mix32((seed ^ 0x9e3779b9u) + image_index);
+    h = mix32(h ^ (light * 0x85ebca6bu + 0xc2b2ae35u));
+    return (int)(((unsigned long long)h * F) >> 32);
+}
+
+// glibc powf is computed in double and rounded once; do the same on the device
+__device__ __forceinline__ float powf_like_glibc(float x, float y) { return (float)pow((double)x, (double)y); }
+
+__global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p) {
+    const int kpx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = kpx < p.bands.n_px;
+    int my_j = -1;
+    unsigned long long ref_tests = 0;
+    if (in_range) {
+        const int n = p.bands.n_px;
+        const int tri = p.px.hit_tri[kpx];
+        if (tri < 0) {
+            if (p.k == 0) p.px.accum[kpx] = p.px.accum[n + kpx] = p.px.accum[2 * n + kpx] = 0.f; // vec3 ctor, vec.h:44
+            if (p.k < p.L) {
+                p.px.rj[kpx] = -1;
+                if (p.dbg_occ) p.dbg_occ[(size_t)kpx * p.L + p.k] = -2;
+            }
+        } else {
+            int w, h;
+            p.bands.map(kpx, w, h);
+            const f3 origin = strict::ld(p.cam.o);
+            const f3 dir = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
+            const float *mat;
+            f3 N;
+            float t;
+            f3 acc;
+            if (p.k == 0) {
+                t = p.px.hit_t[kpx];
+                if (tri < p.n_tris) {
+                    const float *q = p.tri_verts + 9 * (size_t)tri;
+                    const f3 v0 = strict::ld(q), v1 = strict::ld(q + 3), v2 = strict::ld(q + 6);
+                    N = strict::normalize(strict::cross(strict::sub(v1, v0), strict::sub(v2, v0))); // main.cpp:728-731
+                    const int g = p.tri_geom[tri];
+                    if (p.geom_has_normals && p.geom_has_normals[g]) { // main.cpp:733-738, u == 0
+                        const float *nq = p.tri_normals + 9 * (size_t)tri;
+                        const f3 N0 = strict::ld(nq), N1 = strict::ld(nq + 3), N2 = strict::ld(nq + 6);
+                        const float u = 0.f, v = p.px.hit_v[kpx];
+                        const float wgt = __fsub_rn(__fsub_rn(1.f, u), v);
+                        N = strict::normalize(strict::add(strict::add(strict::mul(N1, u), strict::mul(N2, v)), strict::mul(N0, wgt)));
+                    }
+                } else { // extension: sphere normal
+                    const float4 cr = p.spheres[tri - p.n_tris];
+                    N = strict::normalize(strict::sub(strict::add(origin, strict::mul(dir, t)), strict::mk(cr.x, cr.y, cr.z)));
+                }
+                p.px.nrm[kpx] = N.x, p.px.nrm[n + kpx] = N.y, p.px.nrm[2 * n + kpx] = N.z;
+                acc = strict::mk(0.f, 0.f, 0.f);
+            } else {
+                N = strict::mk(p.px.nrm[kpx], p.px.nrm[n + kpx], p.px.nrm[2 * n + kpx]);
+                acc = strict::mk(p.px.accum[kpx], p.px.accum[n + kpx], p.px.accum[2 * n + kpx]);
+                t = p.px.rt[kpx]; // what occlusion() left in t
+            }
+            mat = (tri < p.n_tris) ? p.geom_material + 13 * (size_t)p.tri_geom[tri]
+                                   : p.sphere_material + 13 * (size_t)(tri - p.n_tris);
+            const float fL = (float)p.L;
+            if (p.k > 0) { // finish light k-1: main.cpp:768-788
+                const int occ = p.px.occ[kpx];
+                if (p.dbg_occ) p.dbg_occ[(size_t)kpx * p.L + (p.k - 1)] = occ;
+                ref_tests += (occ >= 0 && occ < p.n_tris) ? (unsigned)(occ + 1) : (unsigned)p.n_tris;
+                if (occ < 0) {
+                    const f3 Lv = strict::mk(p.px.rd[kpx], p.px.rd[n + kpx], p.px.rd[2 * n + kpx]);
+                    const float d = strict::dot(N, Lv);
+                    if (d > 0.f) {
+                        const f3 ka = strict::ld(mat), kd = strict::ld(mat + 3), ks = strict::ld(mat + 6), ke = strict::ld(mat + 9);
+                        const float Ns = mat[12];
+                        f3 c = strict::div(strict::add(strict::mul(ka, 0.5f), ke), fL);
+                        const f3 Hh = strict::normalize(strict::mul(strict::add(N, Lv), 2.f));
+                        const float pw = powf_like_glibc(strict::dot(N, Hh), Ns);
+                        c = strict::add(c, strict::div(strict::add(strict::mul(kd, d), strict::mul(ks, pw)), fL));
+                        acc = strict::add(acc, c);
+                    }
+                }
+            }
+            p.px.accum[kpx] = acc.x, p.px.accum[n + kpx] = acc.y, p.px.accum[2 * n + kpx] = acc.z;
+            if (p.k < p.L) { // set up light k: main.cpp:740-766
+                const int vb = p.li.light_vbase[p.k];
+                const int F = p.li.light_vbase[p.k + 1] - vb;
+                int fid;
+                if (p.rng_mode == 0)
+                    fid = hash_faceid(p.seed, (uint32_t)(h * p.bands.W + w), (uint32_t)p.k, (uint32_t)F);
+                else
+                    fid = p.faceid[(size_t)kpx * p.L + p.k];
+                fid = min(max(fid, 0), F - 1);
+                const f3 v0 = strict::ld(p.li.light_verts + 3 * (size_t)(vb + fid));
+                // P = v0 + ((v1-v0)*r1 + (v2-v0)*r2) with v1 = v2 = v0 (main.cpp:749-754)
+                const f3 zero = strict::sub(v0, v0);
+                const f3 P = strict::add(v0, strict::add(strict::mul(zero, 0.5f), strict::mul(zero, 0.5f)));
+                const f3 hit = strict::add(origin, strict::mul(dir, __fsub_rn(t, TRC_EPS)));
+                f3 Lv = strict::sub(P, hit);
+                const float len = strict::length(Lv);
+                t = __fsub_rn(len, TRC_EPS);
+                Lv = strict::normalize(Lv);
+                p.px.ro[kpx] = hit.x, p.px.ro[n + kpx] = hit.y, p.px.ro[2 * n + kpx] = hit.z;
+                p.px.rd[kpx] = Lv.x, p.px.rd[n + kpx] = Lv.y, p.px.rd[2 * n + kpx] = Lv.z;
+                p.px.rt[kpx] = t;
+                // filter direction: the line through the light vertex, pointing at the hit point.
+                // A ray longer than the table's reach bound (never expected) or a degenerate one
+                // gets the zero direction: every row is then a candidate and the strict path decides.
+                float fx = hit.x - v0.x, fy = hit.y - v0.y, fz = hit.z - v0.z;
+                const float l2 = fx * fx + fy * fy + fz * fz;
+                const float inv = rsqrtf(l2);
+                const bool ok = (l2 > 0.f) && ((double)len <= p.lmax) && isfinite(inv);
+                fx = ok ? fx * inv : 0.f, fy = ok ? fy * inv : 0.f, fz = ok ? fz * inv : 0.f;
+                p.px.re[kpx] = fx, p.px.re[n + kpx] = fy, p.px.re[2 * n + kpx] = fz;
+                p.px.rj[kpx] = fid;
+                p.px.occ[kpx] = -1;
+                my_j = fid;
+            }
+        }
+    }
+    if (p.k < p.L) { // histogram of rays per light vertex, warp-aggregated
+        const unsigned active = __ballot_sync(0xffffffffu, my_j >= 0);
+        if (my_j >= 0) {
+            const unsigned peers = __match_any_sync(active, my_j);
+            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&p.seg_count[my_j], __popc(peers));
+        }
+    }
+    if (p.k > 0) {
+        for (int o = 16; o; o >>= 1) ref_tests += __shfl_down_sync(0xffffffffu, ref_tests, o);
+        if ((threadIdx.x & 31) == 0 && ref_tests) atomicAdd(&p.counters->tests_shadow_ref, ref_tests);
+    }
+}
+
+// seg_count[F] -> seg_off[F+1], blk_off[F+1] (ray blocks of rays_per_block), cursors zeroed
+__global__ void list_prefix_kernel(const int *seg_count, int F, int rays_per_block, int *seg_off, int *blk_off, int *cursor) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int so = 0, bo = 0;
+        for (int j = 0; j < F; ++j) {
+            seg_off[j] = so;
+            blk_off[j] = bo;
+            cursor[j] = 0;
+            so += seg_count[j];
+            bo += (seg_count[j] + rays_per_block - 1) / rays_per_block;
+        }
+        seg_off[F] = so;
+        blk_off[F] = bo;
+    }
+}
+
+__global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const int *__restrict__ seg_off, int *cursor,
+                                    int *__restrict__ list) {
+    const int kpx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = kpx < n_px ? rj[kpx] : -1;
+    const unsigned active = __ballot_sync(0xffffffffu, j >= 0);
+    if (j >= 0) {
+        const unsigned peers = __match_any_sync(active, j);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[j], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+        list[seg_off[j] + base + rank] = kpx;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+struct ShadowParams {
+    const float4 *tables; // tables of the current light's vertices, table j at + j*table_stride
+    size_t table_stride;  // in float4
+    int n_tiles, n_tris, F, n_px;
+    const float *tri_verts;
+    const float4 *spheres;
+    int n_spheres;
+    const int *list, *seg_off, *blk_off;
+    PixelState px;
+    sweep::Counters *counters;
+    int *work;
+};
+
+template <int R, bool EXHAUSTIVE>
+__global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        sweep::fence_barrier_init();
+    }
+    __syncthreads();
+    const int n = p.n_px;
+    const int total_blocks = p.blk_off[p.F];
+    unsigned gtile = 0, n_strict = 0, n_miss = 0;
+    unsigned long long tests = 0;
+    for (;;) {
+        if (tid == 0) {
+            const int b = atomicAdd(p.work, 1);
+            int j = 0;
+            if (b < total_blocks)
+                while (b >= p.blk_off[j + 1]) ++j;
+            sm.blk = b;
+            sm.seg = j;
+        }
+        __syncthreads();
+        const int blk = sm.blk, j = sm.seg;
+        if (blk >= total_blocks) break;
+        const int seg_begin = p.seg_off[j], seg_end = p.seg_off[j + 1];
+        const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
+        float ex[R], ey[R], ez[R];
+        int kp[R];
+        unsigned valid = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int e = base + r * sweep::THREADS + tid;
+            if (e < seg_end) valid |= 1u << r;
+            e = min(e, seg_end - 1);
+            const int k = p.list[e];
+            kp[r] = k;
+            ex[r] = p.px.re[k], ey[r] = p.px.re[n + k], ez[r] = p.px.re[2 * n + k];
+            sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
+            sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
+            sm.t[r][tid] = p.px.rt[k];
+            sm.tri[r][tid] = -1;
+        }
+        unsigned done = 0;
+        unsigned swept = 0;
+        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, p.tables + (size_t)j * p.table_stride, p.n_tiles, p.tri_verts, ex, ey,
+                                                ez, valid, done, gtile, n_strict, swept, n_miss);
+        tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!((valid >> r) & 1u)) continue;
+            float t = sm.t[r][tid];
+            int tri = sm.tri[r][tid];
+            if (tri < 0 && p.n_spheres > 0) { // extension: spheres after all triangles, in order
+                const f3 o = strict::mk(sm.ox[r][tid], sm.oy[r][tid], sm.oz[r][tid]);
+                const f3 d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
+                for (int s = 0; s < p.n_spheres && tri < 0; ++s)
+                    if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
+            }
+            p.px.occ[kp[r]] = tri;
+            p.px.rt[kp[r]] = t;
+        }
+        __syncthreads();
+    }
+    atomicAdd(&p.counters->tests_shadow, tests);
+    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
+    if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
+}
+
+// ---------------------------------------------------------------------------------
+// main.cpp:679-684: x>1 -> 1, int(x*255) truncation.  u8 cannot carry the
+// reference's negative / INT_MIN (NaN) prints: those clamp to 0.
+__device__ __forceinline__ unsigned quant(float x) {
+    x = (x > 1.f) ? 1.f : x;
+    const float y = __fmul_rn(x, 255.f);
+    if (!(y >= 0.f)) return 0u;
+    const int q = (int)y;
+    return (unsigned)(q > 255 ? 255 : q);
+}
+
+// 16 pixels per thread: 48 contiguous bytes = three 128-bit stores, fully coalesced
+__global__ void quantise_kernel(const float *__restrict__ accum, int n_px, uint8_t *__restrict__ rgb8) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k0 = g * 16;
+    if (k0 >= n_px) return;
+    if (k0 + 16 <= n_px && ((uintptr_t)rgb8 & 15u) == 0) {
+        unsigned bytes[48];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 *src = reinterpret_cast<const float4 *>(accum + (size_t)c * n_px + k0);
+            const bool al = (((uintptr_t)src) & 15u) == 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 f;
+                if (al)
+                    f = src[q];
+                else {
+                    const float *s1 = accum + (size_t)c * n_px + k0 + 4 * q;
+                    f = make_float4(s1[0], s1[1], s1[2], s1[3]);
+                }
+                bytes[(4 * q + 0) * 3 + c] = quant(f.x);
+                bytes[(4 * q + 1) * 3 + c] = quant(f.y);
+                bytes[(4 * q + 2) * 3 + c] = quant(f.z);
+                bytes[(4 * q + 3) * 3 + c] = quant(f.w);
+            }
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(rgb8 + (size_t)k0 * 3);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint4 o;
+            unsigned *ow = &o.x;
+#pragma unroll
+            for (int wv = 0; wv < 4; ++wv) {
+                const int b = (q * 4 + wv) * 4;
+                ow[wv] = bytes[b] | (bytes[b + 1] << 8) | (bytes[b + 2] << 16) | (bytes[b + 3] << 24);
+            }
+            dst[q] = o;
+        }
+    } else {
+        for (int k = k0; k < min(k0 + 16, n_px); ++k)
+            for (int c = 0; c < 3; ++c) rgb8[(size_t)k * 3 + c] = (uint8_t)quant(accum[(size_t)c * n_px + k]);
+    }
+}
+
+// hit mask in local pixel order (= the reference's scan order) for the mt19937 replay
+__global__ void hitmask_kernel(const int *__restrict__ hit_tri, int n_px, uint8_t *__restrict__ mask) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_px) mask[k] = hit_tri[k] >= 0;
+}
+
+// rank 0 after the gather: rank r's buffer holds its bands back to back
+__global__ void assemble_bands_kernel(const uint8_t *__restrict__ gathered, uint8_t *__restrict__ frame, int W, int H,
+                                      int band_rows, int band_count, int rows_pad) {
+    const size_t row_bytes = (size_t)W * 3;
+    const size_t total = row_bytes * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int pr = (int)(i / row_bytes);
+        const size_t x = i - (size_t)pr * row_bytes;
+        const int gb = pr / band_rows;
+        const int rank = gb % band_count;
+        const int lb = gb / band_count;
+        const int lr = lb * band_rows + (pr - gb * band_rows);
+        frame[i] = gathered[((size_t)rank * rows_pad + lr) * row_bytes + x];
+    }
+}
+
+}  // namespace trk

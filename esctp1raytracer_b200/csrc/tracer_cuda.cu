@@ -1,0 +1,538 @@
+// tracer_cuda.cu — C ABI (include/tracer_cuda.h) over the sm_100a kernels.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tracer_cuda.h"
+#include "kernels.cuh"
+
+extern "C" int tracer__mt19937_scan(uint32_t seed, int32_t n_lights, const int32_t *faces_per_light, int64_t n_px,
+                                    const uint8_t *hit_scan, int32_t *faceid_scan);
+
+namespace {
+
+constexpr int RAYS = 8; // rays per thread in the sweeps
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+} g;
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK_CUDA(call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(TRACER_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+    } while (0)
+
+template <typename T>
+int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(TRACER_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return 0;
+}
+template <typename T>
+void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+}  // namespace
+
+struct tracer_scene_dev {
+    int n_geoms = 0, n_tris = 0, n_pad = 0, n_lights = 0, n_spheres = 0, V = 0;
+    float *tri_verts = nullptr, *tri_normals = nullptr, *geom_material = nullptr, *sphere_material = nullptr;
+    int *tri_geom = nullptr, *geom_has_normals = nullptr;
+    float4 *spheres = nullptr;
+    int *light_vbase = nullptr;
+    float *light_verts = nullptr;
+    std::vector<int> h_light_vbase, h_light_F;
+    std::vector<float> h_light_verts;
+    double bb_lo[3], bb_hi[3];
+    float4 *eye_table = nullptr, *light_tables = nullptr;
+    size_t table_stride = 0; // float4 per table
+    double light_lmax = -1.0;
+    // per-frame workspace
+    int ws_npx = 0, ws_L = 0;
+    int *hit_tri = nullptr, *rj = nullptr, *occ = nullptr, *list = nullptr, *faceid = nullptr, *dbg_occ = nullptr;
+    float *hit_t = nullptr, *hit_v = nullptr, *carry = nullptr, *nrm = nullptr, *accum = nullptr, *ro = nullptr,
+          *rd = nullptr, *re = nullptr, *rt = nullptr;
+    uint8_t *rgb8 = nullptr, *mask = nullptr;
+    int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *work = nullptr;
+    int maxF = 0;
+    sweep::Counters *counters = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_shadow;
+    tracer_frame_stats stats{};
+};
+
+namespace {
+
+int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
+    const int L = std::max(1, s->n_lights);
+    if (n_px > s->ws_npx) {
+        dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->faceid);
+        dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
+        dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
+        dev_free(s->dbg_occ);
+        s->ws_npx = 0;
+        const size_t n = (size_t)n_px;
+        int rc = 0;
+        rc |= dev_alloc(&s->hit_tri, n) | dev_alloc(&s->rj, n) | dev_alloc(&s->occ, n) | dev_alloc(&s->list, n);
+        rc |= dev_alloc(&s->faceid, n * L);
+        rc |= dev_alloc(&s->hit_t, n) | dev_alloc(&s->hit_v, n) | dev_alloc(&s->carry, n);
+        rc |= dev_alloc(&s->nrm, 3 * n) | dev_alloc(&s->accum, 3 * n + 16) | dev_alloc(&s->ro, 3 * n);
+        rc |= dev_alloc(&s->rd, 3 * n) | dev_alloc(&s->re, 3 * n) | dev_alloc(&s->rt, n);
+        rc |= dev_alloc(&s->rgb8, 3 * n + 64) | dev_alloc(&s->mask, n);
+        if (rc) return TRACER_ERR_NOMEM;
+        s->ws_npx = n_px;
+    }
+    if (want_dbg_occ && !s->dbg_occ) {
+        if (dev_alloc(&s->dbg_occ, (size_t)s->ws_npx * L)) return TRACER_ERR_NOMEM;
+    }
+    return 0;
+}
+
+template <int R, bool EX>
+int launch_primary(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(sweep::Smem<R>);
+    CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trk::primary_kernel<R, EX><<<grid, sweep::THREADS, smem, st>>>(p);
+    CK_CUDA(cudaGetLastError());
+    return 0;
+}
+template <int R, bool EX>
+int launch_shadow(const trk::ShadowParams &p, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(sweep::Smem<R>);
+    CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trk::shadow_kernel<R, EX><<<grid, sweep::THREADS, smem, st>>>(p);
+    CK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int build_table(const tracer_scene_dev *s, const double o[3], double lmax, float4 *table, cudaStream_t st) {
+    const int th = 256;
+    trk::build_origin_table<<<(s->n_pad + th - 1) / th, th, 0, st>>>(s->tri_verts, s->n_tris, s->n_pad, o[0], o[1], o[2],
+                                                                      lmax, table);
+    CK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tracer_cuda_last_error(void) { return g_err.c_str(); }
+
+int tracer_cuda_init(int device_ordinal) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(TRACER_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0"));
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(TRACER_ERR_INVALID, "device ordinal out of range");
+    CK_CUDA(cudaSetDevice(device_ordinal));
+    CK_CUDA(cudaGetDeviceProperties(&g.prop, device_ordinal));
+    if (g.prop.major < 10)
+        return fail(TRACER_ERR_NO_DEVICE, std::string("kernels are built for sm_100a only; device is sm_") +
+                                              std::to_string(g.prop.major) + std::to_string(g.prop.minor));
+    if (!g.stream) CK_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.device = device_ordinal;
+    g.n_sms = g.prop.multiProcessorCount;
+    g.inited = true;
+    return TRACER_OK;
+}
+
+void tracer_cuda_shutdown(void) {
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.inited = false;
+}
+
+int tracer_cuda_device_info(tracer_device_info *out) {
+    if (!out) return fail(TRACER_ERR_INVALID, "null out");
+    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    std::memset(out, 0, sizeof *out);
+    std::snprintf(out->name, sizeof out->name, "%s", g.prop.name);
+    out->sm_count = g.prop.multiProcessorCount;
+    out->cc_major = g.prop.major, out->cc_minor = g.prop.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+    out->clock_khz = khz;
+    out->total_mem = (int64_t)g.prop.totalGlobalMem;
+    out->l2_bytes = g.prop.l2CacheSize;
+    return TRACER_OK;
+}
+
+void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
+    if (!s) return;
+    dev_free(s->tri_verts), dev_free(s->tri_normals), dev_free(s->geom_material), dev_free(s->sphere_material);
+    dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
+    dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables);
+    dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->faceid), dev_free(s->dbg_occ);
+    dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
+    dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
+    dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
+    dev_free(s->counters);
+    for (auto &e : s->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : s->ev_shadow) cudaEventDestroy(e);
+    delete s;
+}
+
+int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out) {
+    if (!out) return fail(TRACER_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    if (!sc || sc->n_geoms < 0 || sc->n_lights < 0 || sc->n_spheres < 0) return fail(TRACER_ERR_INVALID, "bad scene");
+    if (sc->n_geoms > 0 && (!sc->geom_tri_offset || !sc->geom_material)) return fail(TRACER_ERR_INVALID, "null scene array");
+    const int G = sc->n_geoms;
+    const int N = G > 0 ? sc->geom_tri_offset[G] : 0;
+    if (N < 0 || (N > 0 && !sc->tri_verts)) return fail(TRACER_ERR_INVALID, "bad triangle arrays");
+    for (int g2 = 0; g2 < G; ++g2)
+        if (sc->geom_tri_offset[g2] > sc->geom_tri_offset[g2 + 1] || sc->geom_tri_offset[g2] < 0)
+            return fail(TRACER_ERR_INVALID, "geom_tri_offset must be non-decreasing");
+    if (sc->n_lights > 0 && !sc->light_geom) return fail(TRACER_ERR_INVALID, "null light_geom");
+    if (sc->n_spheres > 0 && (!sc->sphere_cr || !sc->sphere_material)) return fail(TRACER_ERR_INVALID, "null sphere arrays");
+    bool any_normals = false;
+    for (int g2 = 0; g2 < G && sc->geom_has_normals; ++g2) any_normals |= sc->geom_has_normals[g2] != 0;
+    if (any_normals && !sc->tri_normals) return fail(TRACER_ERR_INVALID, "geom_has_normals set but tri_normals is null");
+
+    CK_CUDA(cudaSetDevice(g.device));
+    auto *s = new tracer_scene_dev();
+    s->n_geoms = G, s->n_tris = N, s->n_lights = sc->n_lights, s->n_spheres = sc->n_spheres;
+    s->n_pad = std::max(1, (N + sweep::TILE - 1) / sweep::TILE) * sweep::TILE;
+    s->table_stride = (size_t)s->n_pad * 3;
+#define TRY(x)                         \
+    do {                               \
+        int rc_ = (x);                 \
+        if (rc_) {                     \
+            tracer_cuda_scene_destroy(s); \
+            return rc_;                \
+        }                              \
+    } while (0)
+#define TRY_CUDA(call)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            tracer_cuda_scene_destroy(s);                                                                   \
+            return fail(TRACER_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+        }                                                                                                   \
+    } while (0)
+    TRY(dev_alloc(&s->tri_verts, (size_t)N * 9));
+    TRY_CUDA(cudaMemcpy(s->tri_verts, sc->tri_verts, (size_t)N * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    if (any_normals) {
+        TRY(dev_alloc(&s->tri_normals, (size_t)N * 9));
+        TRY_CUDA(cudaMemcpy(s->tri_normals, sc->tri_normals, (size_t)N * 9 * sizeof(float), cudaMemcpyHostToDevice));
+        TRY(dev_alloc(&s->geom_has_normals, (size_t)G));
+        TRY_CUDA(cudaMemcpy(s->geom_has_normals, sc->geom_has_normals, (size_t)G * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    TRY(dev_alloc(&s->geom_material, (size_t)G * 13));
+    TRY_CUDA(cudaMemcpy(s->geom_material, sc->geom_material, (size_t)G * 13 * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        std::vector<int> tg((size_t)std::max(N, 1));
+        for (int g2 = 0; g2 < G; ++g2)
+            for (int t = sc->geom_tri_offset[g2]; t < sc->geom_tri_offset[g2 + 1]; ++t) tg[t] = g2;
+        TRY(dev_alloc(&s->tri_geom, (size_t)N));
+        TRY_CUDA(cudaMemcpy(s->tri_geom, tg.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (sc->n_spheres > 0) {
+        TRY(dev_alloc(&s->spheres, (size_t)sc->n_spheres));
+        TRY_CUDA(cudaMemcpy(s->spheres, sc->sphere_cr, (size_t)sc->n_spheres * 4 * sizeof(float), cudaMemcpyHostToDevice));
+        TRY(dev_alloc(&s->sphere_material, (size_t)sc->n_spheres * 13));
+        TRY_CUDA(cudaMemcpy(s->sphere_material, sc->sphere_material, (size_t)sc->n_spheres * 13 * sizeof(float),
+                            cudaMemcpyHostToDevice));
+    }
+    // bounding box of everything a ray can start from or end at
+    for (int c = 0; c < 3; ++c) s->bb_lo[c] = 1e300, s->bb_hi[c] = -1e300;
+    for (size_t i = 0; i < (size_t)N * 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const double x = sc->tri_verts[3 * i + c];
+            s->bb_lo[c] = std::min(s->bb_lo[c], x), s->bb_hi[c] = std::max(s->bb_hi[c], x);
+        }
+    for (int i = 0; i < sc->n_spheres; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const double x = sc->sphere_cr[4 * i + c], r = std::fabs(sc->sphere_cr[4 * i + 3]);
+            s->bb_lo[c] = std::min(s->bb_lo[c], x - r), s->bb_hi[c] = std::max(s->bb_hi[c], x + r);
+        }
+    // lights: light.vertex[faceID], faceID in [0, F) (main.cpp:743-751) = the first F de-indexed vertices
+    s->h_light_vbase.assign(1, 0);
+    for (int l = 0; l < sc->n_lights; ++l) {
+        const int lg = sc->light_geom[l];
+        if (lg < 0 || lg >= G) {
+            tracer_cuda_scene_destroy(s);
+            return fail(TRACER_ERR_INVALID, "light_geom index out of range");
+        }
+        const int t0 = sc->geom_tri_offset[lg], F = sc->geom_tri_offset[lg + 1] - t0;
+        if (F <= 0) {
+            tracer_cuda_scene_destroy(s);
+            return fail(TRACER_ERR_INVALID, "light geometry has no faces");
+        }
+        s->h_light_F.push_back(F);
+        for (int f = 0; f < F; ++f)
+            for (int c = 0; c < 3; ++c) s->h_light_verts.push_back(sc->tri_verts[9 * (size_t)t0 + 3 * (size_t)f + c]);
+        s->h_light_vbase.push_back(s->h_light_vbase.back() + F);
+        s->maxF = std::max(s->maxF, F);
+    }
+    s->V = s->h_light_vbase.back();
+    TRY(dev_alloc(&s->light_vbase, s->h_light_vbase.size()));
+    TRY_CUDA(cudaMemcpy(s->light_vbase, s->h_light_vbase.data(), s->h_light_vbase.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRY(dev_alloc(&s->light_verts, s->h_light_verts.size()));
+    TRY_CUDA(cudaMemcpy(s->light_verts, s->h_light_verts.data(), s->h_light_verts.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t need = (size_t)(s->V + 1) * s->table_stride * sizeof(float4);
+        if (need > free_b / 2) {
+            tracer_cuda_scene_destroy(s);
+            return fail(TRACER_ERR_NOMEM, "light-vertex tables (" + std::to_string(need >> 20) + " MiB) exceed half of free HBM");
+        }
+    }
+    TRY(dev_alloc(&s->eye_table, s->table_stride));
+    TRY(dev_alloc(&s->light_tables, s->table_stride * (size_t)std::max(1, s->V)));
+    TRY(dev_alloc(&s->seg_count, (size_t)s->maxF + 1));
+    TRY(dev_alloc(&s->seg_off, (size_t)s->maxF + 2));
+    TRY(dev_alloc(&s->blk_off, (size_t)s->maxF + 2));
+    TRY(dev_alloc(&s->cursor, (size_t)s->maxF + 1));
+    TRY(dev_alloc(&s->work, 1));
+    TRY(dev_alloc(&s->counters, 1));
+    for (auto &e : s->ev) TRY_CUDA(cudaEventCreate(&e));
+    s->ev_shadow.resize(2 * (size_t)std::max(1, s->n_lights));
+    for (auto &e : s->ev_shadow) TRY_CUDA(cudaEventCreate(&e));
+#undef TRY
+#undef TRY_CUDA
+    *out = s;
+    return TRACER_OK;
+}
+
+int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int32_t W, int32_t H,
+                             const tracer_render_opts *opts_in, uint8_t *rgb_out) {
+    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    if (!s || !cam || !rgb_out) return fail(TRACER_ERR_INVALID, "null argument");
+    if (W < 2 || H < 2) return fail(TRACER_ERR_INVALID, "width and height must be >= 2 (the reference divides by W-1, H-1)");
+    if ((int64_t)W * H > (int64_t)1 << 30) return fail(TRACER_ERR_INVALID, "frame too large");
+    tracer_render_opts o;
+    std::memset(&o, 0, sizeof o);
+    if (opts_in) std::memcpy(&o, opts_in, std::min<size_t>(sizeof o, opts_in->struct_size ? opts_in->struct_size : sizeof o));
+    if (o.samples_per_pixel > 1) return fail(TRACER_ERR_INVALID, "samples_per_pixel > 1 is not implemented yet");
+    const int band_count = o.band_count <= 1 ? 1 : o.band_count;
+    const int band_rows = band_count > 1 ? o.band_rows : H;
+    if (band_count > 1 && (band_rows <= 0 || o.band_index < 0 || o.band_index >= band_count))
+        return fail(TRACER_ERR_INVALID, "bad band selection");
+    if (o.rng_mode == TRACER_RNG_MT19937 && band_count > 1)
+        return fail(TRACER_ERR_INVALID, "TRACER_RNG_MT19937 needs the whole frame in one call (band_count <= 1)");
+    if (o.rng_mode == TRACER_RNG_EXPLICIT && !o.faceid && s->n_lights > 0)
+        return fail(TRACER_ERR_INVALID, "TRACER_RNG_EXPLICIT needs opts->faceid");
+    if (o.rng_mode < 0 || o.rng_mode > 2) return fail(TRACER_ERR_INVALID, "bad rng_mode");
+    const int n_rows = tracer_band_row_count(H, band_rows, band_count > 1 ? o.band_index : 0, band_count);
+    const int n_px = n_rows * W;
+    const int L = s->n_lights;
+    CK_CUDA(cudaSetDevice(g.device));
+    cudaStream_t st = o.cuda_stream ? (cudaStream_t)o.cuda_stream : g.stream;
+    std::memset(&s->stats, 0, sizeof s->stats);
+    s->stats.n_sms = g.n_sms;
+    s->stats.n_pixels = n_px;
+    if (n_px == 0) return TRACER_OK;
+    if (int rc = ensure_workspace(s, n_px, o.out_occ_tri != nullptr)) return rc;
+    int launches = 0;
+
+    trk::Cam dc;
+    std::memcpy(dc.o, cam->origin, 12), std::memcpy(dc.llc, cam->lower_left_corner, 12);
+    std::memcpy(dc.hor, cam->horizontal, 12), std::memcpy(dc.ver, cam->vertical, 12);
+    trk::Bands bands{W, H, band_rows, band_count > 1 ? o.band_index : 0, band_count, n_px};
+
+    // reach bound for shadow segments: len_k <= (k+1) * diag(bbox U eye)  (t carries over lights, main.cpp:764)
+    double lo[3], hi[3], diag2 = 0;
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = std::min(s->bb_lo[c], (double)cam->origin[c]), hi[c] = std::max(s->bb_hi[c], (double)cam->origin[c]);
+        if (hi[c] >= lo[c]) diag2 += (hi[c] - lo[c]) * (hi[c] - lo[c]);
+    }
+    const double lmax_needed = (L + 1) * std::sqrt(diag2) * 1.001 + 1e-30;
+    if (L > 0 && (s->light_lmax < lmax_needed)) {
+        s->light_lmax = lmax_needed * 2.0; // head-room so that camera moves rarely trigger a rebuild
+        for (int j = 0; j < s->V; ++j) {
+            const double oo[3] = {s->h_light_verts[3 * j], s->h_light_verts[3 * j + 1], s->h_light_verts[3 * j + 2]};
+            if (int rc = build_table(s, oo, s->light_lmax, s->light_tables + (size_t)j * s->table_stride, st)) return rc;
+            ++launches;
+        }
+    }
+    CK_CUDA(cudaEventRecord(s->ev[0], st));
+    {
+        const double oo[3] = {cam->origin[0], cam->origin[1], cam->origin[2]};
+        if (int rc = build_table(s, oo, 0.0, s->eye_table, st)) return rc;
+        ++launches;
+    }
+    CK_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(sweep::Counters), st));
+    CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
+
+    const int rays_per_block = sweep::THREADS * RAYS;
+    const int n_tiles = s->n_pad / sweep::TILE;
+    // ---- primary: raygen + closest hit ----------------------------------------------
+    CK_CUDA(cudaEventRecord(s->ev[1], st));
+    {
+        trk::PrimaryParams p{};
+        p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
+        p.tri_verts = s->tri_verts, p.spheres = s->spheres, p.n_spheres = s->n_spheres;
+        p.hit_tri = s->hit_tri, p.hit_t = s->hit_t, p.hit_v = s->hit_v, p.counters = s->counters, p.work = s->work;
+        p.n_blocks = (n_px + rays_per_block - 1) / rays_per_block;
+        const int grid = std::min(p.n_blocks, g.n_sms);
+        int rc = o.exhaustive_strict ? launch_primary<RAYS, true>(p, grid, st) : launch_primary<RAYS, false>(p, grid, st);
+        if (rc) return rc;
+        ++launches;
+    }
+    CK_CUDA(cudaEventRecord(s->ev[2], st));
+
+    // ---- faceIDs ------------------------------------------------------------------------
+    if (L > 0 && o.rng_mode == TRACER_RNG_EXPLICIT) {
+        std::vector<int> loc((size_t)n_px * L);
+        for (int k = 0; k < n_px; ++k) {
+            int w, h;
+            bands.map(k, w, h);
+            std::memcpy(&loc[(size_t)k * L], o.faceid + ((size_t)h * W + w) * L, sizeof(int) * L);
+        }
+        CK_CUDA(cudaMemcpyAsync(s->faceid, loc.data(), loc.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK_CUDA(cudaStreamSynchronize(st));
+    } else if (L > 0 && o.rng_mode == TRACER_RNG_MT19937) {
+        trk::hitmask_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->hit_tri, n_px, s->mask);
+        CK_CUDA(cudaGetLastError());
+        ++launches;
+        std::vector<uint8_t> hm((size_t)n_px);
+        CK_CUDA(cudaMemcpyAsync(hm.data(), s->mask, (size_t)n_px, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> fid((size_t)n_px * L);
+        tracer__mt19937_scan(o.seed, L, s->h_light_F.data(), n_px, hm.data(), fid.data()); // local order == scan order
+        CK_CUDA(cudaMemcpyAsync(s->faceid, fid.data(), fid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // ---- lights: (finish k-1, set up k) -> group by light vertex -> first-occluder sweep ----
+    trk::PixelState px{s->hit_tri, s->hit_t, s->hit_v, s->carry, s->nrm, s->accum, s->ro, s->rd, s->re, s->rt, s->rj, s->occ};
+    for (int k = 0; k <= L; ++k) {
+        trk::LightStepParams lp{};
+        lp.cam = dc, lp.bands = bands, lp.px = px;
+        lp.li = trk::LightInfo{s->light_vbase, s->light_verts};
+        lp.k = k, lp.L = L, lp.n_tris = s->n_tris;
+        lp.tri_verts = s->tri_verts, lp.tri_normals = s->tri_normals, lp.tri_geom = s->tri_geom;
+        lp.geom_has_normals = s->geom_has_normals, lp.geom_material = s->geom_material;
+        lp.sphere_material = s->sphere_material, lp.spheres = s->spheres;
+        lp.rng_mode = o.rng_mode, lp.seed = o.seed, lp.faceid = s->faceid, lp.lmax = s->light_lmax;
+        lp.seg_count = s->seg_count, lp.counters = s->counters, lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
+        if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * (s->maxF + 1), st));
+        trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
+        CK_CUDA(cudaGetLastError());
+        ++launches;
+        if (k == L) break;
+        const int F = s->h_light_F[k];
+        trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, rays_per_block, s->seg_off, s->blk_off, s->cursor);
+        CK_CUDA(cudaGetLastError());
+        trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
+        CK_CUDA(cudaGetLastError());
+        launches += 2;
+        CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
+        CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
+        trk::ShadowParams sp{};
+        sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * s->table_stride, sp.table_stride = s->table_stride;
+        sp.n_tiles = n_tiles, sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
+        sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;
+        sp.list = s->list, sp.seg_off = s->seg_off, sp.blk_off = s->blk_off, sp.px = px;
+        sp.counters = s->counters, sp.work = s->work;
+        const int max_blocks = (n_px + rays_per_block - 1) / rays_per_block + F;
+        const int grid = std::min(max_blocks, g.n_sms);
+        int rc = o.exhaustive_strict ? launch_shadow<RAYS, true>(sp, grid, st) : launch_shadow<RAYS, false>(sp, grid, st);
+        if (rc) return rc;
+        ++launches;
+        CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
+    }
+
+    // ---- quantise + pack ------------------------------------------------------------------
+    uint8_t *dst8 = o.rgb_out_is_device ? rgb_out : s->rgb8;
+    trk::quantise_kernel<<<((n_px + 15) / 16 + 127) / 128, 128, 0, st>>>(s->accum, n_px, dst8);
+    CK_CUDA(cudaGetLastError());
+    ++launches;
+    CK_CUDA(cudaEventRecord(s->ev[3], st));
+    if (!o.rgb_out_is_device) CK_CUDA(cudaMemcpyAsync(rgb_out, s->rgb8, (size_t)n_px * 3, cudaMemcpyDeviceToHost, st));
+
+    // ---- optional debug read-backs -----------------------------------------------------------
+    if (o.out_tri) CK_CUDA(cudaMemcpyAsync(o.out_tri, s->hit_tri, (size_t)n_px * 4, cudaMemcpyDeviceToHost, st));
+    if (o.out_t) CK_CUDA(cudaMemcpyAsync(o.out_t, s->hit_t, (size_t)n_px * 4, cudaMemcpyDeviceToHost, st));
+    if (o.out_v) CK_CUDA(cudaMemcpyAsync(o.out_v, s->hit_v, (size_t)n_px * 4, cudaMemcpyDeviceToHost, st));
+    if (o.out_occ_tri && L > 0)
+        CK_CUDA(cudaMemcpyAsync(o.out_occ_tri, s->dbg_occ, (size_t)n_px * L * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<float> acc;
+    if (o.out_rgb) {
+        acc.resize((size_t)n_px * 3);
+        CK_CUDA(cudaMemcpyAsync(acc.data(), s->accum, acc.size() * 4, cudaMemcpyDeviceToHost, st));
+    }
+    sweep::Counters hc;
+    CK_CUDA(cudaMemcpyAsync(&hc, s->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(cudaStreamSynchronize(st));
+    if (o.out_rgb)
+        for (int k = 0; k < n_px; ++k)
+            for (int c = 0; c < 3; ++c) o.out_rgb[(size_t)k * 3 + c] = acc[(size_t)c * n_px + k];
+
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[3]);
+    s->stats.ms_total = ms;
+    cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]);
+    s->stats.ms_primary = ms;
+    double sh = 0;
+    for (int k = 0; k < L; ++k) {
+        cudaEventElapsedTime(&ms, s->ev_shadow[2 * k], s->ev_shadow[2 * k + 1]);
+        sh += ms;
+    }
+    s->stats.ms_shadow = sh;
+    s->stats.ms_other = s->stats.ms_total - s->stats.ms_primary - sh;
+    s->stats.n_primary_rays = n_px;
+    s->stats.n_shadow_rays = (int64_t)hc.n_hits * L;
+    s->stats.tests_primary = (int64_t)hc.tests_primary;
+    s->stats.tests_shadow = (int64_t)hc.tests_shadow;
+    s->stats.tests_shadow_ref = (int64_t)hc.tests_shadow_ref;
+    s->stats.strict_evals = (int64_t)hc.strict_evals;
+    s->stats.filter_misses = (int64_t)hc.filter_misses;
+    s->stats.kernel_launches = launches;
+    return TRACER_OK;
+}
+
+int tracer_cuda_last_stats(tracer_scene_dev *s, tracer_frame_stats *out) {
+    if (!s || !out) return fail(TRACER_ERR_INVALID, "null argument");
+    *out = s->stats;
+    return TRACER_OK;
+}
+
+int tracer_cuda_render(const tracer_scene_flat *scene, const tracer_camera *cam, int32_t width, int32_t height,
+                       const tracer_render_opts *opts, uint8_t *rgb_out) {
+    tracer_scene_dev *s = nullptr;
+    if (int rc = tracer_cuda_scene_create(scene, &s)) return rc;
+    const int rc = tracer_cuda_render_scene(s, cam, width, height, opts, rgb_out);
+    tracer_cuda_scene_destroy(s);
+    return rc;
+}
+
+int tracer_cuda_assemble_bands(const uint8_t *gathered_dev, uint8_t *frame_dev, int32_t width, int32_t height,
+                               int32_t band_rows, int32_t band_count, int32_t rows_per_rank_padded, void *cuda_stream) {
+    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    if (!gathered_dev || !frame_dev || width <= 0 || height <= 0 || band_rows <= 0 || band_count <= 0)
+        return fail(TRACER_ERR_INVALID, "bad argument");
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g.stream;
+    trk::assemble_bands_kernel<<<g.n_sms * 8, 256, 0, st>>>(gathered_dev, frame_dev, width, height, band_rows, band_count,
+                                                            rows_per_rank_padded);
+    CK_CUDA(cudaGetLastError());
+    CK_CUDA(cudaStreamSynchronize(st));
+    return TRACER_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle.
+
+Bar (BASELINE.json north_star): hit ids equal (ties within 1e-5 in t excepted) and PPM
+channels within +-1 LSB on >= 99.9 % of pixels.  The strict-finalisation design is meant
+to do better: ids, t, v, occlusion decisions and the float accumulator are expected to be
+BIT-IDENTICAL whenever ks == 0 (no powf), which these tests assert; with ks != 0 the
+float channels may differ by the device pow's rounding, and the u8 bar applies.
+"""
+import numpy as np
+import pytest
+from conftest import bits, golden_names, load_golden, to_flat, to_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def renderer():
+    from esctp1raytracer_b200 import Renderer
+
+    return Renderer(0)
+
+
+def _cam(fr):
+    from esctp1raytracer_b200 import Camera
+
+    return Camera.for_frame(fr["eye"], fr["look"], fr["W"], fr["H"])
+
+
+def _to_ppm_order(a, W, H):
+    """image index order (h*W+w) -> PPM row order (row 0 = h=H-1)"""
+    return a.reshape(H, W, *a.shape[1:])[::-1].reshape(a.shape)
+
+
+def _check_frame(out, W, H, tri, t, v, rgb, q, has_pow, occ=None):
+    assert out.stats == {} or out.stats["filter_misses"] == 0
+    assert np.array_equal(out.tri, _to_ppm_order(tri, W, H)), "hit ids differ"
+    assert np.array_equal(bits(out.t), bits(_to_ppm_order(t, W, H))), "closest-hit t differs"
+    assert np.array_equal(bits(out.v), bits(_to_ppm_order(v, W, H))), "closest-hit v differs"
+    if occ is not None:
+        assert np.array_equal(out.occ_tri, _to_ppm_order(occ, W, H)), "shadow decisions differ"
+    ref_rgb = _to_ppm_order(rgb, W, H)
+    if not has_pow:
+        assert np.array_equal(bits(out.rgb), bits(ref_rgb)), "float accumulator differs"
+        assert np.array_equal(out.rgb8.reshape(-1, 3), np.asarray(q, np.uint8).reshape(-1, 3))
+    d = np.abs(out.rgb8.reshape(-1, 3).astype(int) - np.asarray(q).reshape(-1, 3).astype(int))
+    assert (d.max(axis=1) <= 1).mean() >= 0.999, "PPM channels: more than 0.1 % of pixels off by > 1 LSB"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_explicit_faceids(renderer, name):
+    """CUDA vs the frames the reference itself rendered (tests/golden), faceIDs replayed."""
+    from esctp1raytracer_b200 import RNG_EXPLICIT
+
+    fs, fr = load_golden(name)
+    W, H = fr["W"], fr["H"]
+    out = renderer.trace(to_scene(fs), _cam(fr), W, H, rng_mode=RNG_EXPLICIT, faceid=fr["faceid"], debug=True)
+    has_pow = bool(fs.geom_material[:, 6:9].any())
+    _check_frame(out, W, H, fr["tri"], fr["t"], fr["v"], fr["rgb"], fr["q"], has_pow)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_mt19937_seed(renderer, name):
+    """Given only the seed, the library's own std::mt19937 replay reproduces the seeded serial path."""
+    from esctp1raytracer_b200 import RNG_MT19937
+
+    fs, fr = load_golden(name)
+    W, H = fr["W"], fr["H"]
+    rs = renderer.upload(to_scene(fs))
+    out = renderer.trace(rs, _cam(fr), W, H, rng_mode=RNG_MT19937, seed=fr["seed"], debug=True)
+    has_pow = bool(fs.geom_material[:, 6:9].any())
+    _check_frame(out, W, H, fr["tri"], fr["t"], fr["v"], fr["rgb"], fr["q"], has_pow)
+    assert out.stats["kernel_launches"] > 0 and out.stats["tests_primary"] == W * H * fs.n_tris
+
+
+@pytest.mark.parametrize("name", ["cornell_original", "cornell_sphere", "cornell_original_3lights"])
+def test_exhaustive_strict_mode_agrees_and_filter_never_misses(renderer, name):
+    from esctp1raytracer_b200 import RNG_EXPLICIT
+
+    fs, fr = load_golden(name)
+    W, H = fr["W"], fr["H"]
+    rs = renderer.upload(to_scene(fs))
+    a = renderer.trace(rs, _cam(fr), W, H, rng_mode=RNG_EXPLICIT, faceid=fr["faceid"], debug=True, exhaustive_strict=True)
+    assert a.stats["filter_misses"] == 0
+    _check_frame(a, W, H, fr["tri"], fr["t"], fr["v"], fr["rgb"], fr["q"], False)
+
+
+def _soup_case(renderer, restated, n_tris, n_geoms, n_lights, W, H, seed, **kw):
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    s = scenes.soup_scene(n_tris, n_geoms, n_lights, seed=seed, **kw)
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    fid = hash_faceids(seed, W, H, s.faces_per_light)
+    o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=fid)
+    rs = renderer.upload(s)
+    out = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True)
+    has_pow = bool(s.geom_material[:, 6:9].any() or s.sphere_material[:, 6:9].any())
+    _check_frame(out, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), has_pow, occ=o.occ_tri)
+    st = out.stats
+    assert st["tests_primary"] == o.n_tests[0]
+    assert st["tests_shadow_ref"] == o.n_tests[1]  # the reference's own count of shadow tests
+    assert st["n_shadow_rays"] == int((o.tri >= 0).sum()) * n_lights
+    return s, rs, cam, out, o
+
+
+def test_soup_hash_rng_4_lights(renderer, restated):
+    """config-4 shaped scene (small): 4 lights, the t carry between lights, counter-based RNG."""
+    _soup_case(renderer, restated, 20000, 40, 4, 96, 64, 5)
+
+
+def test_soup_normals_and_specular(renderer, restated):
+    _soup_case(renderer, restated, 6000, 20, 2, 80, 60, 9, edge=(0.05, 0.2), with_normals=True, specular=True)
+
+
+def test_soup_with_spheres_extension(renderer, restated):
+    """analytic spheres: no reference behaviour exists (parity unpinned); oracle = our restatement."""
+    s, rs, cam, out, o = _soup_case(renderer, restated, 5000, 20, 2, 80, 60, 3, n_spheres=60, edge=(0.03, 0.1))
+    assert (o.tri >= s.n_tris).any()
+
+
+def test_large_triangle_count_subset(renderer, restated):
+    """200k triangles at 256x144 on the GPU; the oracle checks a random pixel subset."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    W, H, seed = 256, 144, 21
+    s = scenes.soup_scene(200_000, 200, 4, seed=seed)
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    out = renderer.trace(renderer.upload(s), cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True)
+    fid = hash_faceids(seed, W, H, s.faces_per_light)
+    idx = np.random.default_rng(0).choice(W * H, 192, replace=False)
+    ph, pw = idx // W, idx % W
+    o = restated.render_pixels(to_flat(s), cam.as_array(), W, H, pw, ph, fid[idx])
+    k = (H - 1 - ph) * W + pw  # local (PPM-order) index
+    assert np.array_equal(out.tri[k], o.tri)
+    assert np.array_equal(bits(out.t[k]), bits(o.t))
+    assert np.array_equal(out.occ_tri[k], o.occ_tri)
+    assert np.array_equal(bits(out.rgb[k]), bits(o.rgb))
+    assert np.array_equal(out.rgb8.reshape(-1, 3)[k], o.rgb8)
+
+
+def test_bands_equal_whole_frame(renderer):
+    """interleaved row bands rendered separately (what each rank does) == the whole frame, byte for byte"""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+
+    s = scenes.box_scene()
+    W, H = 100, 77
+    cam = Camera.for_frame((0, 1, 2.9), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    full = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=4).rgb8
+    for n, B in ((2, 8), (4, 8), (3, 5), (8, 16)):
+        frame = np.zeros_like(full)
+        for r in range(n):
+            part = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=4, bands=(B, r, n)).rgb8
+            rows = [pr for pr in range(H) if (pr // B) % n == r]
+            assert part.shape[0] == len(rows)
+            frame[rows] = part
+        assert np.array_equal(frame, full)
+
+
+def test_edge_cases(renderer):
+    from esctp1raytracer_b200 import RNG_HASH, Camera, Scene, TracerError, scenes
+
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), 16, 9)
+    # empty scene: black frame (src/main.cpp:537-543 with no model)
+    empty = Scene(np.array([0]), np.zeros((0, 3, 3), np.float32), np.zeros((0, 13), np.float32), np.zeros(0, np.int32))
+    assert not renderer.trace(empty, cam, 16, 9).rgb8.any()
+    # no light (models/cornell/water.obj): black frame
+    s = scenes.box_scene()
+    nolight = Scene(s.geom_tri_offset, s.tri_verts, s.geom_material, np.zeros(0, np.int32))
+    out = renderer.trace(nolight, cam, 16, 9, debug=True)
+    assert not out.rgb8.any() and (out.tri >= 0).any()
+    # camera looking away: all rays miss
+    away = Camera.for_frame((0, 1, 3), (0, 1, 6), 16, 9)
+    out = renderer.trace(s, away, 16, 9, debug=True)
+    assert (out.tri == -1).all() and not out.rgb8.any()
+    # ragged sizes (not a multiple of anything), one-shot call
+    assert renderer.trace(s, Camera.for_frame((0, 1, 2.9), (0, 1, 0), 37, 23), 37, 23).rgb8.shape == (23, 37, 3)
+    with pytest.raises(TracerError):
+        renderer.trace(s, cam, 1, 9)  # the reference divides by W-1
+
+
+def test_idempotent_and_seed_sensitivity(renderer):
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+
+    s = scenes.soup_scene(30000, 30, 4, seed=2)
+    W, H = 128, 72
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=1).rgb8
+    b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=1).rgb8
+    c = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=2).rgb8
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def test_fp32_peak_microbenchmark_runs(renderer):
+    tf0, _ = renderer.fp32_peak(0, 3)
+    tf1, _ = renderer.fp32_peak(1, 3)
+    assert 10.0 < tf0 < 100.0 and 10.0 < tf1 < 100.0
