@@ -4,6 +4,7 @@
 //   variant 0: scalar FFMA, 16 independent chains per thread
 //   variant 1: packed FFMA2 (fma.rn.f32x2), 8 independent 2-wide chains per thread
 //   variant 2: the renderer's instruction mix (9 FFMA + min3/max per pair, no memory)
+//   variant 3: scalar FFMA, every chain with its own multiplier and addend registers
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -49,6 +50,24 @@ __global__ void __launch_bounds__(256) ffma2_kernel(float *out, int outer, float
     if (s == 123.456f) out[0] = s;
 }
 
+// scalar FFMA with distinct multiplier/addend registers per chain (no shared operands)
+__global__ void __launch_bounds__(256) ffma_distinct_kernel(float *out, int outer, float a, float b) {
+    float x[CHAINS], m[CHAINS], c[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) x[i] = (float)(threadIdx.x + i), m[i] = a + 1e-8f * i, c[i] = b * (i + 1);
+    for (int o = 0; o < outer; ++o) {
+#pragma unroll
+        for (int k = 0; k < INNER; ++k) {
+#pragma unroll
+            for (int i = 0; i < CHAINS; ++i) x[i] = fmaf(x[i], m[i], c[i]);
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;
+}
+
 // the sweep's per-pair instruction mix, registers only: 8 rays x (9 FFMA + 2 FMNMX + 1 FMNMX)
 __global__ void __launch_bounds__(256) mix_kernel(float *out, int outer, float a, float b) {
     float ex[8], ey[8], ez[8];
@@ -90,8 +109,10 @@ extern "C" int tracer_cuda_fp32_peak(int32_t variant, int32_t iters, double *tfl
             ffma_kernel<<<grid, block>>>(out, outer, 1.0000001f, 1e-9f);
         else if (variant == 1)
             ffma2_kernel<<<grid, block>>>(out, outer, 1.0000001f, 1e-9f);
-        else
+        else if (variant == 2)
             mix_kernel<<<grid, block>>>(out, outer, 1.0000001f, 1e-9f);
+        else
+            ffma_distinct_kernel<<<grid, block>>>(out, outer, 1.0000001f, 1e-9f);
     };
     for (int i = 0; i < 3; ++i) launch();
     cudaEventRecord(e0);

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         }
         unsigned done = 0;
         unsigned swept = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, p.n_tiles, p.tri_verts, ex, ey, ez, valid, done, gtile,
+        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, p.n_tiles, p.n_tris, p.tri_verts, ex, ey, ez, valid, done, gtile,
                                                  n_strict, swept, n_miss);
         n_swept += swept;
         tests += (unsigned long long)__popc(valid) * p.n_tris;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         }
         unsigned done = 0;
         unsigned swept = 0;
-        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, p.tables + (size_t)j * p.table_stride, p.n_tiles, p.tri_verts, ex, ey,
+        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, p.tables + (size_t)j * p.table_stride, p.n_tiles, p.n_tris, p.tri_verts, ex, ey,
                                                 ez, valid, done, gtile, n_strict, swept, n_miss);
         tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
 #pragma unroll

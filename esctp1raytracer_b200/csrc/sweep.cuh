@@ -149,7 +149,7 @@ __device__ __noinline__ unsigned strict_anyhit(Smem<R> &sm, int tid, unsigned ma
 // valid:    bit r set = ray r exists; done: bit r set = ray r needs no more tests
 // gtile:    running tile counter of this CTA (mbarrier phase bookkeeping across ray blocks)
 template <int R, bool ANYHIT, bool EXHAUSTIVE>
-__device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restrict__ table, int n_tiles,
+__device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restrict__ table, int n_tiles, int n_tris,
                                             const float *__restrict__ tri_verts, const float (&ex)[R],
                                             const float (&ey)[R], const float (&ez)[R], unsigned valid, unsigned &done,
                                             unsigned &gtile, unsigned &n_strict, unsigned &n_tiles_swept,
@@ -193,7 +193,7 @@ __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restric
                     const int tri = it * TILE + i;
                     if (EXHAUSTIVE) {
                         // validation mode: strict-test every pair, count pairs the filter would have lost
-                        const unsigned todo = valid & ~done;
+                        const unsigned todo = tri < n_tris ? (valid & ~done) : 0u; // skip padding rows
                         if (todo) {
                             if (ANYHIT) {
                                 const unsigned nw = strict_anyhit<R>(sm, tid, todo, tri, tri_verts, n_strict);
