@@ -198,7 +198,7 @@ class Renderer:
     def upload(self, scene: Scene) -> ResidentScene:
         return ResidentScene(self, scene)
 
-    def _opts(self, scene, width, height, rng_mode, seed, faceid, bands, exhaustive, debug, n_px, keep):
+    def _opts(self, scene, width, height, rng_mode, seed, faceid, bands, exhaustive, debug, n_px, keep, tuning):
         o = _lib.RenderOpts()
         o.struct_size = C.sizeof(_lib.RenderOpts)
         o.rng_mode, o.seed = rng_mode, seed & 0xFFFFFFFF
@@ -211,6 +211,7 @@ class Renderer:
         if bands is not None:
             o.band_rows, o.band_index, o.band_count = bands
         o.exhaustive_strict = int(exhaustive)
+        o.rays_per_thread, o.shadow_chunks = tuning
         dbg = {}
         if debug:
             L = scene.n_lights
@@ -221,7 +222,8 @@ class Renderer:
         return o, dbg
 
     def trace(self, scene, camera: Camera, width: int, height: int, *, rng_mode=RNG_HASH, seed=1, faceid=None,
-              bands=None, exhaustive_strict=False, debug=False, out_device_ptr=None, stream=None) -> Frame:
+              bands=None, exhaustive_strict=False, debug=False, out_device_ptr=None, stream=None,
+              rays_per_thread=0, shadow_chunks=0) -> Frame:
         """Render; ``scene`` is a Scene (one-shot: upload + render, the drop-in call) or a
         ResidentScene.  ``bands`` = (band_rows, band_index, band_count).  With
         ``out_device_ptr`` the packed rows are left in HBM at that address."""
@@ -229,7 +231,8 @@ class Renderer:
         rows = height if bands is None else band_row_count(height, *bands)
         n_px = rows * width
         keep = []
-        o, dbg = self._opts(sc, width, height, rng_mode, seed, faceid, bands, exhaustive_strict, debug, n_px, keep)
+        o, dbg = self._opts(sc, width, height, rng_mode, seed, faceid, bands, exhaustive_strict, debug, n_px, keep,
+                            (rays_per_thread, shadow_chunks))
         out = None
         if out_device_ptr is not None:
             o.rgb_out_is_device = 1

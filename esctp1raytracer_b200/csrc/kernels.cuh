@@ -95,9 +95,16 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
             rd = make_float4((float)(s * Dx), (float)(s * Dy), (float)(s * Dz), Kf);
         }
     }
-    table[3 * (size_t)i] = rb;
-    table[3 * (size_t)i + 1] = rc;
-    table[3 * (size_t)i + 2] = rd;
+    // pair-interleaved record (sweep.cuh: edge_min): triangle i is slot i&1 of record i>>1
+    float *rec = reinterpret_cast<float *>(table) + (size_t)(i >> 1) * 24 + (i & 1);
+    const float4 rows[3] = {rb, rc, rd};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        rec[8 * r + 0] = rows[r].x;
+        rec[8 * r + 2] = rows[r].y;
+        rec[8 * r + 4] = rows[r].z;
+        rec[8 * r + 6] = rows[r].w;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         const int blk = sm.blk;
         if (blk >= p.n_blocks) break;
         const int base = blk * (sweep::THREADS * R);
-        float ex[R], ey[R], ez[R];
+        float2 ex[R], ey[R], ez[R];
         unsigned valid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             int w, h;
             p.bands.map(k, w, h);
             const f3 d = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
-            ex[r] = d.x, ey[r] = d.y, ez[r] = d.z;
+            ex[r] = make_float2(d.x, d.x), ey[r] = make_float2(d.y, d.y), ez[r] = make_float2(d.z, d.z);
             sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
             sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
             sm.t[r][tid] = FLT_MAX; // main.cpp:715-717
@@ -152,10 +159,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             sm.tri[r][tid] = -1;
         }
         unsigned done = 0;
-        unsigned swept = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, p.n_tiles, p.n_tris, p.tri_verts, ex, ey, ez, valid, done, gtile,
-                                                 n_strict, swept, n_miss);
-        n_swept += swept;
+        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, 0, p.n_tiles, p.n_tris, p.tri_verts, ex, ey, ez, valid, done,
+                                                 gtile, n_strict, n_swept, n_miss);
         tests += (unsigned long long)__popc(valid) * p.n_tris;
         // extension: analytic spheres after all triangles, strict, in order
 #pragma unroll
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             int tri = sm.tri[r][tid];
             if (p.n_spheres > 0) {
                 const f3 o = strict::ld(p.cam.o);
-                const f3 d = strict::mk(ex[r], ey[r], ez[r]);
+                const f3 d = strict::mk(ex[r].x, ey[r].x, ez[r].x);
                 for (int s = 0; s < p.n_spheres; ++s)
                     if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
             }
@@ -357,22 +362,20 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
     }
 }
 
-// seg_count[F] -> seg_off[F+1], blk_off[F+1] (ray blocks of rays_per_block), cursors zeroed
-__global__ void list_prefix_kernel(const int *seg_count, int F, int rays_per_block, int *seg_off, int *blk_off, int *cursor) {
+// seg_count[F] -> seg_off[F+1] (fixed for this light), cursors zeroed
+__global__ void list_prefix_kernel(const int *seg_count, int F, int *seg_off, int *cursor) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int so = 0, bo = 0;
+        int so = 0;
         for (int j = 0; j < F; ++j) {
             seg_off[j] = so;
-            blk_off[j] = bo;
             cursor[j] = 0;
             so += seg_count[j];
-            bo += (seg_count[j] + rays_per_block - 1) / rays_per_block;
         }
         seg_off[F] = so;
-        blk_off[F] = bo;
     }
 }
 
+// after this kernel cursor[j] == number of rays in segment j: it doubles as the first chunk's count
 __global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const int *__restrict__ seg_off, int *cursor,
                                     int *__restrict__ list) {
     const int kpx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,15 +392,35 @@ __global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const 
     }
 }
 
+// before each triangle chunk: live-ray counts per light vertex -> ray-block offsets; reset the
+// survivors' counters and the work counter
+__global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block, int *blk_off, int *cnt_out, int *work) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int bo = 0;
+        for (int j = 0; j < F; ++j) {
+            blk_off[j] = bo;
+            cnt_out[j] = 0;
+            bo += (cnt_in[j] + rays_per_block - 1) / rays_per_block;
+        }
+        blk_off[F] = bo;
+        *work = 0;
+    }
+}
+
 // ---------------------------------------------------------------------------------
+// First in-order occluder, one triangle chunk [tile_lo, tile_hi) per launch.  Rays are
+// grouped by light vertex (segment j of the list, table j); rays that are still
+// unoccluded at the end of the chunk are compacted into list_out for the next chunk, so
+// the pairs actually swept track the reference's own early-exit count (main.cpp:324).
 struct ShadowParams {
     const float4 *tables; // tables of the current light's vertices, table j at + j*table_stride
     size_t table_stride;  // in float4
-    int n_tiles, n_tris, F, n_px;
+    int tile_lo, tile_hi, n_tris, F, n_px, is_last;
     const float *tri_verts;
     const float4 *spheres;
     int n_spheres;
-    const int *list, *seg_off, *blk_off;
+    const int *list_in, *seg_off, *cnt_in, *blk_off;
+    int *list_out, *cnt_out;
     PixelState px;
     sweep::Counters *counters;
     int *work;
@@ -429,9 +452,9 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         __syncthreads();
         const int blk = sm.blk, j = sm.seg;
         if (blk >= total_blocks) break;
-        const int seg_begin = p.seg_off[j], seg_end = p.seg_off[j + 1];
+        const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
-        float ex[R], ey[R], ez[R];
+        float2 ex[R], ey[R], ez[R];
         int kp[R];
         unsigned valid = 0;
 #pragma unroll
@@ -439,32 +462,63 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
             int e = base + r * sweep::THREADS + tid;
             if (e < seg_end) valid |= 1u << r;
             e = min(e, seg_end - 1);
-            const int k = p.list[e];
+            const int k = p.list_in[e];
             kp[r] = k;
-            ex[r] = p.px.re[k], ey[r] = p.px.re[n + k], ez[r] = p.px.re[2 * n + k];
+            const float fx = p.px.re[k], fy = p.px.re[n + k], fz = p.px.re[2 * n + k];
+            ex[r] = make_float2(fx, fx), ey[r] = make_float2(fy, fy), ez[r] = make_float2(fz, fz);
             sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
             sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
             sm.t[r][tid] = p.px.rt[k];
+            sm.v[r][tid] = 0.f;
             sm.tri[r][tid] = -1;
         }
         unsigned done = 0;
         unsigned swept = 0;
-        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, p.tables + (size_t)j * p.table_stride, p.n_tiles, p.n_tris, p.tri_verts, ex, ey,
-                                                ez, valid, done, gtile, n_strict, swept, n_miss);
+        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, p.tables + (size_t)j * p.table_stride, p.tile_lo, p.tile_hi, p.n_tris,
+                                                p.tri_verts, ex, ey, ez, valid, done, gtile, n_strict, swept, n_miss);
         tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
+        unsigned surv = valid & ~done;
+        // finished rays: publish occluder and the t it left behind
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (!((valid >> r) & 1u)) continue;
             float t = sm.t[r][tid];
             int tri = sm.tri[r][tid];
-            if (tri < 0 && p.n_spheres > 0) { // extension: spheres after all triangles, in order
+            if (tri < 0 && p.is_last && p.n_spheres > 0) { // extension: spheres after all triangles, in order
                 const f3 o = strict::mk(sm.ox[r][tid], sm.oy[r][tid], sm.oz[r][tid]);
                 const f3 d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
                 for (int s = 0; s < p.n_spheres && tri < 0; ++s)
                     if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
             }
-            p.px.occ[kp[r]] = tri;
-            p.px.rt[kp[r]] = t;
+            if (tri >= 0) {
+                p.px.occ[kp[r]] = tri;
+                p.px.rt[kp[r]] = t;
+            }
+        }
+        if (!p.is_last) { // compact the survivors of this block into the next chunk's list
+            const int mine = __popc(surv);
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += y;
+            }
+            if ((tid & 31) == 31) sm.scan[tid >> 5] = incl;
+            __syncthreads();
+            if (tid < 32) {
+                int w = tid < sweep::THREADS / 32 ? sm.scan[tid] : 0;
+                int wi = w;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (tid >= o) wi += y;
+                }
+                if (tid < sweep::THREADS / 32) sm.scan[tid] = wi - w; // exclusive warp offsets
+                if (tid == 31) sm.base_out = wi ? atomicAdd(&p.cnt_out[j], wi) : 0;
+            }
+            __syncthreads();
+            int pos = seg_begin + sm.base_out + sm.scan[tid >> 5] + (incl - mine);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if ((surv >> r) & 1u) p.list_out[pos++] = kp[r];
         }
         __syncthreads();
     }

@@ -15,7 +15,6 @@ extern "C" int tracer__mt19937_scan(uint32_t seed, int32_t n_lights, const int32
 
 namespace {
 
-constexpr int RAYS = 8; // rays per thread in the sweeps
 
 struct Ctx {
     bool inited = false;
@@ -69,11 +68,12 @@ struct tracer_scene_dev {
     double light_lmax = -1.0;
     // per-frame workspace
     int ws_npx = 0, ws_L = 0;
-    int *hit_tri = nullptr, *rj = nullptr, *occ = nullptr, *list = nullptr, *faceid = nullptr, *dbg_occ = nullptr;
+    int *hit_tri = nullptr, *rj = nullptr, *occ = nullptr, *list = nullptr, *list_b = nullptr, *faceid = nullptr,
+        *dbg_occ = nullptr;
     float *hit_t = nullptr, *hit_v = nullptr, *carry = nullptr, *nrm = nullptr, *accum = nullptr, *ro = nullptr,
           *rd = nullptr, *re = nullptr, *rt = nullptr;
     uint8_t *rgb8 = nullptr, *mask = nullptr;
-    int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *work = nullptr;
+    int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr;
     int maxF = 0;
     sweep::Counters *counters = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -86,7 +86,7 @@ namespace {
 int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
     const int L = std::max(1, s->n_lights);
     if (n_px > s->ws_npx) {
-        dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->faceid);
+        dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->list_b), dev_free(s->faceid);
         dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
         dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
         dev_free(s->dbg_occ);
@@ -94,6 +94,7 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
         const size_t n = (size_t)n_px;
         int rc = 0;
         rc |= dev_alloc(&s->hit_tri, n) | dev_alloc(&s->rj, n) | dev_alloc(&s->occ, n) | dev_alloc(&s->list, n);
+        rc |= dev_alloc(&s->list_b, n);
         rc |= dev_alloc(&s->faceid, n * L);
         rc |= dev_alloc(&s->hit_t, n) | dev_alloc(&s->hit_v, n) | dev_alloc(&s->carry, n);
         rc |= dev_alloc(&s->nrm, 3 * n) | dev_alloc(&s->accum, 3 * n + 16) | dev_alloc(&s->ro, 3 * n);
@@ -109,7 +110,7 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
 }
 
 template <int R, bool EX>
-int launch_primary(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem<R>);
     CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trk::primary_kernel<R, EX><<<grid, sweep::THREADS, smem, st>>>(p);
@@ -117,12 +118,30 @@ int launch_primary(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     return 0;
 }
 template <int R, bool EX>
-int launch_shadow(const trk::ShadowParams &p, int grid, cudaStream_t st) {
+int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem<R>);
     CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trk::shadow_kernel<R, EX><<<grid, sweep::THREADS, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
+}
+int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+    if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
+    if (R == 4) return ex ? launch_primary_t<4, true>(p, grid, st) : launch_primary_t<4, false>(p, grid, st);
+    return ex ? launch_primary_t<2, true>(p, grid, st) : launch_primary_t<2, false>(p, grid, st);
+}
+int launch_shadow(int R, bool ex, const trk::ShadowParams &p, int grid, cudaStream_t st) {
+    if (R == 8) return ex ? launch_shadow_t<8, true>(p, grid, st) : launch_shadow_t<8, false>(p, grid, st);
+    if (R == 4) return ex ? launch_shadow_t<4, true>(p, grid, st) : launch_shadow_t<4, false>(p, grid, st);
+    return ex ? launch_shadow_t<2, true>(p, grid, st) : launch_shadow_t<2, false>(p, grid, st);
+}
+
+// rays per thread: 8 when that still gives every SM several ray blocks, else 4 or 2
+int pick_rays(int64_t n_rays, int n_sms, int forced) {
+    if (forced == 2 || forced == 4 || forced == 8) return forced;
+    if (n_rays >= (int64_t)sweep::THREADS * 8 * n_sms * 4) return 8;
+    if (n_rays >= (int64_t)sweep::THREADS * 4 * n_sms * 2) return 4;
+    return 2;
 }
 
 int build_table(const tracer_scene_dev *s, const double o[3], double lmax, float4 *table, cudaStream_t st) {
@@ -183,7 +202,8 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->tri_verts), dev_free(s->tri_normals), dev_free(s->geom_material), dev_free(s->sphere_material);
     dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
     dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables);
-    dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->faceid), dev_free(s->dbg_occ);
+    dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->list_b), dev_free(s->faceid);
+    dev_free(s->dbg_occ), dev_free(s->cnt_b);
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
@@ -308,6 +328,7 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     TRY(dev_alloc(&s->seg_off, (size_t)s->maxF + 2));
     TRY(dev_alloc(&s->blk_off, (size_t)s->maxF + 2));
     TRY(dev_alloc(&s->cursor, (size_t)s->maxF + 1));
+    TRY(dev_alloc(&s->cnt_b, (size_t)s->maxF + 1));
     TRY(dev_alloc(&s->work, 1));
     TRY(dev_alloc(&s->counters, 1));
     for (auto &e : s->ev) TRY_CUDA(cudaEventCreate(&e));
@@ -379,7 +400,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(sweep::Counters), st));
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
 
-    const int rays_per_block = sweep::THREADS * RAYS;
+    const int R = pick_rays(n_px, g.n_sms, o.rays_per_thread);
+    const int rays_per_block = sweep::THREADS * R;
     const int n_tiles = s->n_pad / sweep::TILE;
     // ---- primary: raygen + closest hit ----------------------------------------------
     CK_CUDA(cudaEventRecord(s->ev[1], st));
@@ -390,8 +412,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.hit_tri = s->hit_tri, p.hit_t = s->hit_t, p.hit_v = s->hit_v, p.counters = s->counters, p.work = s->work;
         p.n_blocks = (n_px + rays_per_block - 1) / rays_per_block;
         const int grid = std::min(p.n_blocks, g.n_sms);
-        int rc = o.exhaustive_strict ? launch_primary<RAYS, true>(p, grid, st) : launch_primary<RAYS, false>(p, grid, st);
-        if (rc) return rc;
+        if (int rc = launch_primary(R, o.exhaustive_strict != 0, p, grid, st)) return rc;
         ++launches;
     }
     CK_CUDA(cudaEventRecord(s->ev[2], st));
@@ -437,24 +458,33 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         ++launches;
         if (k == L) break;
         const int F = s->h_light_F[k];
-        trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, rays_per_block, s->seg_off, s->blk_off, s->cursor);
+        trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
         CK_CUDA(cudaGetLastError());
         trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
         CK_CUDA(cudaGetLastError());
         launches += 2;
-        CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
-        trk::ShadowParams sp{};
-        sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * s->table_stride, sp.table_stride = s->table_stride;
-        sp.n_tiles = n_tiles, sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
-        sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;
-        sp.list = s->list, sp.seg_off = s->seg_off, sp.blk_off = s->blk_off, sp.px = px;
-        sp.counters = s->counters, sp.work = s->work;
-        const int max_blocks = (n_px + rays_per_block - 1) / rays_per_block + F;
-        const int grid = std::min(max_blocks, g.n_sms);
-        int rc = o.exhaustive_strict ? launch_shadow<RAYS, true>(sp, grid, st) : launch_shadow<RAYS, false>(sp, grid, st);
-        if (rc) return rc;
-        ++launches;
+        // triangle chunks: after each one the still-unoccluded rays are compacted (early exit, main.cpp:324)
+        int n_chunks = o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(64, n_tiles / 8));
+        n_chunks = std::min(n_chunks, n_tiles);
+        int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
+        for (int c = 0; c < n_chunks; ++c) {
+            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, rays_per_block, s->blk_off, cnt_out, s->work);
+            CK_CUDA(cudaGetLastError());
+            trk::ShadowParams sp{};
+            sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * s->table_stride, sp.table_stride = s->table_stride;
+            sp.tile_lo = (int)((int64_t)n_tiles * c / n_chunks), sp.tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
+            sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.is_last = (c == n_chunks - 1), sp.tri_verts = s->tri_verts;
+            sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;
+            sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off;
+            sp.list_out = list_out, sp.cnt_out = cnt_out, sp.px = px;
+            sp.counters = s->counters, sp.work = s->work;
+            const int max_blocks = (n_px + rays_per_block - 1) / rays_per_block + F;
+            const int grid = std::min(max_blocks, g.n_sms);
+            if (int rc = launch_shadow(R, o.exhaustive_strict != 0, sp, grid, st)) return rc;
+            launches += 2;
+            std::swap(list_in, list_out), std::swap(cnt_in, cnt_out);
+        }
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
     }
 

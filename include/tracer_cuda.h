@@ -109,6 +109,8 @@ typedef struct tracer_render_opts {
 
     int32_t exhaustive_strict; /* debug: bypass the conservative filter, strict-test every pair */
     int32_t samples_per_pixel; /* extension (parity unpinned): 0/1 = reference; n*n stratified jitter */
+    int32_t rays_per_thread;   /* tuning: 0 = auto, else 2, 4 or 8 rays per thread in the sweeps */
+    int32_t shadow_chunks;     /* tuning: 0 = auto; triangle chunks between shadow-ray compactions */
 
     /* optional debug outputs, HOST pointers, indexed like the output rows
      * (local pixel k = local_row*W + w), any may be NULL */
