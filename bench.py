@@ -255,11 +255,17 @@ def main():
         host_frame = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
 
         def e2e_step():
+            ta = time.perf_counter()
             r2 = renderer.upload(scene)  # host -> HBM every step
+            tb = time.perf_counter()
             fr, _ = tdist.render_frame(renderer, r2, cam, W, H, rank=rank, world=world, seed=seed)
+            tc = time.perf_counter()
             if rank == 0:
                 host_frame.copy_(fr, non_blocking=False)  # HBM -> host read of the result
+            td = time.perf_counter()
             r2.close()
+            if os.environ.get("BENCH_DEBUG") and rank == 0:
+                print(f"e2e_step: upload {tb-ta:.3f} render {tc-tb:.3f} readback {td-tc:.3f} close {time.perf_counter()-td:.3f}", file=sys.stderr)
 
         e2e_step()
         barrier()

@@ -84,8 +84,30 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
         const double eps = (double)TRC_EPS;
         const double K = (double)sweep::CK * eps * emax * reach;
         const double tau = (double)sweep::CK * eps * l1 * l2 * reach;
-        if (!(fabs(tprime) > tau)) { // side of the plane undefined (or NaN): always candidate
+        if (!(fabs(tprime) > tau)) {
+            // O lies within the noise of the triangle's plane: the side s is undefined.  A line through
+            // O can then only reach the (noise-dilated) triangle if it runs almost inside that plane:
+            // |d.n| <= (h + delta) / (rho - delta), with h the distance of O from the plane, rho a lower
+            // bound of the distance from O to the triangle and delta the positional noise scaled by the
+            // triangle's aspect.  Two of the three rows encode that slab (+n and -n), the third is
+            // always true.  When O is (nearly) ON the triangle — a light vertex against its own light's
+            // faces — the slab degenerates and the row is "always candidate": the strict path decides.
             rb = rc = rd = make_float4(0.f, 0.f, 0.f, 1.f);
+            const double area2 = sqrt(Nx * Nx + Ny * Ny + Nz * Nz);
+            if (area2 > 0.0 && emax > 0.0) {
+                const double shape = emax * emax / area2;
+                const double delta = 4.0 * (double)sweep::CK * eps * reach * shape;
+                const double rho = fmax(la, fmax(lb, lc)) - emax;
+                const double h = fabs(tprime) / area2;
+                if (rho > 4.0 * delta) {
+                    const double kappa = (h + delta) / (rho - delta) * 1.01 + 8.0 * eps;
+                    if (kappa < 1.0) {
+                        const float kf = (float)(kappa * 1.0000002) + 1e-37f;
+                        rb = make_float4((float)(Nx / area2), (float)(Ny / area2), (float)(Nz / area2), kf);
+                        rc = make_float4(-rb.x, -rb.y, -rb.z, kf);
+                    }
+                }
+            }
         } else {
             const double s = tprime > 0 ? 1.0 : -1.0;
             // round K up a little so the float row never under-states it

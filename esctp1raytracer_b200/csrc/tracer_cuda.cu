@@ -65,7 +65,7 @@ struct tracer_scene_dev {
     double bb_lo[3], bb_hi[3];
     float4 *eye_table = nullptr, *light_tables = nullptr;
     size_t table_stride = 0; // float4 per table
-    double light_lmax = -1.0;
+    std::vector<double> light_lmax; // per light: reach bound its vertex tables were built for
     // per-frame workspace
     int ws_npx = 0, ws_L = 0;
     int *hit_tri = nullptr, *rj = nullptr, *occ = nullptr, *list = nullptr, *list_b = nullptr, *faceid = nullptr,
@@ -382,12 +382,16 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lo[c] = std::min(s->bb_lo[c], (double)cam->origin[c]), hi[c] = std::max(s->bb_hi[c], (double)cam->origin[c]);
         if (hi[c] >= lo[c]) diag2 += (hi[c] - lo[c]) * (hi[c] - lo[c]);
     }
-    const double lmax_needed = (L + 1) * std::sqrt(diag2) * 1.001 + 1e-30;
-    if (L > 0 && (s->light_lmax < lmax_needed)) {
-        s->light_lmax = lmax_needed * 2.0; // head-room so that camera moves rarely trigger a rebuild
-        for (int j = 0; j < s->V; ++j) {
+    // shadow segments of light k are bounded by len_k <= (k+1) * diag: t carries over lights (main.cpp:764)
+    const double diag = std::sqrt(diag2) * 1.001 + 1e-30;
+    s->light_lmax.resize((size_t)L, -1.0);
+    for (int k = 0; k < L; ++k) {
+        const double need = (k + 1) * diag;
+        if (s->light_lmax[k] >= need) continue;
+        s->light_lmax[k] = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
+        for (int j = s->h_light_vbase[k]; j < s->h_light_vbase[k + 1]; ++j) {
             const double oo[3] = {s->h_light_verts[3 * j], s->h_light_verts[3 * j + 1], s->h_light_verts[3 * j + 2]};
-            if (int rc = build_table(s, oo, s->light_lmax, s->light_tables + (size_t)j * s->table_stride, st)) return rc;
+            if (int rc = build_table(s, oo, s->light_lmax[k], s->light_tables + (size_t)j * s->table_stride, st)) return rc;
             ++launches;
         }
     }
@@ -450,7 +454,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.tri_verts = s->tri_verts, lp.tri_normals = s->tri_normals, lp.tri_geom = s->tri_geom;
         lp.geom_has_normals = s->geom_has_normals, lp.geom_material = s->geom_material;
         lp.sphere_material = s->sphere_material, lp.spheres = s->spheres;
-        lp.rng_mode = o.rng_mode, lp.seed = o.seed, lp.faceid = s->faceid, lp.lmax = s->light_lmax;
+        lp.rng_mode = o.rng_mode, lp.seed = o.seed, lp.faceid = s->faceid, lp.lmax = k < L ? s->light_lmax[k] : 0.0;
         lp.seg_count = s->seg_count, lp.counters = s->counters, lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
         if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * (s->maxF + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
@@ -468,8 +472,19 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         int n_chunks = o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(64, n_tiles / 8));
         n_chunks = std::min(n_chunks, n_tiles);
         int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
+        std::vector<int> h_cnt((size_t)F);
         for (int c = 0; c < n_chunks; ++c) {
-            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, rays_per_block, s->blk_off, cnt_out, s->work);
+            // live rays per light vertex (a few ints): lets the host stop early and size the ray blocks
+            CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+            CK_CUDA(cudaStreamSynchronize(st));
+            int64_t n_live = 0;
+            for (int j = 0; j < F; ++j) n_live += h_cnt[j];
+            if (n_live == 0) break; // every shadow ray of this light already has its occluder
+            const int Rk = pick_rays(n_live, g.n_sms, o.rays_per_thread);
+            const int rpb = sweep::THREADS * Rk;
+            int max_blocks = 0;
+            for (int j = 0; j < F; ++j) max_blocks += (h_cnt[j] + rpb - 1) / rpb;
+            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, rpb, s->blk_off, cnt_out, s->work);
             CK_CUDA(cudaGetLastError());
             trk::ShadowParams sp{};
             sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * s->table_stride, sp.table_stride = s->table_stride;
@@ -479,9 +494,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off;
             sp.list_out = list_out, sp.cnt_out = cnt_out, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            const int max_blocks = (n_px + rays_per_block - 1) / rays_per_block + F;
             const int grid = std::min(max_blocks, g.n_sms);
-            if (int rc = launch_shadow(R, o.exhaustive_strict != 0, sp, grid, st)) return rc;
+            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, sp, grid, st)) return rc;
             launches += 2;
             std::swap(list_in, list_out), std::swap(cnt_in, cnt_out);
         }

@@ -54,6 +54,32 @@ def box_scene(specular=False) -> Scene:
     return Scene(np.array(off), np.array(verts, np.float32), np.array(mats), np.array([len(geoms) - 1]))
 
 
+def coplanar_scene(grid=12) -> Scene:
+    """Stress case for the filter's sign-ambiguous rows: box_scene plus (a) a grid of triangles lying
+    exactly in the light's plane (y = 1.98), some sharing the light's own vertices, and (b) a thin fin
+    whose plane passes exactly through the default eye (0, 1, 2.9)."""
+    base = box_scene()
+    tris = []
+    xs = np.linspace(-0.9, 0.9, grid + 1)
+    zs = np.linspace(-0.9, 0.9, grid + 1)
+    for i in range(grid):
+        for j in range(grid):
+            x0, x1, z0, z1 = xs[i], xs[i + 1], zs[j], zs[j + 1]
+            if x1 <= -0.3 or x0 >= 0.3 or z1 <= -0.3 or z0 >= 0.25:
+                tris += _quad((x0, 1.98, z0), (x1, 1.98, z0), (x1, 1.98, z1), (x0, 1.98, z1))
+    # triangles touching the light's corners, in its plane
+    tris.append([(-0.24, 1.98, -0.22), (-0.3, 1.98, -0.22), (-0.24, 1.98, -0.3)])
+    tris.append([(0.23, 1.98, 0.16), (0.3, 1.98, 0.16), (0.23, 1.98, 0.25)])
+    fin = [[(0.0, 0.2, 0.5), (0.0, 1.6, 0.5), (0.0, 0.9, -0.4)], [(0.0, 0.2, 0.5), (0.0, 0.9, -0.4), (0.0, 0.1, -0.4)]]
+    verts = np.concatenate([base.tri_verts[: base.geom_tri_offset[-2]], np.array(tris, np.float32), np.array(fin, np.float32),
+                            base.tri_verts[base.geom_tri_offset[-2]:]])
+    n0 = int(base.geom_tri_offset[-2])
+    off = list(base.geom_tri_offset[:-1]) + [n0 + len(tris), n0 + len(tris) + 2, n0 + len(tris) + 2 + 2]
+    mats = np.concatenate([base.geom_material[:-1], _mat(kd=(0.3, 0.3, 0.8))[None], _mat(kd=(0.8, 0.8, 0.2))[None],
+                           base.geom_material[-1:]])
+    return Scene(np.array(off), verts, mats, np.array([len(off) - 2]))
+
+
 def soup_scene(n_tris=1_000_000, n_geoms=1000, n_lights=4, n_spheres=0, seed=42, edge=(0.01, 0.02), specular=False,
                with_normals=False) -> Scene:
     """Triangle soup in the box [-1,1] x [0,2] x [-1,1] seen from (0,1,3) looking at (0,1,0).

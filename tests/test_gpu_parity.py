@@ -117,6 +117,39 @@ def test_soup_with_spheres_extension(renderer, restated):
     assert (o.tri >= s.n_tris).any()
 
 
+def test_coplanar_light_plane_and_eye_plane(renderer, restated):
+    """Triangles exactly in the light's plane / through the eye: the filter's sign-ambiguous rows
+    (slab rows and always-candidate rows) must not lose a single strict accept."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    s = scenes.coplanar_scene()
+    W, H, seed = 120, 90, 13
+    for eye in ((0, 1, 2.9), (0.4, 0.7, 2.5)):
+        cam = Camera.for_frame(eye, (0, 1, 0), W, H)
+        fid = hash_faceids(seed, W, H, s.faces_per_light)
+        o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=fid)
+        rs = renderer.upload(s)
+        out = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True)
+        _check_frame(out, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), False, occ=o.occ_tri)
+        ex = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True, exhaustive_strict=True)
+        assert ex.stats["filter_misses"] == 0
+        assert np.array_equal(ex.rgb8, out.rgb8)
+
+
+def test_soup_exhaustive_no_filter_misses(renderer):
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+
+    s = scenes.soup_scene(3000, 12, 4, seed=8, edge=(0.02, 0.3))
+    W, H = 64, 48
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True)
+    b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, exhaustive_strict=True)
+    assert b.stats["filter_misses"] == 0
+    assert np.array_equal(a.rgb8, b.rgb8) and np.array_equal(a.occ_tri, b.occ_tri) and np.array_equal(a.tri, b.tri)
+    assert a.stats["strict_evals"] < b.stats["strict_evals"] / 20
+
+
 def test_large_triangle_count_subset(renderer, restated):
     """200k triangles at 256x144 on the GPU; the oracle checks a random pixel subset."""
     from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes

@@ -1,0 +1,207 @@
+// sweep_mb.cu — development microbenchmark of the sweep's inner loop (no TMA, no strict path):
+// the tile sits in shared memory and is swept repeatedly, so only the issue/pipe behaviour of
+// each formulation is measured.  Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a
+//        -lineinfo tools/sweep_mb.cu -o tools/sweep_mb.bin ; run on the GPU box.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <vector>
+
+constexpr int TILE = 256;
+
+__device__ __forceinline__ float2 edge_min_tp(const float4 *q, float2 ex, float2 ey, float2 ez) {
+    const float2 X = __ffma2_rn(ex, make_float2(q[0].x, q[0].y),
+                                __ffma2_rn(ey, make_float2(q[0].z, q[0].w), __ffma2_rn(ez, make_float2(q[1].x, q[1].y), make_float2(q[1].z, q[1].w))));
+    const float2 Y = __ffma2_rn(ex, make_float2(q[2].x, q[2].y),
+                                __ffma2_rn(ey, make_float2(q[2].z, q[2].w), __ffma2_rn(ez, make_float2(q[3].x, q[3].y), make_float2(q[3].z, q[3].w))));
+    const float2 Z = __ffma2_rn(ex, make_float2(q[4].x, q[4].y),
+                                __ffma2_rn(ey, make_float2(q[4].z, q[4].w), __ffma2_rn(ez, make_float2(q[5].x, q[5].y), make_float2(q[5].z, q[5].w))));
+    return make_float2(fminf(fminf(X.x, Y.x), Z.x), fminf(fminf(X.y, Y.y), Z.y));
+}
+
+// V0: triangle-pair FFMA2, ray direction broadcast (production v2)
+template <int R, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_tripair(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE / 2 * 6];
+    for (int i = threadIdx.x; i < TILE / 2 * 6; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float2 ex[R], ey[R], ez[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3), c = -1.f;
+        ex[r] = make_float2(a, a), ey[r] = make_float2(b, b), ez[r] = make_float2(c, c);
+    }
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll UNROLL
+        for (int pi = 0; pi < TILE / 2; ++pi) {
+            float4 q[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) q[j] = tile[6 * pi + j];
+            float M = -1.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float2 m = edge_min_tp(q, ex[r], ey[r], ez[r]);
+                M = fmaxf(fmaxf(M, m.x), m.y);
+            }
+            if (M >= 0.f) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+// V1: ray-pair FFMA2: coefficients broadcast, two rays per packed lane
+template <int R2, int UNROLL>  // R2 = ray pairs per thread
+__global__ void __launch_bounds__(512, 1) k_raypair(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE * 3];
+    for (int i = threadIdx.x; i < TILE * 3; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float2 ex[R2], ey[R2], ez[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3);
+        ex[r] = make_float2(a, a * 1.01f), ey[r] = make_float2(b, b * 0.99f), ez[r] = make_float2(-1.f, -1.01f);
+    }
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll UNROLL
+        for (int i = 0; i < TILE; ++i) {
+            const float4 rb = tile[3 * i], rc = tile[3 * i + 1], rd = tile[3 * i + 2];
+            float M = -1.f;
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                const float2 X = __ffma2_rn(ex[r], make_float2(rb.x, rb.x), __ffma2_rn(ey[r], make_float2(rb.y, rb.y), __ffma2_rn(ez[r], make_float2(rb.z, rb.z), make_float2(rb.w, rb.w))));
+                const float2 Y = __ffma2_rn(ex[r], make_float2(rc.x, rc.x), __ffma2_rn(ey[r], make_float2(rc.y, rc.y), __ffma2_rn(ez[r], make_float2(rc.z, rc.z), make_float2(rc.w, rc.w))));
+                const float2 Z = __ffma2_rn(ex[r], make_float2(rd.x, rd.x), __ffma2_rn(ey[r], make_float2(rd.y, rd.y), __ffma2_rn(ez[r], make_float2(rd.z, rd.z), make_float2(rd.w, rd.w))));
+                M = fmaxf(fmaxf(M, fminf(fminf(X.x, Y.x), Z.x)), fminf(fminf(X.y, Y.y), Z.y));
+            }
+            if (M >= 0.f) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+// V2: scalar FFMA (v1 formulation)
+template <int R, int UNROLL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_scalar(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE * 3];
+    for (int i = threadIdx.x; i < TILE * 3; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float ex[R], ey[R], ez[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ex[r] = seed * (threadIdx.x + 1) * (r + 1), ey[r] = seed * (threadIdx.x + 7) * (r + 3), ez[r] = -1.f;
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll UNROLL
+        for (int i = 0; i < TILE; ++i) {
+            const float4 rb = tile[3 * i], rc = tile[3 * i + 1], rd = tile[3 * i + 2];
+            float M = -1.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float x = fmaf(ex[r], rb.x, fmaf(ey[r], rb.y, fmaf(ez[r], rb.z, rb.w)));
+                const float y = fmaf(ex[r], rc.x, fmaf(ey[r], rc.y, fmaf(ez[r], rc.z, rc.w)));
+                const float z = fmaf(ex[r], rd.x, fmaf(ey[r], rd.y, fmaf(ez[r], rd.z, rd.w)));
+                M = fmaxf(M, fminf(fminf(x, y), z));
+            }
+            if (M >= 0.f) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+// V3: triangle-pair FFMA2 but sign test through integer OR instead of FMNMX (LOP3 on the ALU pipe)
+template <int R, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_tripair_lop(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE / 2 * 6];
+    for (int i = threadIdx.x; i < TILE / 2 * 6; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float2 ex[R], ey[R], ez[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3), c = -1.f;
+        ex[r] = make_float2(a, a), ey[r] = make_float2(b, b), ez[r] = make_float2(c, c);
+    }
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll UNROLL
+        for (int pi = 0; pi < TILE / 2; ++pi) {
+            float4 q[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) q[j] = tile[6 * pi + j];
+            unsigned A = 0xffffffffu; // sign bit of A stays set unless some ray has all three >= 0 for some triangle
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float2 X = __ffma2_rn(ex[r], make_float2(q[0].x, q[0].y), __ffma2_rn(ey[r], make_float2(q[0].z, q[0].w), __ffma2_rn(ez[r], make_float2(q[1].x, q[1].y), make_float2(q[1].z, q[1].w))));
+                const float2 Y = __ffma2_rn(ex[r], make_float2(q[2].x, q[2].y), __ffma2_rn(ey[r], make_float2(q[2].z, q[2].w), __ffma2_rn(ez[r], make_float2(q[3].x, q[3].y), make_float2(q[3].z, q[3].w))));
+                const float2 Z = __ffma2_rn(ex[r], make_float2(q[4].x, q[4].y), __ffma2_rn(ey[r], make_float2(q[4].z, q[4].w), __ffma2_rn(ez[r], make_float2(q[5].x, q[5].y), make_float2(q[5].z, q[5].w))));
+                const unsigned s0 = __float_as_uint(X.x) | __float_as_uint(Y.x) | __float_as_uint(Z.x);
+                const unsigned s1 = __float_as_uint(X.y) | __float_as_uint(Y.y) | __float_as_uint(Z.y);
+                A &= s0 & s1;
+            }
+            if ((int)A >= 0) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+template <typename F>
+double run(const char *name, F launch, double pairs_per_launch) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) launch();
+    cudaEventRecord(e0);
+    const int iters = 5;
+    for (int i = 0; i < iters; ++i) launch();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaError_t err = cudaGetLastError();
+    const double tf = 18.0 * pairs_per_launch * iters / (ms * 1e-3) / 1e12;
+    printf("%-34s %8.3f ms/launch  %7.2f TFLOP/s-equiv  %s\n", name, ms / iters, tf, err == cudaSuccess ? "" : cudaGetErrorString(err));
+    return tf;
+}
+
+int main() {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    std::vector<float> h(TILE * 12);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = -0.5f - 0.001f * (float)(i % 97); // never a candidate
+    float4 *tile_g;
+    float *out;
+    cudaMalloc(&tile_g, h.size() * 4);
+    cudaMemcpy(tile_g, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    cudaMalloc(&out, 64);
+    const int reps = 400;
+    const float seed = 1e-3f;
+#define PAIRS(threads, R) ((double)sms * (threads) * (R) * TILE * reps)
+    run("tripair R=4 u2 512thr", [&] { k_tripair<4, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("tripair R=8 u2 512thr", [&] { k_tripair<8, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("tripair R=8 u1 512thr", [&] { k_tripair<8, 1><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("tripair R=8 u4 512thr", [&] { k_tripair<8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("tripair R=6 u2 512thr", [&] { k_tripair<6, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 6));
+    run("tripair R=8 u2 256thr", [&] { k_tripair<8, 2><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
+    run("tripair R=8 u2 384thr", [&] { k_tripair<8, 2><<<sms, 384>>>(tile_g, reps, out, seed); }, PAIRS(384, 8));
+    run("tripair-lop R=8 u2 512thr", [&] { k_tripair_lop<8, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("tripair-lop R=4 u2 512thr", [&] { k_tripair_lop<4, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("raypair R=8 (4 pairs) u2", [&] { k_raypair<4, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("raypair R=8 (4 pairs) u4", [&] { k_raypair<4, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("raypair R=4 (2 pairs) u4", [&] { k_raypair<2, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("raypair R=16 (8 pairs) u2", [&] { k_raypair<8, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 16));
+    run("scalar R=8 u2 512thr", [&] { k_scalar<8, 2, 512><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("scalar R=8 u4 256thr", [&] { k_scalar<8, 4, 256><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
+    run("scalar R=4 u4 512thr", [&] { k_scalar<4, 4, 512><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    return 0;
+}
