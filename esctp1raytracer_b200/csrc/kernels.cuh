@@ -117,16 +117,9 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
             rd = make_float4((float)(s * Dx), (float)(s * Dy), (float)(s * Dz), Kf);
         }
     }
-    // pair-interleaved record (sweep.cuh: edge_min): triangle i is slot i&1 of record i>>1
-    float *rec = reinterpret_cast<float *>(table) + (size_t)(i >> 1) * 24 + (i & 1);
-    const float4 rows[3] = {rb, rc, rd};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        rec[8 * r + 0] = rows[r].x;
-        rec[8 * r + 2] = rows[r].y;
-        rec[8 * r + 4] = rows[r].z;
-        rec[8 * r + 6] = rows[r].w;
-    }
+    table[3 * (size_t)i] = rb;
+    table[3 * (size_t)i + 1] = rc;
+    table[3 * (size_t)i + 2] = rd;
 }
 
 // ---------------------------------------------------------------------------------
@@ -163,7 +156,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         const int blk = sm.blk;
         if (blk >= p.n_blocks) break;
         const int base = blk * (sweep::THREADS * R);
-        float2 ex[R], ey[R], ez[R];
+        float ex[R], ey[R], ez[R];
         unsigned valid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -173,7 +166,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             int w, h;
             p.bands.map(k, w, h);
             const f3 d = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
-            ex[r] = make_float2(d.x, d.x), ey[r] = make_float2(d.y, d.y), ez[r] = make_float2(d.z, d.z);
+            ex[r] = d.x, ey[r] = d.y, ez[r] = d.z;
             sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
             sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
             sm.t[r][tid] = FLT_MAX; // main.cpp:715-717
@@ -192,7 +185,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             int tri = sm.tri[r][tid];
             if (p.n_spheres > 0) {
                 const f3 o = strict::ld(p.cam.o);
-                const f3 d = strict::mk(ex[r].x, ey[r].x, ez[r].x);
+                const f3 d = strict::mk(ex[r], ey[r], ez[r]);
                 for (int s = 0; s < p.n_spheres; ++s)
                     if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
             }
@@ -476,7 +469,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         if (blk >= total_blocks) break;
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
-        float2 ex[R], ey[R], ez[R];
+        float ex[R], ey[R], ez[R];
         int kp[R];
         unsigned valid = 0;
 #pragma unroll
@@ -486,8 +479,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
             e = min(e, seg_end - 1);
             const int k = p.list_in[e];
             kp[r] = k;
-            const float fx = p.px.re[k], fy = p.px.re[n + k], fz = p.px.re[2 * n + k];
-            ex[r] = make_float2(fx, fx), ey[r] = make_float2(fy, fy), ez[r] = make_float2(fz, fz);
+            ex[r] = p.px.re[k], ey[r] = p.px.re[n + k], ez[r] = p.px.re[2 * n + k];
             sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
             sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
             sm.t[r][tid] = p.px.rt[k];

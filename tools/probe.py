@@ -23,7 +23,8 @@ if argv:
     cases = [tuple(int(x) for x in a.split(",")) for a in argv]
 for n, W, H, L in cases:
     s = scenes.soup_scene(n, max(10, n // 1000), L, seed=42)
-    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    look = (0, 1, 6) if os.environ.get('PROBE_AWAY') else (0, 1, 0)
+    cam = Camera.for_frame((0, 1, 3), look, W, H)
     rs = r.upload(s)
     for it in range(3):
         t0 = time.time()

@@ -2,6 +2,8 @@
 // the tile sits in shared memory and is swept repeatedly, so only the issue/pipe behaviour of
 // each formulation is measured.  Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a
 //        -lineinfo tools/sweep_mb.cu -o tools/sweep_mb.bin ; run on the GPU box.
+#define SWEEP_NO_STRICT
+#include "../esctp1raytracer_b200/csrc/sweep.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(512, 1) k_tripair(const float4 *tile_g, int re
     float2 ex[R], ey[R], ez[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3), c = -1.f;
+        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3), c = -1.f - seed * r;
         ex[r] = make_float2(a, a), ey[r] = make_float2(b, b), ez[r] = make_float2(c, c);
     }
     int hits = 0;
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(512, 1) k_raypair(const float4 *tile_g, int re
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
         const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3);
-        ex[r] = make_float2(a, a * 1.01f), ey[r] = make_float2(b, b * 0.99f), ez[r] = make_float2(-1.f, -1.01f);
+        ex[r] = make_float2(a, a * 1.01f), ey[r] = make_float2(b, b * 0.99f), ez[r] = make_float2(-1.f - seed * r, -1.01f);
     }
     int hits = 0;
     for (int rep = 0; rep < reps; ++rep) {
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_scalar(const float4 *tile_g, int
     __syncthreads();
     float ex[R], ey[R], ez[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) ex[r] = seed * (threadIdx.x + 1) * (r + 1), ey[r] = seed * (threadIdx.x + 7) * (r + 3), ez[r] = -1.f;
+    for (int r = 0; r < R; ++r) ex[r] = seed * (threadIdx.x + 1) * (r + 1), ey[r] = seed * (threadIdx.x + 7) * (r + 3), ez[r] = -1.f - seed * r;
     int hits = 0;
     for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll UNROLL
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(512, 1) k_tripair_lop(const float4 *tile_g, in
     float2 ex[R], ey[R], ez[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3), c = -1.f;
+        const float a = seed * (threadIdx.x + 1) * (r + 1), b = seed * (threadIdx.x + 7) * (r + 3), c = -1.f - seed * r;
         ex[r] = make_float2(a, a), ey[r] = make_float2(b, b), ez[r] = make_float2(c, c);
     }
     int hits = 0;
@@ -154,6 +156,81 @@ __global__ void __launch_bounds__(512, 1) k_tripair_lop(const float4 *tile_g, in
         }
     }
     if (hits == 123456789) out[0] = hits;
+}
+
+// V4: triangle-pair layout, NF2 of the three rows as packed FFMA2 and the rest as scalar FFMA;
+//     per-pair branch replaced by a sign-bit shift register tested once per batch of BATCH pairs.
+template <int R, int NF2, int BATCH, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_mixed(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE / 2 * 6];
+    for (int i = threadIdx.x; i < TILE / 2 * 6; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float ex[R], ey[R], ez[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ex[r] = seed * (threadIdx.x + 1) * (r + 1), ey[r] = seed * (threadIdx.x + 7) * (r + 3), ez[r] = -1.f - seed * r;
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TILE / 2; b += BATCH) {
+            unsigned neg = 0xffffffffu;
+#pragma unroll UNROLL
+            for (int k = 0; k < BATCH; ++k) {
+                const float4 *q = &tile[6 * (b + k)];
+                float M = -1.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float m0[3], m1[3];
+#pragma unroll
+                    for (int row = 0; row < 3; ++row) {
+                        const float4 qa = q[2 * row], qb = q[2 * row + 1];
+                        if (row < NF2) {
+                            const float2 X = __ffma2_rn(make_float2(ex[r], ex[r]), make_float2(qa.x, qa.y),
+                                                        __ffma2_rn(make_float2(ey[r], ey[r]), make_float2(qa.z, qa.w),
+                                                                   __ffma2_rn(make_float2(ez[r], ez[r]), make_float2(qb.x, qb.y), make_float2(qb.z, qb.w))));
+                            m0[row] = X.x, m1[row] = X.y;
+                        } else {
+                            m0[row] = fmaf(ex[r], qa.x, fmaf(ey[r], qa.z, fmaf(ez[r], qb.x, qb.z)));
+                            m1[row] = fmaf(ex[r], qa.y, fmaf(ey[r], qa.w, fmaf(ez[r], qb.y, qb.w)));
+                        }
+                    }
+                    M = fmaxf(fmaxf(M, fminf(fminf(m0[0], m0[1]), m0[2])), fminf(fminf(m1[0], m1[1]), m1[2]));
+                }
+                neg = __funnelshift_l(__float_as_uint(M), neg, 1); // shift in the sign bit: 0 = candidate
+            }
+            if (~neg & ((BATCH >= 32) ? 0xffffffffu : ((1u << BATCH) - 1u))) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+// VP: the production data path (TMA tile stream + mbarrier + per-tile barrier) without the strict path
+template <int R>
+__global__ void __launch_bounds__(sweep::THREADS, 1) k_prod(const float4 *table, int n_tiles, int n_blocks, int *work, float *out, float seed) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        sweep::fence_barrier_init();
+    }
+    __syncthreads();
+    unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0;
+    for (;;) {
+        if (tid == 0) sm.blk = atomicAdd(work, 1);
+        __syncthreads();
+        const int blk = sm.blk;
+        if (blk >= n_blocks) break;
+        float ex[R], ey[R], ez[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ex[r] = seed * (tid + 1) * (r + 1 + blk), ey[r] = seed * (tid + 7) * (r + 3), ez[r] = -1.f - seed * r;
+        unsigned done = 0;
+        sweep::sweep_table<R, false, false>(sm, table, 0, n_tiles, n_tiles * 256, nullptr, ex, ey, ez, 0xffu >> (8 - R), done, gtile,
+                                            n_strict, n_swept, n_miss);
+        __syncthreads();
+    }
+    if (n_strict == 123456789u) out[0] = n_strict;
 }
 
 template <typename F>
@@ -203,5 +280,40 @@ int main() {
     run("scalar R=8 u2 512thr", [&] { k_scalar<8, 2, 512><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
     run("scalar R=8 u4 256thr", [&] { k_scalar<8, 4, 256><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
     run("scalar R=4 u4 512thr", [&] { k_scalar<4, 4, 512><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("mixed R=8 NF2=3 batch8 u4", [&] { k_mixed<8, 3, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("mixed R=8 NF2=3 batch16 u4", [&] { k_mixed<8, 3, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("mixed R=8 NF2=3 batch8 u8", [&] { k_mixed<8, 3, 8, 8><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("mixed R=8 NF2=2 batch8 u4", [&] { k_mixed<8, 2, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("mixed R=8 NF2=1 batch8 u4", [&] { k_mixed<8, 1, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("mixed R=8 NF2=0 batch8 u4", [&] { k_mixed<8, 0, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("mixed R=4 NF2=3 batch8 u4", [&] { k_mixed<4, 3, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("mixed R=4 NF2=2 batch8 u4", [&] { k_mixed<4, 2, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("mixed R=4 NF2=1 batch8 u4", [&] { k_mixed<4, 1, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("mixed R=4 NF2=1 batch8 u8", [&] { k_mixed<4, 1, 8, 8><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("mixed R=6 NF2=1 batch8 u4", [&] { k_mixed<6, 1, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 6));
+    run("mixed R=6 NF2=2 batch8 u4", [&] { k_mixed<6, 2, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 6));
+    {   // production data path
+        const int n_tiles = 400;
+        std::vector<float> ht((size_t)n_tiles * TILE * 12, 0.f);
+        for (size_t i = 0; i < ht.size(); ++i) ht[i] = ((i % 4) == 3) ? -1.f : 0.001f * (float)(i % 89); // K = -1: never candidate
+        float4 *table;
+        int *work;
+        cudaMalloc(&table, ht.size() * 4);
+        cudaMemcpy(table, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+        cudaMalloc(&work, 4);
+        auto prod = [&](auto kern, int R, int blocks_per_sm) {
+            const size_t smem = R == 8 ? sizeof(sweep::Smem<8>) : R == 4 ? sizeof(sweep::Smem<4>) : sizeof(sweep::Smem<2>);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const int n_blocks = sms * blocks_per_sm;
+            char name[64];
+            snprintf(name, sizeof name, "PROD path R=%d blocks/SM=%d", R, blocks_per_sm);
+            run(name, [&] { cudaMemset(work, 0, 4); kern<<<sms, sweep::THREADS, smem>>>(table, n_tiles, n_blocks, work, out, seed); },
+                (double)n_blocks * sweep::THREADS * R * TILE * n_tiles);
+        };
+        prod(k_prod<4>, 4, 1);
+        prod(k_prod<8>, 8, 1);
+        prod(k_prod<4>, 4, 4);
+        prod(k_prod<2>, 2, 2);
+    }
     return 0;
 }
