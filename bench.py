@@ -12,7 +12,7 @@ synthetic 1M-triangle + 1k-sphere scene at 3840x2160, 4 lights ("c4").  Other wo
 `value`  : scene resident in HBM, frame left in HBM on rank 0 (CUDA events, max over ranks).
 `e2e`    : the drop-in C-ABI call with HOST buffers each step — scene upload (pinned host ->
            HBM), render, gather, device -> host read of the packed frame.
-`roofline`: FP32-FMA bound (no tensor cores on this path).  achieved = 18 flop (9 FFMA per
+`roofline`: FP32-FMA bound (no tensor cores on this path).  achieved = 12 flop (6 FFMA per
            ray-triangle pair, the filter formulation the kernels execute) x ALGORITHMIC pairs
            (P*N primary + the reference's own in-order count for shadow rays) / sweep-kernel
            time; peak = our own FFMA microbenchmark measured in the same process
@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_PAIR = 18.0      # 9 FFMA: what the sweep executes per (ray, triangle) pair
+FLOP_PER_PAIR = 12.0      # 6 FFMA (2-D affine edge rows): what the sweep executes per (ray, triangle) pair
 FLOP_PER_PAIR_REF = 46.0  # Moller-Trumbore with precomputed edges, reported beside it
 EYE, LOOK = (0.0, 1.0, 3.0), (0.0, 1.0, 0.0)
 
@@ -311,7 +311,7 @@ def main():
                 "swept_pairs_per_step": swept_pairs / args.steps, "sweep_ms_per_step": sweep_ms_max / args.steps,
                 "executed_tflops": FLOP_PER_PAIR * swept_pairs / world / sweep_s / 1e12,
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / world / sweep_s / 1e12,
-                "ceiling_note": "9 FFMA + ~3.6 other issue slots per pair: FP32-pipe share of issue <= ~0.78",
+                "ceiling_note": "6 FFMA + 1.5 LOP3 (~2 issue slots) + 0.5 LDS/SHF per pair: FP32-pipe share of issue <= ~0.70; measured loop ceiling 0.58 of nominal (tools/sweep_mb.cu)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
                         "streams": "filter tables (48 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
             },

@@ -55,13 +55,30 @@ __device__ __forceinline__ f3 primary_dir(const Cam &c, int W, int H, int w, int
 // If O is within the same noise of the triangle's plane the side s is undefined
 // (e.g. a light vertex against its own light's faces): the row is made
 // "always candidate" and the pair is always decided by the strict path.
-__global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tris, int n_pad, double ox, double oy,
-                                   double oz, double lmax, float4 *__restrict__ table) {
+//
+// Direction parametrisation of the ray group this table serves: d' = p*U + q*V + W with
+// |d'| <= dmax.  A 3-D row (vec, K) valid for unit directions becomes the affine 2-D row
+// (U.vec, V.vec, W.vec + K*dmax): d'.vec + K|d'| >= 0 is relaxed to d'.vec + K*dmax >= 0.
+struct TableParam {
+    double o[3], U[3], V[3], W[3], dmax, lmax;
+};
+
+__device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K) {
+    const double A = tp.U[0] * vx + tp.U[1] * vy + tp.U[2] * vz;
+    const double B = tp.V[0] * vx + tp.V[1] * vy + tp.V[2] * vz;
+    const double C = tp.W[0] * vx + tp.W[1] * vy + tp.W[2] * vz + K * tp.dmax * 1.0001;
+    // + 0.0f: a stored -0 would make the sign-bit test treat an exact zero as negative
+    return make_float4((float)A, (float)B, (float)C + 0.0f, 0.f);
+}
+
+__global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tris, int n_pad, const TableParam tp,
+                                   float4 *__restrict__ table) {
+    const double ox = tp.o[0], oy = tp.o[1], oz = tp.o[2], lmax = tp.lmax;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     float4 rb, rc, rd;
     if (i >= n_tris) { // padding rows: never candidate
-        rb = rc = rd = make_float4(0.f, 0.f, 0.f, -1.f);
+        rb = rc = rd = make_float4(0.f, 0.f, -1.f, 0.f);
     } else {
         const float *p = tri_verts + 9 * (size_t)i;
         const double v0x = p[0], v0y = p[1], v0z = p[2];
@@ -92,7 +109,7 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
             // triangle's aspect.  Two of the three rows encode that slab (+n and -n), the third is
             // always true.  When O is (nearly) ON the triangle — a light vertex against its own light's
             // faces — the slab degenerates and the row is "always candidate": the strict path decides.
-            rb = rc = rd = make_float4(0.f, 0.f, 0.f, 1.f);
+            rb = rc = rd = make_float4(0.f, 0.f, 1.f, 0.f);
             const double area2 = sqrt(Nx * Nx + Ny * Ny + Nz * Nz);
             if (area2 > 0.0 && emax > 0.0) {
                 const double shape = emax * emax / area2;
@@ -102,24 +119,31 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
                 if (rho > 4.0 * delta) {
                     const double kappa = (h + delta) / (rho - delta) * 1.01 + 8.0 * eps;
                     if (kappa < 1.0) {
-                        const float kf = (float)(kappa * 1.0000002) + 1e-37f;
-                        rb = make_float4((float)(Nx / area2), (float)(Ny / area2), (float)(Nz / area2), kf);
-                        rc = make_float4(-rb.x, -rb.y, -rb.z, kf);
+                        rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37);
+                        rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37);
                     }
                 }
             }
         } else {
             const double s = tprime > 0 ? 1.0 : -1.0;
             // round K up a little so the float row never under-states it
-            const float Kf = (float)(K * 1.0000002) + 1e-37f;
-            rb = make_float4((float)(s * Bx), (float)(s * By), (float)(s * Bz), Kf);
-            rc = make_float4((float)(s * Cx), (float)(s * Cy), (float)(s * Cz), Kf);
-            rd = make_float4((float)(s * Dx), (float)(s * Dy), (float)(s * Dz), Kf);
+            const double Kd = K * 1.0000002 + 1e-37;
+            rb = project_row(tp, s * Bx, s * By, s * Bz, Kd);
+            rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd);
+            rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd);
         }
     }
     table[3 * (size_t)i] = rb;
     table[3 * (size_t)i + 1] = rc;
     table[3 * (size_t)i + 2] = rd;
+}
+
+// every row a candidate: the group of rays whose assumptions failed (never observed in practice)
+__global__ void build_allcand_table(int n_tris, int n_pad, float4 *__restrict__ table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const float4 r = make_float4(0.f, 0.f, i < n_tris ? 1.f : -1.f, 0.f);
+    table[3 * (size_t)i] = table[3 * (size_t)i + 1] = table[3 * (size_t)i + 2] = r;
 }
 
 // ---------------------------------------------------------------------------------
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         const int blk = sm.blk;
         if (blk >= p.n_blocks) break;
         const int base = blk * (sweep::THREADS * R);
-        float ex[R], ey[R], ez[R];
+        float rp[R], rq[R];
         unsigned valid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -166,7 +190,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             int w, h;
             p.bands.map(k, w, h);
             const f3 d = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
-            ex[r] = d.x, ey[r] = d.y, ez[r] = d.z;
+            // filter parameters: the reference's own (s,t) on the image plane (main.cpp:709-710)
+            rp[r] = __fdiv_rn((float)w, (float)(p.bands.W - 1)), rq[r] = __fdiv_rn((float)h, (float)(p.bands.H - 1));
             sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
             sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
             sm.t[r][tid] = FLT_MAX; // main.cpp:715-717
@@ -174,8 +199,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             sm.tri[r][tid] = -1;
         }
         unsigned done = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, 0, p.n_tiles, p.n_tris, p.tri_verts, ex, ey, ez, valid, done,
-                                                 gtile, n_strict, n_swept, n_miss);
+        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, 0, p.n_tiles, p.n_tris, p.tri_verts, rp, rq, valid, done, gtile,
+                                                 n_strict, n_swept, n_miss);
         tests += (unsigned long long)__popc(valid) * p.n_tris;
         // extension: analytic spheres after all triangles, strict, in order
 #pragma unroll
@@ -185,7 +210,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             int tri = sm.tri[r][tid];
             if (p.n_spheres > 0) {
                 const f3 o = strict::ld(p.cam.o);
-                const f3 d = strict::mk(ex[r], ey[r], ez[r]);
+                const f3 d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
                 for (int s = 0; s < p.n_spheres; ++s)
                     if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
             }
@@ -204,6 +229,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
 }
 
 // ---------------------------------------------------------------------------------
+constexpr int NFACE = 7; // ray groups per light vertex: 6 cube faces + 1 "all candidates"
+
 struct LightInfo {              // device arrays describing the lights
     const int *light_vbase;     // [L+1] prefix sum of F_l: index of light l's first vertex/table
     const float *light_verts;   // [V*3] light.vertex[faceID] positions (main.cpp:749)
@@ -215,9 +242,10 @@ struct PixelState {
     float *carry_t;       // the `t` variable of scan_row across lights (main.cpp:715, 764, occlusion's t2)
     float *nrm;           // [3][n_px]
     float *accum;         // [3][n_px]
-    float *ro, *rd, *re;  // [3][n_px] shadow ray origin, strict unit dir, filter dir
+    float *ro, *rd;       // [3][n_px] shadow ray origin, strict unit dir
+    float *re;            // [2][n_px] filter parameters (p,q) on the ray's cube face
     float *rt;            // [n_px] tmax in, t after occlusion() out
-    int *rj;              // [n_px] light-vertex slot within the current light, -1 none
+    int *rj;              // [n_px] ray group within the current light: faceID*NFACE + cube face, -1 none
     int *occ;             // [n_px] first in-order occluder, -1 none
 };
 
@@ -349,18 +377,23 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
                 p.px.ro[kpx] = hit.x, p.px.ro[n + kpx] = hit.y, p.px.ro[2 * n + kpx] = hit.z;
                 p.px.rd[kpx] = Lv.x, p.px.rd[n + kpx] = Lv.y, p.px.rd[2 * n + kpx] = Lv.z;
                 p.px.rt[kpx] = t;
-                // filter direction: the line through the light vertex, pointing at the hit point.
-                // A ray longer than the table's reach bound (never expected) or a degenerate one
-                // gets the zero direction: every row is then a candidate and the strict path decides.
-                float fx = hit.x - v0.x, fy = hit.y - v0.y, fz = hit.z - v0.z;
-                const float l2 = fx * fx + fy * fy + fz * fz;
-                const float inv = rsqrtf(l2);
-                const bool ok = (l2 > 0.f) && ((double)len <= p.lmax) && isfinite(inv);
-                fx = ok ? fx * inv : 0.f, fy = ok ? fy * inv : 0.f, fz = ok ? fz * inv : 0.f;
-                p.px.re[kpx] = fx, p.px.re[n + kpx] = fy, p.px.re[2 * n + kpx] = fz;
-                p.px.rj[kpx] = fid;
+                // filter parameters: the line through the light vertex towards the hit point, on the cube
+                // face of its dominant axis: (p,q) = (d_a, d_b)/|d_c|.  A ray longer than the table's reach
+                // bound (never expected) or a degenerate one goes to the "all candidates" group instead.
+                const float fd[3] = {hit.x - v0.x, hit.y - v0.y, hit.z - v0.z};
+                const float ax = fabsf(fd[0]), ay = fabsf(fd[1]), az = fabsf(fd[2]);
+                const int c = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+                const float dc = fd[c];
+                const float inv = 1.0f / fabsf(dc);
+                const bool ok = (fabsf(dc) > 0.f) && ((double)len <= p.lmax) && isfinite(inv);
+                const int face = ok ? 2 * c + (dc < 0.f ? 1 : 0) : NFACE - 1;
+                const float da = c == 0 ? fd[1] : (c == 1 ? fd[2] : fd[0]); // axis (c+1)%3
+                const float db = c == 0 ? fd[2] : (c == 1 ? fd[0] : fd[1]); // axis (c+2)%3
+                p.px.re[kpx] = ok ? da * inv : 0.f;
+                p.px.re[n + kpx] = ok ? db * inv : 0.f;
+                p.px.rj[kpx] = fid * NFACE + face;
                 p.px.occ[kpx] = -1;
-                my_j = fid;
+                my_j = fid * NFACE + face;
             }
         }
     }
@@ -428,9 +461,10 @@ __global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block
 // unoccluded at the end of the chunk are compacted into list_out for the next chunk, so
 // the pairs actually swept track the reference's own early-exit count (main.cpp:324).
 struct ShadowParams {
-    const float4 *tables; // tables of the current light's vertices, table j at + j*table_stride
-    size_t table_stride;  // in float4
-    int tile_lo, tile_hi, n_tris, F, n_px, is_last;
+    const float4 *tables;  // face tables of the current light's vertices: group g=(j,f<6) at + (j*6+f)*table_stride
+    const float4 *allcand; // table of group f == 6
+    size_t table_stride;   // in float4
+    int tile_lo, tile_hi, n_tris, F, n_px, is_last; // F = number of ray groups (light vertices * NFACE)
     const float *tri_verts;
     const float4 *spheres;
     int n_spheres;
@@ -469,7 +503,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         if (blk >= total_blocks) break;
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
-        float ex[R], ey[R], ez[R];
+        float rp[R], rq[R];
         int kp[R];
         unsigned valid = 0;
 #pragma unroll
@@ -479,7 +513,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
             e = min(e, seg_end - 1);
             const int k = p.list_in[e];
             kp[r] = k;
-            ex[r] = p.px.re[k], ey[r] = p.px.re[n + k], ez[r] = p.px.re[2 * n + k];
+            rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
             sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
             sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
             sm.t[r][tid] = p.px.rt[k];
@@ -488,8 +522,10 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         }
         unsigned done = 0;
         unsigned swept = 0;
-        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, p.tables + (size_t)j * p.table_stride, p.tile_lo, p.tile_hi, p.n_tris,
-                                                p.tri_verts, ex, ey, ez, valid, done, gtile, n_strict, swept, n_miss);
+        const int face = j % NFACE;
+        const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
+        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, tab, p.tile_lo, p.tile_hi, p.n_tris, p.tri_verts, rp, rq, valid, done,
+                                                gtile, n_strict, swept, n_miss);
         tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
         unsigned surv = valid & ~done;
         // finished rays: publish occluder and the t it left behind

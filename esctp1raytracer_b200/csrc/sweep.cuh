@@ -3,7 +3,7 @@
 //
 // What the reference does per (ray, triangle) pair: full Moller-Trumbore with
 // a double-precision divide (ray_triangle.h:7-57, ~52 flop).  What this kernel
-// does per pair: 9 FMA (issued as 4.5 packed FFMA2).  The saving comes from two
+// does per pair: 6 FFMA + 1.5 LOP3.  The saving comes from two
 // observations.
 //
 //  1. Every sweep is a bundle of rays through ONE common point.  Primary rays
@@ -18,7 +18,14 @@
 //     plane O lies on, s = sign(e2.(e1 x a)), is a per-triangle constant.
 //     A line through O can only hit the triangle if s*u', s*v', s*w' >= 0.
 //     The three vectors (pre-multiplied by s) plus a safety margin K are
-//     tabulated once per (O, triangle): 48 bytes.
+//     tabulated once per (O, triangle).
+//
+//  1b. Directions through one point have two degrees of freedom.  Each ray group
+//     uses a parametrisation d' = p*U + q*V + W (the image plane for primary
+//     rays: U,V,W = horizontal, vertical, llc-origin and (p,q) = the reference's
+//     own (s,t); a cube face around a light vertex for shadow rays), so each
+//     edge function becomes AFFINE in (p,q):  u'(p,q) = p*(U.B) + q*(V.B) + (W.B + K|d'|max)
+//     = 2 FFMA.  The table row is 3 x (A,B,C,-) = 48 bytes per (O, group, triangle).
 //
 //  2. The test above is used as a CONSERVATIVE FILTER only: K bounds every
 //     rounding difference between this evaluation and the reference's own
@@ -34,13 +41,15 @@
 //    (cp.async.bulk + mbarrier complete_tx, UBLKCP in SASS), STAGES deep;
 //  * every lane of every warp reads the SAME row at the same time, so the three
 //    LDS.128 per triangle are pure broadcasts, amortised over R rays per thread
-//    held in registers (R = 8: 72 FFMA per 3 loads);
-//  * the inner loop has NO per-triangle branch: the sign of max-over-rays of
-//    min(u',v',w') is shifted into a bit register and tested once per batch of
-//    BATCH triangles; candidates (a few per ray per sweep) are then re-evaluated
-//    in index order.  This keeps the hot loop a straight FFMA/FMNMX3/LDS stream;
-//  * scalar FFMA, not packed FFMA2: on B200 the packed form measured ~7 % slower
-//    in this loop (the limiter is not issue slots once the branch is gone);
+//    held in registers (R = 8: 48 FFMA per 3 loads);
+//  * "all three >= 0" is tested on the sign bits: (u'|v'|w') as integers (one LOP3),
+//    AND-ed over the R rays; FMNMX3 measured ~2 issue slots next to FFMA, LOP3 ~1.3;
+//  * the inner loop has NO per-triangle branch: the resulting sign bit is shifted
+//    into a bit register and tested once per batch of BATCH triangles; candidates
+//    (a few per ray per sweep) are then re-evaluated in index order.  This keeps
+//    the hot loop a straight FFMA/LOP3/LDS stream;
+//  * scalar FFMA, not packed fma.rn.f32x2: with honest operands the packed form
+//    measured no faster in this loop on B200;
 //  * 512 threads (16 warps, 4 per scheduler) per CTA, one CTA per SM.
 #pragma once
 #include <cstdint>
@@ -110,13 +119,13 @@ struct Counters {
     unsigned long long tests_primary, tests_shadow, strict_evals, tests_shadow_ref, n_hits, filter_misses;
 };
 
-// One 48-byte row triple per triangle: rb = (s*B, K), rc = (s*C, K), rd = (s*D, K).
-// min over the three edge functions of the line with direction (ex,ey,ez).
-__device__ __forceinline__ float edge_min(const float4 rb, const float4 rc, const float4 rd, float ex, float ey, float ez) {
-    const float x = fmaf(ex, rb.x, fmaf(ey, rb.y, fmaf(ez, rb.z, rb.w)));
-    const float y = fmaf(ex, rc.x, fmaf(ey, rc.y, fmaf(ez, rc.z, rc.w)));
-    const float z = fmaf(ex, rd.x, fmaf(ey, rd.y, fmaf(ez, rd.z, rd.w)));
-    return fminf(fminf(x, y), z);
+// One 48-byte row triple per triangle: rb = (A,B,C,-) of s*u', rc of s*v', rd of s*w'.
+// Sign word of the three edge functions at the ray parameters (p,q): sign bit clear <=> all three >= 0.
+__device__ __forceinline__ unsigned edge_sign(const float4 rb, const float4 rc, const float4 rd, float p, float q) {
+    const float x = fmaf(p, rb.x, fmaf(q, rb.y, rb.z));
+    const float y = fmaf(p, rc.x, fmaf(q, rc.y, rc.z));
+    const float z = fmaf(p, rd.x, fmaf(q, rd.y, rd.z));
+    return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
 }
 
 // ---- strict path: the reference's own test on the surviving pairs ---------------
@@ -150,15 +159,14 @@ __device__ __noinline__ unsigned strict_tri(Smem<R> &sm, int tid, unsigned mask,
 }
 
 // ---- the sweep over tiles [tile_lo, tile_hi) of one origin table, for the R rays of each thread ---
-// ex/ey/ez: filter directions (unit-ish vectors along the line through the table's origin)
+// rp/rq: the rays' parameters in the table's direction parametrisation
 // valid: bit r set = ray r exists; done: bit r set = ray r needs no more tests
 // gtile: running tile counter of this CTA (mbarrier phase bookkeeping across ray blocks)
 template <int R, bool ANYHIT, bool EXHAUSTIVE>
 __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
-                                            int n_tris, const float *__restrict__ tri_verts, const float (&ex)[R],
-                                            const float (&ey)[R], const float (&ez)[R], unsigned valid, unsigned &done,
-                                            unsigned &gtile, unsigned &n_strict, unsigned &n_tiles_swept,
-                                            unsigned &n_miss) {
+                                            int n_tris, const float *__restrict__ tri_verts, const float (&rp)[R],
+                                            const float (&rq)[R], unsigned valid, unsigned &done, unsigned &gtile,
+                                            unsigned &n_strict, unsigned &n_tiles_swept, unsigned &n_miss) {
     const int tid = threadIdx.x;
     const int n_tiles = tile_hi - tile_lo;
     const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
@@ -181,16 +189,16 @@ __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restric
             const float4 *__restrict__ tp = sm.tile[s];
 #pragma unroll 1
             for (int b0 = 0; b0 < TILE; b0 += BATCH) {
-                // hot loop: straight-line, no branch per triangle.  neg collects the sign bit of
-                // max over rays of min(u',v',w'): 0 = some ray may hit that triangle.
+                // hot loop: straight-line, no branch per triangle.  neg collects, per triangle, the AND
+                // over rays of sign(u'|v'|w'): 0 = some ray may hit that triangle.
                 unsigned neg = 0xffffffffu;
 #pragma unroll 4
                 for (int k = 0; k < BATCH; ++k) {
                     const float4 rb = tp[3 * (b0 + k)], rc = tp[3 * (b0 + k) + 1], rd = tp[3 * (b0 + k) + 2];
-                    float M = -1.f;
+                    unsigned A = 0xffffffffu;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) M = fmaxf(M, edge_min(rb, rc, rd, ex[r], ey[r], ez[r]));
-                    neg = __funnelshift_l(__float_as_uint(M), neg, 1);
+                    for (int r = 0; r < R; ++r) A &= edge_sign(rb, rc, rd, rp[r], rq[r]);
+                    neg = __funnelshift_l(A, neg, 1);
                 }
 #ifdef SWEEP_NO_STRICT // development microbenchmark only (tools/sweep_mb.cu): timing without the strict path
                 if (~neg & 0xffffu) ++n_strict;
@@ -208,7 +216,7 @@ __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restric
                                  rd = lds128_opaque(&tp[3 * (b0 + k) + 2]);
                     unsigned mask = 0;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) mask |= (edge_min(rb, rc, rd, ex[r], ey[r], ez[r]) >= 0.f ? 1u : 0u) << r;
+                    for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
                     const unsigned live = valid & ~done;
                     if (EXHAUSTIVE) {
                         // validation mode: strict-test every pair, count accepts the filter would have lost

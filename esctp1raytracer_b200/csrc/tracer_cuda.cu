@@ -63,9 +63,10 @@ struct tracer_scene_dev {
     std::vector<int> h_light_vbase, h_light_F;
     std::vector<float> h_light_verts;
     double bb_lo[3], bb_hi[3];
-    float4 *eye_table = nullptr, *light_tables = nullptr;
+    float4 *eye_table = nullptr, *light_tables = nullptr, *allcand_table = nullptr;
+    std::vector<double> table_lmax; // per (light vertex, cube face): reach bound it was built for, < 0 = not built
+    bool allcand_built = false;
     size_t table_stride = 0; // float4 per table
-    std::vector<double> light_lmax; // per light: reach bound its vertex tables were built for
     // per-frame workspace
     int ws_npx = 0, ws_L = 0;
     int *hit_tri = nullptr, *rj = nullptr, *occ = nullptr, *list = nullptr, *list_b = nullptr, *faceid = nullptr,
@@ -98,7 +99,7 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
         rc |= dev_alloc(&s->faceid, n * L);
         rc |= dev_alloc(&s->hit_t, n) | dev_alloc(&s->hit_v, n) | dev_alloc(&s->carry, n);
         rc |= dev_alloc(&s->nrm, 3 * n) | dev_alloc(&s->accum, 3 * n + 16) | dev_alloc(&s->ro, 3 * n);
-        rc |= dev_alloc(&s->rd, 3 * n) | dev_alloc(&s->re, 3 * n) | dev_alloc(&s->rt, n);
+        rc |= dev_alloc(&s->rd, 3 * n) | dev_alloc(&s->re, 2 * n) | dev_alloc(&s->rt, n);
         rc |= dev_alloc(&s->rgb8, 3 * n + 64) | dev_alloc(&s->mask, n);
         if (rc) return TRACER_ERR_NOMEM;
         s->ws_npx = n_px;
@@ -144,12 +145,22 @@ int pick_rays(int64_t n_rays, int n_sms, int forced) {
     return 2;
 }
 
-int build_table(const tracer_scene_dev *s, const double o[3], double lmax, float4 *table, cudaStream_t st) {
+int build_table(const tracer_scene_dev *s, const trk::TableParam &tp, float4 *table, cudaStream_t st) {
     const int th = 256;
-    trk::build_origin_table<<<(s->n_pad + th - 1) / th, th, 0, st>>>(s->tri_verts, s->n_tris, s->n_pad, o[0], o[1], o[2],
-                                                                      lmax, table);
+    trk::build_origin_table<<<(s->n_pad + th - 1) / th, th, 0, st>>>(s->tri_verts, s->n_tris, s->n_pad, tp, table);
     CK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// cube face f around point o: d' = p*e_a + q*e_b + sg*e_c, c = f/2, a = (c+1)%3, b = (c+2)%3, |d'| <= sqrt(3)
+trk::TableParam face_param(const float *o, int f, double lmax) {
+    trk::TableParam tp{};
+    const int c = f / 2, a = (c + 1) % 3, b = (c + 2) % 3;
+    for (int i = 0; i < 3; ++i) tp.o[i] = o[i];
+    tp.U[a] = 1.0, tp.V[b] = 1.0, tp.W[c] = (f & 1) ? -1.0 : 1.0;
+    tp.dmax = std::sqrt(3.0);
+    tp.lmax = lmax;
+    return tp;
 }
 
 }  // namespace
@@ -201,7 +212,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     if (!s) return;
     dev_free(s->tri_verts), dev_free(s->tri_normals), dev_free(s->geom_material), dev_free(s->sphere_material);
     dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
-    dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables);
+    dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables), dev_free(s->allcand_table);
     dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->list_b), dev_free(s->faceid);
     dev_free(s->dbg_occ), dev_free(s->cnt_b);
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
@@ -316,19 +327,22 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const size_t need = (size_t)(s->V + 1) * s->table_stride * sizeof(float4);
+        const size_t need = (size_t)(6 * s->V + 2) * s->table_stride * sizeof(float4);
         if (need > free_b / 2) {
             tracer_cuda_scene_destroy(s);
-            return fail(TRACER_ERR_NOMEM, "light-vertex tables (" + std::to_string(need >> 20) + " MiB) exceed half of free HBM");
+            return fail(TRACER_ERR_NOMEM, "light-vertex face tables (" + std::to_string(need >> 20) + " MiB) exceed half of free HBM");
         }
     }
     TRY(dev_alloc(&s->eye_table, s->table_stride));
-    TRY(dev_alloc(&s->light_tables, s->table_stride * (size_t)std::max(1, s->V)));
-    TRY(dev_alloc(&s->seg_count, (size_t)s->maxF + 1));
-    TRY(dev_alloc(&s->seg_off, (size_t)s->maxF + 2));
-    TRY(dev_alloc(&s->blk_off, (size_t)s->maxF + 2));
-    TRY(dev_alloc(&s->cursor, (size_t)s->maxF + 1));
-    TRY(dev_alloc(&s->cnt_b, (size_t)s->maxF + 1));
+    TRY(dev_alloc(&s->light_tables, s->table_stride * (size_t)std::max(1, 6 * s->V)));
+    TRY(dev_alloc(&s->allcand_table, s->table_stride));
+    s->table_lmax.assign((size_t)6 * s->V, -1.0);
+    const size_t n_groups = (size_t)s->maxF * trk::NFACE;
+    TRY(dev_alloc(&s->seg_count, n_groups + 1));
+    TRY(dev_alloc(&s->seg_off, n_groups + 2));
+    TRY(dev_alloc(&s->blk_off, n_groups + 2));
+    TRY(dev_alloc(&s->cursor, n_groups + 1));
+    TRY(dev_alloc(&s->cnt_b, n_groups + 1));
     TRY(dev_alloc(&s->work, 1));
     TRY(dev_alloc(&s->counters, 1));
     for (auto &e : s->ev) TRY_CUDA(cudaEventCreate(&e));
@@ -384,21 +398,23 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     }
     // shadow segments of light k are bounded by len_k <= (k+1) * diag: t carries over lights (main.cpp:764)
     const double diag = std::sqrt(diag2) * 1.001 + 1e-30;
-    s->light_lmax.resize((size_t)L, -1.0);
-    for (int k = 0; k < L; ++k) {
-        const double need = (k + 1) * diag;
-        if (s->light_lmax[k] >= need) continue;
-        s->light_lmax[k] = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
-        for (int j = s->h_light_vbase[k]; j < s->h_light_vbase[k + 1]; ++j) {
-            const double oo[3] = {s->h_light_verts[3 * j], s->h_light_verts[3 * j + 1], s->h_light_verts[3 * j + 2]};
-            if (int rc = build_table(s, oo, s->light_lmax[k], s->light_tables + (size_t)j * s->table_stride, st)) return rc;
-            ++launches;
-        }
-    }
     CK_CUDA(cudaEventRecord(s->ev[0], st));
-    {
-        const double oo[3] = {cam->origin[0], cam->origin[1], cam->origin[2]};
-        if (int rc = build_table(s, oo, 0.0, s->eye_table, st)) return rc;
+    {   // eye table on the image plane: d'(s,t) = (llc - origin) + s*horizontal + t*vertical (camera.h:31-34)
+        trk::TableParam tp{};
+        for (int c = 0; c < 3; ++c) {
+            tp.o[c] = cam->origin[c], tp.U[c] = cam->horizontal[c], tp.V[c] = cam->vertical[c];
+            tp.W[c] = (double)cam->lower_left_corner[c] - (double)cam->origin[c];
+        }
+        for (int corner = 0; corner < 4; ++corner) { // |d'| is convex in (s,t): its maximum is at a corner
+            double n2 = 0;
+            for (int c = 0; c < 3; ++c) {
+                const double v = tp.W[c] + (corner & 1) * tp.U[c] + (corner >> 1) * tp.V[c];
+                n2 += v * v;
+            }
+            tp.dmax = std::max(tp.dmax, std::sqrt(n2));
+        }
+        tp.lmax = 0.0;
+        if (int rc = build_table(s, tp, s->eye_table, st)) return rc;
         ++launches;
     }
     CK_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(sweep::Counters), st));
@@ -454,14 +470,14 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.tri_verts = s->tri_verts, lp.tri_normals = s->tri_normals, lp.tri_geom = s->tri_geom;
         lp.geom_has_normals = s->geom_has_normals, lp.geom_material = s->geom_material;
         lp.sphere_material = s->sphere_material, lp.spheres = s->spheres;
-        lp.rng_mode = o.rng_mode, lp.seed = o.seed, lp.faceid = s->faceid, lp.lmax = k < L ? s->light_lmax[k] : 0.0;
+        lp.rng_mode = o.rng_mode, lp.seed = o.seed, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
         lp.seg_count = s->seg_count, lp.counters = s->counters, lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
-        if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * (s->maxF + 1), st));
+        if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
         CK_CUDA(cudaGetLastError());
         ++launches;
         if (k == L) break;
-        const int F = s->h_light_F[k];
+        const int F = s->h_light_F[k] * trk::NFACE; // ray groups: (light vertex, cube face)
         trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
         CK_CUDA(cudaGetLastError());
         trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
@@ -480,6 +496,27 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             int64_t n_live = 0;
             for (int j = 0; j < F; ++j) n_live += h_cnt[j];
             if (n_live == 0) break; // every shadow ray of this light already has its occluder
+            if (c == 0) { // build (once) the face tables of the groups that actually have rays
+                for (int gi = 0; gi < F; ++gi) {
+                    if (!h_cnt[gi]) continue;
+                    const int face = gi % trk::NFACE, vtx = s->h_light_vbase[k] + gi / trk::NFACE;
+                    if (face == trk::NFACE - 1) {
+                        if (!s->allcand_built) {
+                            trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table);
+                            CK_CUDA(cudaGetLastError());
+                            s->allcand_built = true, ++launches;
+                        }
+                        continue;
+                    }
+                    double &built = s->table_lmax[(size_t)vtx * 6 + face];
+                    const double need = (k + 1) * diag;
+                    if (built >= need) continue;
+                    built = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
+                    const trk::TableParam tp = face_param(&s->h_light_verts[3 * (size_t)vtx], face, built);
+                    if (int rc = build_table(s, tp, s->light_tables + ((size_t)vtx * 6 + face) * s->table_stride, st)) return rc;
+                    ++launches;
+                }
+            }
             const int Rk = pick_rays(n_live, g.n_sms, o.rays_per_thread);
             const int rpb = sweep::THREADS * Rk;
             int max_blocks = 0;
@@ -487,7 +524,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, rpb, s->blk_off, cnt_out, s->work);
             CK_CUDA(cudaGetLastError());
             trk::ShadowParams sp{};
-            sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * s->table_stride, sp.table_stride = s->table_stride;
+            sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
+            sp.allcand = s->allcand_table;
             sp.tile_lo = (int)((int64_t)n_tiles * c / n_chunks), sp.tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
             sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.is_last = (c == n_chunks - 1), sp.tri_verts = s->tri_verts;
             sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;

@@ -32,7 +32,7 @@ for n, W, H, L in cases:
                       shadow_chunks=int(os.environ.get('TRACER_CHUNKS', '0')))
         wall = time.time() - t0
     st = out.stats
-    ffma = 9.0
+    ffma = 6.0
     prim = st["tests_primary"] * ffma * 2 / (st["ms_primary"] * 1e-3) / 1e12
     shad = st["tests_shadow"] * ffma * 2 / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
     shad_ref = st["tests_shadow_ref"] * ffma * 2 / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12

@@ -205,6 +205,52 @@ __global__ void __launch_bounds__(512, 1) k_mixed(const float4 *tile_g, int reps
     if (hits == 123456789) out[0] = hits;
 }
 
+// V6: 2-D rows (A,B,C per edge: 6 FFMA per test), sign test via LOP3 (SIGN=1) or FMNMX3 (SIGN=0); 3-D rows when DIM3
+template <int R, int SIGN, int DIM3, int BATCH, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_2d(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE * 3];
+    for (int i = threadIdx.x; i < TILE * 3; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float px[R], py[R], pz[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) px[r] = seed * (threadIdx.x + 1) * (r + 1), py[r] = seed * (threadIdx.x + 7) * (r + 3), pz[r] = -1.f - seed * r;
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TILE; b += BATCH) {
+            unsigned neg = 0xffffffffu;
+#pragma unroll UNROLL
+            for (int k = 0; k < BATCH; ++k) {
+                const float4 rb = tile[3 * (b + k)], rc = tile[3 * (b + k) + 1], rd = tile[3 * (b + k) + 2];
+                float M = -1.f;
+                unsigned A = 0xffffffffu;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float x, y, z;
+                    if (DIM3) {
+                        x = fmaf(px[r], rb.x, fmaf(py[r], rb.y, fmaf(pz[r], rb.z, rb.w)));
+                        y = fmaf(px[r], rc.x, fmaf(py[r], rc.y, fmaf(pz[r], rc.z, rc.w)));
+                        z = fmaf(px[r], rd.x, fmaf(py[r], rd.y, fmaf(pz[r], rd.z, rd.w)));
+                    } else {
+                        x = fmaf(px[r], rb.x, fmaf(py[r], rb.y, rb.z));
+                        y = fmaf(px[r], rc.x, fmaf(py[r], rc.y, rc.z));
+                        z = fmaf(px[r], rd.x, fmaf(py[r], rd.y, rd.z));
+                    }
+                    if (SIGN)
+                        A &= __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
+                    else
+                        M = fmaxf(M, fminf(fminf(x, y), z));
+                }
+                neg = __funnelshift_l(SIGN ? A : __float_as_uint(M), neg, 1);
+            }
+            if (~neg & ((BATCH >= 32) ? 0xffffffffu : ((1u << BATCH) - 1u))) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
 // VP: the production data path (TMA tile stream + mbarrier + per-tile barrier) without the strict path
 template <int R>
 __global__ void __launch_bounds__(sweep::THREADS, 1) k_prod(const float4 *table, int n_tiles, int n_blocks, int *work, float *out, float seed) {
@@ -222,11 +268,11 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) k_prod(const float4 *table,
         __syncthreads();
         const int blk = sm.blk;
         if (blk >= n_blocks) break;
-        float ex[R], ey[R], ez[R];
+        float ex[R], ey[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) ex[r] = seed * (tid + 1) * (r + 1 + blk), ey[r] = seed * (tid + 7) * (r + 3), ez[r] = -1.f - seed * r;
+        for (int r = 0; r < R; ++r) ex[r] = seed * (tid + 1) * (r + 1 + blk), ey[r] = seed * (tid + 7) * (r + 3);
         unsigned done = 0;
-        sweep::sweep_table<R, false, false>(sm, table, 0, n_tiles, n_tiles * 256, nullptr, ex, ey, ez, 0xffu >> (8 - R), done, gtile,
+        sweep::sweep_table<R, false, false>(sm, table, 0, n_tiles, n_tiles * 256, nullptr, ex, ey, 0xffu >> (8 - R), done, gtile,
                                             n_strict, n_swept, n_miss);
         __syncthreads();
     }
@@ -292,10 +338,27 @@ int main() {
     run("mixed R=4 NF2=1 batch8 u8", [&] { k_mixed<4, 1, 8, 8><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
     run("mixed R=6 NF2=1 batch8 u4", [&] { k_mixed<6, 1, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 6));
     run("mixed R=6 NF2=2 batch8 u4", [&] { k_mixed<6, 2, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 6));
+    printf("-- k_2d: TFLOP/s-equiv column counts 18 flop/test for every variant (so 2-D rows show >1x speed, not flops)\n");
+    run("3D rows FMNMX3 R=8 b16 u4", [&] { k_2d<8, 0, 1, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("3D rows LOP3   R=8 b16 u4", [&] { k_2d<8, 1, 1, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("2D rows FMNMX3 R=8 b16 u4", [&] { k_2d<8, 0, 0, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("2D rows LOP3   R=8 b16 u4", [&] { k_2d<8, 1, 0, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("2D rows LOP3   R=12 b16 u4", [&] { k_2d<12, 1, 0, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 12));
+    run("2D rows LOP3   R=16 b16 u2", [&] { k_2d<16, 1, 0, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 16));
+    run("2D rows LOP3   R=8 b16 u8", [&] { k_2d<8, 1, 0, 16, 8><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("2D rows LOP3   R=4 b16 u4", [&] { k_2d<4, 1, 0, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 4));
+    run("2D rows FMNMX3 R=16 b16 u2", [&] { k_2d<16, 0, 0, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 16));
+    printf("-- R / unroll sweep of the 2-D LOP3 loop (18-flop-equiv)\n");
+#define SW(R, U) run("2D LOP3 R=" #R " b16 u" #U, [&] { k_2d<R, 1, 0, 16, U><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, R));
+    SW(5, 4) SW(6, 4) SW(7, 4) SW(9, 4) SW(10, 4) SW(6, 2) SW(10, 2) SW(8, 2) SW(8, 1) SW(6, 8) SW(10, 1)
+    run("2D LOP3 R=8 b32 u4", [&] { k_2d<8, 1, 0, 32, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("2D LOP3 R=8 b8 u4", [&] { k_2d<8, 1, 0, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("2D LOP3 R=8 b16 u4 256thr", [&] { k_2d<8, 1, 0, 16, 4><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
+    run("2D LOP3 R=8 b16 u4 384thr", [&] { k_2d<8, 1, 0, 16, 4><<<sms, 384>>>(tile_g, reps, out, seed); }, PAIRS(384, 8));
     {   // production data path
         const int n_tiles = 400;
         std::vector<float> ht((size_t)n_tiles * TILE * 12, 0.f);
-        for (size_t i = 0; i < ht.size(); ++i) ht[i] = ((i % 4) == 3) ? -1.f : 0.001f * (float)(i % 89); // K = -1: never candidate
+        for (size_t i = 0; i < ht.size(); ++i) ht[i] = ((i % 4) == 2) ? -1.f : 0.0001f * (float)(i % 89); // C = -1: never candidate
         float4 *table;
         int *work;
         cudaMalloc(&table, ht.size() * 4);
