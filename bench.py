@@ -310,6 +310,8 @@ def main():
                 "flop_per_pair": FLOP_PER_PAIR, "algorithmic_pairs_per_step": alg_pairs / args.steps,
                 "swept_pairs_per_step": swept_pairs / args.steps, "sweep_ms_per_step": sweep_ms_max / args.steps,
                 "executed_tflops": FLOP_PER_PAIR * swept_pairs / world / sweep_s / 1e12,
+                "primary_ms_per_step": tot["ms_primary"] / world / args.steps, "shadow_ms_per_step": tot["ms_shadow"] / world / args.steps,
+                "primary_tflops": FLOP_PER_PAIR * tot["tests_primary"] / (tot["ms_primary"] * 1e-3) / 1e12 if tot["ms_primary"] else None,
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / world / sweep_s / 1e12,
                 "ceiling_note": "6 FFMA + 1.5 LOP3 (~2 issue slots) + 0.5 LDS/SHF per pair: FP32-pipe share of issue <= ~0.70; measured loop ceiling 0.58 of nominal (tools/sweep_mb.cu)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,

@@ -147,19 +147,26 @@ __global__ void build_allcand_table(int n_tris, int n_pad, float4 *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------
+// Work decomposition of the sweeps: (ray block) x (triangle slice).  Closest hit is the
+// lexicographic minimum of (t, index) over all valid hits (ray_triangle.h:46-50: t2 >= t rejects,
+// so among equal t the lowest index stays) and the first occluder is the minimum index over all
+// valid hits, so triangle slices can be swept independently and merged with a 64-bit atomicMin:
+//   closest hit  key = t bits << 32 | index      (t > 0: float order == unsigned order)
+//   occluder     key = index << 32  | t2 bits
+// Slicing gives enough work items for every SM on small frames, late shadow chunks and when the
+// frame is split over several GPUs.
+constexpr unsigned long long KEY_NONE = 0xffffffffffffffffull;
+
 struct PrimaryParams {
     Cam cam;
     Bands bands;
     const float4 *table; // eye table
     int n_tiles, n_tris;
     const float *tri_verts;
-    const float4 *spheres;
-    int n_spheres;
-    int *hit_tri;
-    float *hit_t, *hit_v;
+    unsigned long long *best; // [n_px] merged closest-hit keys over triangles, KEY_NONE = miss
     sweep::Counters *counters;
     int *work;
-    int n_blocks;
+    int n_blocks, n_slices;
 };
 
 template <int R, bool EXHAUSTIVE>
@@ -173,12 +180,17 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
     }
     __syncthreads();
     unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0;
-    unsigned long long tests = 0, hits = 0;
+    unsigned long long tests = 0;
+    const int n_items = p.n_blocks * p.n_slices;
     for (;;) {
         if (tid == 0) sm.blk = atomicAdd(p.work, 1);
         __syncthreads();
-        const int blk = sm.blk;
-        if (blk >= p.n_blocks) break;
+        const int item = sm.blk;
+        if (item >= n_items) break;
+        // slice-major order: all CTAs stream the same table tiles at about the same time (L2 reuse)
+        const int slice = item / p.n_blocks, blk = item - slice * p.n_blocks;
+        const int tile_lo = (int)((long long)p.n_tiles * slice / p.n_slices);
+        const int tile_hi = (int)((long long)p.n_tiles * (slice + 1) / p.n_slices);
         const int base = blk * (sweep::THREADS * R);
         float rp[R], rq[R];
         unsigned valid = 0;
@@ -199,31 +211,22 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             sm.tri[r][tid] = -1;
         }
         unsigned done = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, 0, p.n_tiles, p.n_tris, p.tri_verts, rp, rq, valid, done, gtile,
-                                                 n_strict, n_swept, n_miss);
-        tests += (unsigned long long)__popc(valid) * p.n_tris;
-        // extension: analytic spheres after all triangles, strict, in order
+        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, rp, rq, valid, done,
+                                                 gtile, n_strict, n_swept, n_miss);
+        const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
+        tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (!((valid >> r) & 1u)) continue;
-            float t = sm.t[r][tid], v = sm.v[r][tid];
-            int tri = sm.tri[r][tid];
-            if (p.n_spheres > 0) {
-                const f3 o = strict::ld(p.cam.o);
-                const f3 d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
-                for (int s = 0; s < p.n_spheres; ++s)
-                    if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
-            }
-            const int k = base + r * sweep::THREADS + tid;
-            p.hit_tri[k] = tri;
-            p.hit_t[k] = t;
-            p.hit_v[k] = v;
-            hits += tri >= 0;
+            const float t = sm.t[r][tid];
+            const int tri = sm.tri[r][tid];
+            if (tri >= 0)
+                atomicMin(&p.best[base + r * sweep::THREADS + tid],
+                          ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri);
         }
-        __syncthreads(); // slots are rewritten by the next block
+        __syncthreads(); // slots are rewritten by the next item
     }
     atomicAdd(&p.counters->tests_primary, tests);
-    atomicAdd(&p.counters->n_hits, hits);
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
     if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
 }
@@ -237,6 +240,8 @@ struct LightInfo {              // device arrays describing the lights
 };
 
 struct PixelState {
+    const unsigned long long *best;     // [n_px] merged closest-hit keys from primary_kernel
+    unsigned long long *best_occ;       // [n_px] merged first-occluder keys of the current light
     int *hit_tri;
     float *hit_t, *hit_v;
     float *carry_t;       // the `t` variable of scan_row across lights (main.cpp:715, 764, occlusion's t2)
@@ -244,10 +249,37 @@ struct PixelState {
     float *accum;         // [3][n_px]
     float *ro, *rd;       // [3][n_px] shadow ray origin, strict unit dir
     float *re;            // [2][n_px] filter parameters (p,q) on the ray's cube face
-    float *rt;            // [n_px] tmax in, t after occlusion() out
+    float *rt;            // [n_px] tmax of the current shadow ray
     int *rj;              // [n_px] ray group within the current light: faceID*NFACE + cube face, -1 none
-    int *occ;             // [n_px] first in-order occluder, -1 none
 };
+
+// After the sliced closest-hit sweep: unpack the merged (t, index) key, recover v by one strict
+// re-evaluation of the winning triangle (same arithmetic, same bits as in the sweep), then the
+// extension: analytic spheres, tested after all triangles in object order with the running t.
+__global__ void __launch_bounds__(256) resolve_primary_kernel(Cam cam, Bands bands, const unsigned long long *__restrict__ best,
+                                                              const float *__restrict__ tri_verts, int n_tris,
+                                                              const float4 *__restrict__ spheres, int n_spheres,
+                                                              int *__restrict__ hit_tri, float *__restrict__ hit_t,
+                                                              float *__restrict__ hit_v) {
+    const int kpx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kpx >= bands.n_px) return;
+    const unsigned long long key = best[kpx];
+    int tri = key == KEY_NONE ? -1 : (int)(unsigned)(key & 0xffffffffu);
+    float t = FLT_MAX, v = 0.f; // main.cpp:715-717
+    if (tri >= 0 || n_spheres > 0) {
+        int w, h;
+        bands.map(kpx, w, h);
+        const f3 o = strict::ld(cam.o);
+        const f3 d = primary_dir(cam, bands.W, bands.H, w, h);
+        if (tri >= 0) {
+            const float *q = tri_verts + 9 * (size_t)tri;
+            strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v);
+        }
+        for (int s = 0; s < n_spheres; ++s)
+            if (strict::intersect_sphere(o, d, __ldg(&spheres[s]), t)) tri = n_tris + s;
+    }
+    hit_tri[kpx] = tri, hit_t[kpx] = t, hit_v[kpx] = v;
+}
 
 struct LightStepParams {
     Cam cam;
@@ -291,9 +323,11 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
     const bool in_range = kpx < p.bands.n_px;
     int my_j = -1;
     unsigned long long ref_tests = 0;
+    unsigned n_hit = 0;
     if (in_range) {
         const int n = p.bands.n_px;
         const int tri = p.px.hit_tri[kpx];
+        n_hit = (p.k == 0) && tri >= 0;
         if (tri < 0) {
             if (p.k == 0) p.px.accum[kpx] = p.px.accum[n + kpx] = p.px.accum[2 * n + kpx] = 0.f; // vec3 ctor, vec.h:44
             if (p.k < p.L) {
@@ -332,13 +366,16 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
             } else {
                 N = strict::mk(p.px.nrm[kpx], p.px.nrm[n + kpx], p.px.nrm[2 * n + kpx]);
                 acc = strict::mk(p.px.accum[kpx], p.px.accum[n + kpx], p.px.accum[2 * n + kpx]);
-                t = p.px.rt[kpx]; // what occlusion() left in t
+                // what occlusion() left in t: t2 of the first occluder, else tmax (main.cpp:320-324, 764)
+                const unsigned long long ok = p.px.best_occ[kpx];
+                t = ok == KEY_NONE ? p.px.rt[kpx] : __uint_as_float((unsigned)(ok & 0xffffffffu));
             }
             mat = (tri < p.n_tris) ? p.geom_material + 13 * (size_t)p.tri_geom[tri]
                                    : p.sphere_material + 13 * (size_t)(tri - p.n_tris);
             const float fL = (float)p.L;
             if (p.k > 0) { // finish light k-1: main.cpp:768-788
-                const int occ = p.px.occ[kpx];
+                const unsigned long long ok = p.px.best_occ[kpx];
+                const int occ = ok == KEY_NONE ? -1 : (int)(unsigned)(ok >> 32);
                 if (p.dbg_occ) p.dbg_occ[(size_t)kpx * p.L + (p.k - 1)] = occ;
                 ref_tests += (occ >= 0 && occ < p.n_tris) ? (unsigned)(occ + 1) : (unsigned)p.n_tris;
                 if (occ < 0) {
@@ -392,7 +429,6 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
                 p.px.re[kpx] = ok ? da * inv : 0.f;
                 p.px.re[n + kpx] = ok ? db * inv : 0.f;
                 p.px.rj[kpx] = fid * NFACE + face;
-                p.px.occ[kpx] = -1;
                 my_j = fid * NFACE + face;
             }
         }
@@ -407,6 +443,9 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
     if (p.k > 0) {
         for (int o = 16; o; o >>= 1) ref_tests += __shfl_down_sync(0xffffffffu, ref_tests, o);
         if ((threadIdx.x & 31) == 0 && ref_tests) atomicAdd(&p.counters->tests_shadow_ref, ref_tests);
+    } else {
+        for (int o = 16; o; o >>= 1) n_hit += __shfl_down_sync(0xffffffffu, n_hit, o);
+        if ((threadIdx.x & 31) == 0 && n_hit) atomicAdd(&p.counters->n_hits, (unsigned long long)n_hit);
     }
 }
 
@@ -440,7 +479,7 @@ __global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const 
     }
 }
 
-// before each triangle chunk: live-ray counts per light vertex -> ray-block offsets; reset the
+// before each triangle chunk: live-ray counts per ray group -> ray-block offsets; reset the
 // survivors' counters and the work counter
 __global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block, int *blk_off, int *cnt_out, int *work) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -456,20 +495,18 @@ __global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block
 }
 
 // ---------------------------------------------------------------------------------
-// First in-order occluder, one triangle chunk [tile_lo, tile_hi) per launch.  Rays are
-// grouped by light vertex (segment j of the list, table j); rays that are still
-// unoccluded at the end of the chunk are compacted into list_out for the next chunk, so
-// the pairs actually swept track the reference's own early-exit count (main.cpp:324).
+// First in-order occluder, one triangle chunk [tile_lo, tile_hi) per launch, the chunk itself cut
+// into n_slices slices swept by different CTAs (merged by atomicMin on index<<32|t2).  Rays are
+// grouped by (light vertex, cube face): segment j of the list, table j.  After each chunk the rays
+// that are still unoccluded are compacted into the next list (compact_kernel), so the pairs
+// actually swept track the reference's own early-exit count (main.cpp:324).
 struct ShadowParams {
     const float4 *tables;  // face tables of the current light's vertices: group g=(j,f<6) at + (j*6+f)*table_stride
     const float4 *allcand; // table of group f == 6
     size_t table_stride;   // in float4
-    int tile_lo, tile_hi, n_tris, F, n_px, is_last; // F = number of ray groups (light vertices * NFACE)
+    int tile_lo, tile_hi, n_slices, n_tris, F, n_px; // F = number of ray groups (light vertices * NFACE)
     const float *tri_verts;
-    const float4 *spheres;
-    int n_spheres;
     const int *list_in, *seg_off, *cnt_in, *blk_off;
-    int *list_out, *cnt_out;
     PixelState px;
     sweep::Counters *counters;
     int *work;
@@ -487,25 +524,32 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
     __syncthreads();
     const int n = p.n_px;
     const int total_blocks = p.blk_off[p.F];
+    const int n_items = total_blocks * p.n_slices;
+    const int n_tiles = p.tile_hi - p.tile_lo;
     unsigned gtile = 0, n_strict = 0, n_miss = 0;
     unsigned long long tests = 0;
     for (;;) {
         if (tid == 0) {
-            const int b = atomicAdd(p.work, 1);
-            int j = 0;
-            if (b < total_blocks)
+            const int it = atomicAdd(p.work, 1);
+            int j = 0, b = 0, sl = 0;
+            if (it < n_items) {
+                sl = it / total_blocks, b = it - sl * total_blocks; // slice-major
                 while (b >= p.blk_off[j + 1]) ++j;
-            sm.blk = b;
+            }
+            sm.blk = it < n_items ? b : -1;
             sm.seg = j;
+            sm.base_out = sl;
         }
         __syncthreads();
-        const int blk = sm.blk, j = sm.seg;
-        if (blk >= total_blocks) break;
+        const int blk = sm.blk, j = sm.seg, slice = sm.base_out;
+        if (blk < 0) break;
+        const int lo = p.tile_lo + (int)((long long)n_tiles * slice / p.n_slices);
+        const int hi = p.tile_lo + (int)((long long)n_tiles * (slice + 1) / p.n_slices);
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
         float rp[R], rq[R];
         int kp[R];
-        unsigned valid = 0;
+        unsigned valid = 0, done = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int e = base + r * sweep::THREADS + tid;
@@ -519,62 +563,74 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
             sm.t[r][tid] = p.px.rt[k];
             sm.v[r][tid] = 0.f;
             sm.tri[r][tid] = -1;
+            // an earlier slice may already have published an occluder below this slice: nothing to do
+            const unsigned long long seen = p.px.best_occ[k];
+            if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
         }
-        unsigned done = 0;
         unsigned swept = 0;
         const int face = j % NFACE;
         const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, tab, p.tile_lo, p.tile_hi, p.n_tris, p.tri_verts, rp, rq, valid, done,
-                                                gtile, n_strict, swept, n_miss);
+        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, tab, lo, hi, p.n_tris, p.tri_verts, rp, rq, valid, done, gtile, n_strict,
+                                                swept, n_miss);
         tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
-        unsigned surv = valid & ~done;
-        // finished rays: publish occluder and the t it left behind
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (!((valid >> r) & 1u)) continue;
-            float t = sm.t[r][tid];
-            int tri = sm.tri[r][tid];
-            if (tri < 0 && p.is_last && p.n_spheres > 0) { // extension: spheres after all triangles, in order
-                const f3 o = strict::mk(sm.ox[r][tid], sm.oy[r][tid], sm.oz[r][tid]);
-                const f3 d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
-                for (int s = 0; s < p.n_spheres && tri < 0; ++s)
-                    if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) tri = p.n_tris + s;
-            }
-            if (tri >= 0) {
-                p.px.occ[kp[r]] = tri;
-                p.px.rt[kp[r]] = t;
-            }
-        }
-        if (!p.is_last) { // compact the survivors of this block into the next chunk's list
-            const int mine = __popc(surv);
-            int incl = mine;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((tid & 31) >= o) incl += y;
-            }
-            if ((tid & 31) == 31) sm.scan[tid >> 5] = incl;
-            __syncthreads();
-            if (tid < 32) {
-                int w = tid < sweep::THREADS / 32 ? sm.scan[tid] : 0;
-                int wi = w;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, wi, o);
-                    if (tid >= o) wi += y;
-                }
-                if (tid < sweep::THREADS / 32) sm.scan[tid] = wi - w; // exclusive warp offsets
-                if (tid == 31) sm.base_out = wi ? atomicAdd(&p.cnt_out[j], wi) : 0;
-            }
-            __syncthreads();
-            int pos = seg_begin + sm.base_out + sm.scan[tid >> 5] + (incl - mine);
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if ((surv >> r) & 1u) p.list_out[pos++] = kp[r];
+            const int tri = sm.tri[r][tid];
+            if (((valid >> r) & 1u) && tri >= 0) // occlusion() leaves t = t2 behind (main.cpp:320-324): the multi-light carry
+                atomicMin(&p.px.best_occ[kp[r]], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(sm.t[r][tid]));
         }
         __syncthreads();
     }
     atomicAdd(&p.counters->tests_shadow, tests);
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
     if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
+}
+
+// after a chunk: rays without an occluder yet go to the next chunk's list (same segment)
+__global__ void compact_kernel(const int *__restrict__ list_in, const int *__restrict__ seg_off, const int *__restrict__ cnt_in,
+                               int F, const unsigned long long *__restrict__ best_occ, int *__restrict__ list_out,
+                               int *cnt_out) {
+    // grid.y = ray group; grid.x strides over the group's entries
+    const int j = blockIdx.y;
+    if (j >= F) return;
+    const int begin = seg_off[j], count = cnt_in[j];
+    for (int i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        int k = -1;
+        if (i < count) {
+            k = list_in[begin + i];
+            if (best_occ[k] != KEY_NONE) k = -1;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
+        if (m) {
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cnt_out[j], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (k >= 0) list_out[begin + base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = k;
+        }
+    }
+}
+
+// extension: spheres are tested after all triangles, in order, by the rays that found no triangle
+__global__ void shadow_spheres_kernel(const int *__restrict__ list, const int *__restrict__ seg_off, const int *__restrict__ cnt,
+                                      int F, PixelState px, int n_px, const float4 *__restrict__ spheres, int n_spheres,
+                                      int n_tris) {
+    const int j = blockIdx.y;
+    if (j >= F) return;
+    const int begin = seg_off[j], count = cnt[j];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int k = list[begin + i];
+        if (px.best_occ[k] != KEY_NONE) continue;
+        const f3 o = strict::mk(px.ro[k], px.ro[n_px + k], px.ro[2 * n_px + k]);
+        const f3 d = strict::mk(px.rd[k], px.rd[n_px + k], px.rd[2 * n_px + k]);
+        float t = px.rt[k];
+        for (int s = 0; s < n_spheres; ++s)
+            if (strict::intersect_sphere(o, d, __ldg(&spheres[s]), t)) {
+                px.best_occ[k] = ((unsigned long long)(unsigned)(n_tris + s) << 32) | __float_as_uint(t);
+                break;
+            }
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -69,8 +69,8 @@ struct tracer_scene_dev {
     size_t table_stride = 0; // float4 per table
     // per-frame workspace
     int ws_npx = 0, ws_L = 0;
-    int *hit_tri = nullptr, *rj = nullptr, *occ = nullptr, *list = nullptr, *list_b = nullptr, *faceid = nullptr,
-        *dbg_occ = nullptr;
+    int *hit_tri = nullptr, *rj = nullptr, *list = nullptr, *list_b = nullptr, *faceid = nullptr, *dbg_occ = nullptr;
+    unsigned long long *best = nullptr, *best_occ = nullptr;
     float *hit_t = nullptr, *hit_v = nullptr, *carry = nullptr, *nrm = nullptr, *accum = nullptr, *ro = nullptr,
           *rd = nullptr, *re = nullptr, *rt = nullptr;
     uint8_t *rgb8 = nullptr, *mask = nullptr;
@@ -87,14 +87,15 @@ namespace {
 int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
     const int L = std::max(1, s->n_lights);
     if (n_px > s->ws_npx) {
-        dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->list_b), dev_free(s->faceid);
-        dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
+        dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->best), dev_free(s->best_occ), dev_free(s->list), dev_free(s->list_b);
+        dev_free(s->faceid), dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
         dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
         dev_free(s->dbg_occ);
         s->ws_npx = 0;
         const size_t n = (size_t)n_px;
         int rc = 0;
-        rc |= dev_alloc(&s->hit_tri, n) | dev_alloc(&s->rj, n) | dev_alloc(&s->occ, n) | dev_alloc(&s->list, n);
+        rc |= dev_alloc(&s->hit_tri, n) | dev_alloc(&s->rj, n) | dev_alloc(&s->best, n) | dev_alloc(&s->best_occ, n);
+        rc |= dev_alloc(&s->list, n);
         rc |= dev_alloc(&s->list_b, n);
         rc |= dev_alloc(&s->faceid, n * L);
         rc |= dev_alloc(&s->hit_t, n) | dev_alloc(&s->hit_v, n) | dev_alloc(&s->carry, n);
@@ -137,12 +138,28 @@ int launch_shadow(int R, bool ex, const trk::ShadowParams &p, int grid, cudaStre
     return ex ? launch_shadow_t<2, true>(p, grid, st) : launch_shadow_t<2, false>(p, grid, st);
 }
 
-// rays per thread: 8 when that still gives every SM several ray blocks, else 4 or 2
-int pick_rays(int64_t n_rays, int n_sms, int forced) {
-    if (forced == 2 || forced == 4 || forced == 8) return forced;
-    if (n_rays >= (int64_t)sweep::THREADS * 8 * n_sms * 4) return 8;
-    if (n_rays >= (int64_t)sweep::THREADS * 4 * n_sms * 2) return 4;
-    return 2;
+// Work decomposition of a sweep: R rays per thread (8 preferred: best amortisation of the row loads) and
+// n_slices triangle slices, chosen so that ray blocks x slices keeps every SM busy for several items.
+struct Decomp {
+    int R, n_blocks, n_slices;
+};
+Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks) {
+    const int slices_possible = std::max(1, n_tiles / 4); // at least 4 tiles per slice
+    auto blocks_for = [&](int R) {
+        return (int)((n_rays + (int64_t)sweep::THREADS * R - 1) / ((int64_t)sweep::THREADS * R)) + extra_blocks;
+    };
+    Decomp d{2, blocks_for(2), 1};
+    if (forced_R == 2 || forced_R == 4 || forced_R == 8) {
+        d.R = forced_R, d.n_blocks = blocks_for(forced_R);
+    } else {
+        for (int R : {8, 4, 2}) {
+            d.R = R, d.n_blocks = blocks_for(R);
+            if ((int64_t)d.n_blocks * slices_possible >= 4 * (int64_t)n_sms) break;
+        }
+    }
+    const int64_t want = (6 * (int64_t)n_sms + d.n_blocks - 1) / std::max(1, d.n_blocks);
+    d.n_slices = d.n_blocks >= 6 * n_sms ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want, slices_possible));
+    return d;
 }
 
 int build_table(const tracer_scene_dev *s, const trk::TableParam &tp, float4 *table, cudaStream_t st) {
@@ -213,8 +230,8 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->tri_verts), dev_free(s->tri_normals), dev_free(s->geom_material), dev_free(s->sphere_material);
     dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
     dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables), dev_free(s->allcand_table);
-    dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->occ), dev_free(s->list), dev_free(s->list_b), dev_free(s->faceid);
-    dev_free(s->dbg_occ), dev_free(s->cnt_b);
+    dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->best), dev_free(s->best_occ), dev_free(s->list), dev_free(s->list_b);
+    dev_free(s->faceid), dev_free(s->dbg_occ), dev_free(s->cnt_b);
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
@@ -420,20 +437,23 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(sweep::Counters), st));
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
 
-    const int R = pick_rays(n_px, g.n_sms, o.rays_per_thread);
-    const int rays_per_block = sweep::THREADS * R;
     const int n_tiles = s->n_pad / sweep::TILE;
     // ---- primary: raygen + closest hit ----------------------------------------------
+    CK_CUDA(cudaMemsetAsync(s->best, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
     CK_CUDA(cudaEventRecord(s->ev[1], st));
     {
+        const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0);
         trk::PrimaryParams p{};
         p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
-        p.tri_verts = s->tri_verts, p.spheres = s->spheres, p.n_spheres = s->n_spheres;
-        p.hit_tri = s->hit_tri, p.hit_t = s->hit_t, p.hit_v = s->hit_v, p.counters = s->counters, p.work = s->work;
-        p.n_blocks = (n_px + rays_per_block - 1) / rays_per_block;
-        const int grid = std::min(p.n_blocks, g.n_sms);
-        if (int rc = launch_primary(R, o.exhaustive_strict != 0, p, grid, st)) return rc;
-        ++launches;
+        p.tri_verts = s->tri_verts;
+        p.best = s->best, p.counters = s->counters, p.work = s->work;
+        p.n_blocks = (n_px + sweep::THREADS * d.R - 1) / (sweep::THREADS * d.R), p.n_slices = d.n_slices;
+        const int grid = std::min(p.n_blocks * p.n_slices, g.n_sms);
+        if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, p, grid, st)) return rc;
+        trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
+                                                                        s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
+        CK_CUDA(cudaGetLastError());
+        launches += 2;
     }
     CK_CUDA(cudaEventRecord(s->ev[2], st));
 
@@ -461,7 +481,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     }
 
     // ---- lights: (finish k-1, set up k) -> group by light vertex -> first-occluder sweep ----
-    trk::PixelState px{s->hit_tri, s->hit_t, s->hit_v, s->carry, s->nrm, s->accum, s->ro, s->rd, s->re, s->rt, s->rj, s->occ};
+    trk::PixelState px{s->best, s->best_occ, s->hit_tri, s->hit_t, s->hit_v, s->carry, s->nrm, s->accum,
+                       s->ro,   s->rd,       s->re,      s->rt,    s->rj};
     for (int k = 0; k <= L; ++k) {
         trk::LightStepParams lp{};
         lp.cam = dc, lp.bands = bands, lp.px = px;
@@ -483,19 +504,26 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
         CK_CUDA(cudaGetLastError());
         launches += 2;
+        CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
         // triangle chunks: after each one the still-unoccluded rays are compacted (early exit, main.cpp:324)
         int n_chunks = o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(64, n_tiles / 8));
         n_chunks = std::min(n_chunks, n_tiles);
         int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
         std::vector<int> h_cnt((size_t)F);
+        const dim3 cgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
+        bool live = true;
         for (int c = 0; c < n_chunks; ++c) {
-            // live rays per light vertex (a few ints): lets the host stop early and size the ray blocks
+            // live rays per ray group (a few ints): lets the host stop early and size the work items
             CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
             CK_CUDA(cudaStreamSynchronize(st));
             int64_t n_live = 0;
-            for (int j = 0; j < F; ++j) n_live += h_cnt[j];
-            if (n_live == 0) break; // every shadow ray of this light already has its occluder
+            int n_groups_live = 0;
+            for (int j = 0; j < F; ++j) n_live += h_cnt[j], n_groups_live += h_cnt[j] > 0;
+            if (n_live == 0) { // every shadow ray of this light already has its occluder
+                live = false;
+                break;
+            }
             if (c == 0) { // build (once) the face tables of the groups that actually have rays
                 for (int gi = 0; gi < F; ++gi) {
                     if (!h_cnt[gi]) continue;
@@ -517,25 +545,32 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                     ++launches;
                 }
             }
-            const int Rk = pick_rays(n_live, g.n_sms, o.rays_per_thread);
-            const int rpb = sweep::THREADS * Rk;
-            int max_blocks = 0;
-            for (int j = 0; j < F; ++j) max_blocks += (h_cnt[j] + rpb - 1) / rpb;
+            const int tile_lo = (int)((int64_t)n_tiles * c / n_chunks), tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
+            const Decomp d = pick_decomp(n_live, tile_hi - tile_lo, g.n_sms, o.rays_per_thread, n_groups_live);
+            const int rpb = sweep::THREADS * d.R;
+            int n_blocks = 0;
+            for (int j = 0; j < F; ++j) n_blocks += (h_cnt[j] + rpb - 1) / rpb;
             trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, rpb, s->blk_off, cnt_out, s->work);
             CK_CUDA(cudaGetLastError());
             trk::ShadowParams sp{};
             sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
             sp.allcand = s->allcand_table;
-            sp.tile_lo = (int)((int64_t)n_tiles * c / n_chunks), sp.tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
-            sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.is_last = (c == n_chunks - 1), sp.tri_verts = s->tri_verts;
-            sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;
-            sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off;
-            sp.list_out = list_out, sp.cnt_out = cnt_out, sp.px = px;
+            sp.tile_lo = tile_lo, sp.tile_hi = tile_hi, sp.n_slices = d.n_slices;
+            sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
+            sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            const int grid = std::min(max_blocks, g.n_sms);
-            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, sp, grid, st)) return rc;
-            launches += 2;
+            const int grid = std::min(n_blocks * d.n_slices, g.n_sms);
+            if (int rc = launch_shadow(d.R, o.exhaustive_strict != 0, sp, grid, st)) return rc;
+            trk::compact_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, list_out, cnt_out);
+            CK_CUDA(cudaGetLastError());
+            launches += 3;
             std::swap(list_in, list_out), std::swap(cnt_in, cnt_out);
+        }
+        if (live && s->n_spheres > 0) { // extension: spheres come after all triangles in the object order
+            trk::shadow_spheres_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, px, n_px, s->spheres, s->n_spheres,
+                                                               s->n_tris);
+            CK_CUDA(cudaGetLastError());
+            ++launches;
         }
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
     }
