@@ -5,5 +5,5 @@ Only what the path needs: ``csrc/`` (CUDA kernels + C ABI, built into
 ``scenes`` (synthetic workloads), ``dist`` (row-band sharding across GPUs).
 """
 from .api import (RNG_EXPLICIT, RNG_HASH, RNG_MT19937, Camera, Frame, Renderer, ResidentScene, Scene,  # noqa: F401
-                  band_row_count, hash_faceids, mt19937_faceids)
+                  band_row_count, hash_faceids, mt19937_faceids, write_ppm)
 from ._lib import TracerError  # noqa: F401

@@ -19,6 +19,9 @@ ABI_SYMBOLS = [
     "tracer_cuda_render_scene", "tracer_cuda_last_stats", "tracer_band_row_count", "tracer_cuda_assemble_bands",
     "tracer_mt19937_faceids", "tracer_cuda_fp32_peak", "tracer_camera_lookat",
 ]
+# include/tracer_host.h
+HOST_SYMBOLS = ["tracer_scene_load_obj", "tracer_scene_host_flat", "tracer_scene_host_free", "tracer_host_last_error",
+                "tracer_write_ppm"]
 
 
 class TracerError(RuntimeError):
@@ -103,6 +106,13 @@ def load():
     lib.tracer_camera_lookat.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                          C.c_float, C.POINTER(CameraC)]
     lib.tracer_camera_lookat.restype = None
+    lib.tracer_scene_load_obj.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tracer_scene_host_flat.argtypes = [C.c_void_p]
+    lib.tracer_scene_host_flat.restype = C.POINTER(SceneFlat)
+    lib.tracer_scene_host_free.argtypes = [C.c_void_p]
+    lib.tracer_scene_host_free.restype = None
+    lib.tracer_host_last_error.restype = C.c_char_p
+    lib.tracer_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     _lib = lib
     return lib
 

@@ -82,6 +82,28 @@ class Scene:
         o = self.geom_tri_offset
         return np.array([o[g + 1] - o[g] for g in self.light_geom], np.int64)
 
+    @staticmethod
+    def load_obj(path: str) -> "Scene":
+        """model::loadobj (src/scene/sceneloader.cpp:14-106): OBJ/MTL -> scene, through the library's own
+        C++ loader (csrc/host_io.cpp).  Raises TracerError where the reference throws (e.g. any
+        loader warning, sceneloader.cpp:27-30)."""
+        lib = _lib.load()
+        h = C.c_void_p()
+        if lib.tracer_scene_load_obj(path.encode(), C.byref(h)) != 0:
+            raise TracerError(lib.tracer_host_last_error().decode())
+        try:
+            f = lib.tracer_scene_host_flat(h).contents
+            G = f.n_geoms
+            off = np.ctypeslib.as_array(f.geom_tri_offset, (G + 1,)).copy()
+            N = int(off[-1])
+            grab = lambda ptr, shape, dt: (np.ctypeslib.as_array(ptr, shape).astype(dt).copy() if int(np.prod(shape)) else np.zeros(shape, dt))
+            hasn = grab(f.geom_has_normals, (G,), np.int32)
+            return Scene(off, grab(f.tri_verts, (N, 3, 3), np.float32), grab(f.geom_material, (G, 13), np.float32),
+                         grab(f.light_geom, (f.n_lights,), np.int32),
+                         tri_normals=grab(f.tri_normals, (N, 3, 3), np.float32) if hasn.any() else None, geom_has_normals=hasn)
+        finally:
+            lib.tracer_scene_host_free(h)
+
     def c_struct(self) -> _lib.SceneFlat:
         s = _lib.SceneFlat()
         s.n_geoms = self.n_geoms
@@ -262,6 +284,15 @@ class Renderer:
         tf, ms = C.c_double(), C.c_double()
         _lib.check(self.lib.tracer_cuda_fp32_peak(variant, iters, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
+
+
+def write_ppm(path: str, rgb8: np.ndarray, binary: bool = False) -> None:
+    """The reference's PPM writer (src/main.cpp:658-689): ASCII P3, rows top to bottom; P6 when binary."""
+    a = np.ascontiguousarray(rgb8, np.uint8)
+    h, w = a.shape[0], a.shape[1]
+    lib = _lib.load()
+    if lib.tracer_write_ppm(path.encode(), a.ctypes.data_as(C.c_void_p), w, h, int(binary)) != 0:
+        raise TracerError(lib.tracer_host_last_error().decode())
 
 
 def mt19937_faceids(scene: Scene, width: int, height: int, seed: int, hit_mask) -> np.ndarray:

@@ -12,8 +12,8 @@ from conftest import ROOT, bits, load_golden, to_scene
 from esctp1raytracer_b200 import Camera, Scene, _lib, band_row_count, hash_faceids, mt19937_faceids, scenes
 
 
-def _header_functions():
-    src = open(os.path.join(ROOT, "include", "tracer_cuda.h")).read()
+def _header_functions(name="tracer_cuda.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(tracer_[a-z0-9_]+)\s*\(", src)))
 
@@ -26,6 +26,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in tracer_cuda.h but not exported"
     assert sorted(_lib.ABI_SYMBOLS) == declared
     assert lib.tracer_cuda_abi_version() == 1
+    host = _header_functions("tracer_host.h")
+    assert sorted(_lib.HOST_SYMBOLS) == host
+    for name in host:
+        assert hasattr(lib, name), f"{name} declared in tracer_host.h but not exported"
 
 
 def test_struct_sizes_match_c_layout(tmp_path):

@@ -6,6 +6,8 @@ to do better: ids, t, v, occlusion decisions and the float accumulator are expec
 BIT-IDENTICAL whenever ks == 0 (no powf), which these tests assert; with ks != 0 the
 float channels may differ by the device pow's rounding, and the u8 bar applies.
 """
+import os
+
 import numpy as np
 import pytest
 from conftest import bits, golden_names, load_golden, to_flat, to_scene
@@ -228,3 +230,42 @@ def test_fp32_peak_microbenchmark_runs(renderer):
     tf0, _ = renderer.fp32_peak(0, 3)
     tf1, _ = renderer.fp32_peak(1, 3)
     assert 10.0 < tf0 < 100.0 and 10.0 < tf1 < 100.0
+
+
+def test_cli_host_flow_obj_to_ppm(renderer, restated, tmp_path):
+    """The reference's whole flow (-m model.obj -v eye -l look -o out.ppm, src/main.cpp:417-695) through the C++ CLI:
+    our OBJ loader -> camera -> GPU render (std::mt19937 seeded) -> P3 writer, checked against the oracle."""
+    import subprocess
+
+    from conftest import ROOT
+    from esctp1raytracer_b200 import Scene, scenes
+
+    s = scenes.box_scene()
+    obj, mtl = tmp_path / "box.obj", tmp_path / "box.mtl"
+    with open(mtl, "w") as f:
+        for g in range(s.n_geoms):
+            m = s.geom_material[g]
+            f.write(f"newmtl m{g}\nKa {m[0]!r} {m[1]!r} {m[2]!r}\nKd {m[3]!r} {m[4]!r} {m[5]!r}\nKs {m[6]!r} {m[7]!r} {m[8]!r}\n"
+                    f"Ke {m[9]!r} {m[10]!r} {m[11]!r}\nNs {m[12]!r}\n")
+    with open(obj, "w") as f:
+        f.write("mtllib box.mtl\n")
+        for v in s.tri_verts.reshape(-1, 3):
+            f.write(f"v {v[0]!r} {v[1]!r} {v[2]!r}\n")
+        for g in range(s.n_geoms):
+            f.write(f"g geom{g}\nusemtl m{g}\n")
+            for t in range(s.geom_tri_offset[g], s.geom_tri_offset[g + 1]):
+                f.write(f"f {3 * t + 1} {3 * t + 2} {3 * t + 3}\n")
+    loaded = Scene.load_obj(str(obj))
+    assert np.array_equal(bits(loaded.tri_verts), bits(s.tri_verts)) and np.array_equal(loaded.light_geom, s.light_geom)
+    out = tmp_path / "out.ppm"
+    W, H, seed = 96, 72, 31
+    cli = os.path.join(ROOT, "esctp1raytracer_b200", "tracer_cli.bin")
+    r = subprocess.run([cli, "-m", str(obj), "-v", "0,1,2.9", "-l", "0,1,0", "-w", f"{W},{H}", "--seed", str(seed), "-o", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Duration" in r.stderr and "Rendered image in" in r.stdout
+    tok = out.read_text().split()
+    assert tok[:4] == ["P3", str(W), str(H), "255"]
+    got = np.array(tok[4:], dtype=np.int64).reshape(H, W, 3)
+    o = restated.render(to_flat(loaded), restated.camera((0, 1, 2.9), (0, 1, 0), W, H), W, H, seed=seed)
+    assert np.array_equal(got, o.rgb8)
