@@ -20,8 +20,38 @@ struct Cam {
 };
 
 // local pixel k (row-major over the PPM rows this rank renders) -> (w, h)
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
 struct Bands {
     int W, H, band_rows, band_index, band_count, n_px;
+    // extension (parity unpinned): spp_n x spp_n stratified jitter; sample = 0 .. spp_n^2-1
+    int spp_n, sample;
+    uint32_t seed;
+    // image-plane parameters of pixel (w,h): the reference's s = w/(W-1), t = h/(H-1) (main.cpp:709-710);
+    // with jitter, w and h are displaced inside the pixel's stratum first.  Strict arithmetic: the
+    // restatement (oracle/restated.c:pixel_st) computes the same bits.
+    __device__ __forceinline__ void pixel_st(int w, int h, float &s, float &t) const {
+        float fw = (float)w, fh = (float)h;
+        if (spp_n > 1) {
+            const uint32_t h1 = mix32(mix32((seed ^ 0x51ed270bu) + (uint32_t)(h * W + w)) ^ ((uint32_t)sample * 0x9e3779b1u + 0x7f4a7c15u));
+            const uint32_t h2 = mix32(h1 + 0x632be5abu);
+            const float u1 = __fmul_rn((float)(h1 >> 8), 5.9604644775390625e-08f);
+            const float u2 = __fmul_rn((float)(h2 >> 8), 5.9604644775390625e-08f);
+            const float jx = __fdiv_rn(__fadd_rn((float)(sample % spp_n), u1), (float)spp_n);
+            const float jy = __fdiv_rn(__fadd_rn((float)(sample / spp_n), u2), (float)spp_n);
+            fw = __fadd_rn(fw, __fsub_rn(jx, 0.5f));
+            fh = __fadd_rn(fh, __fsub_rn(jy, 0.5f));
+        }
+        s = __fdiv_rn(fw, (float)(W - 1));
+        t = __fdiv_rn(fh, (float)(H - 1));
+    }
     __host__ __device__ __forceinline__ void map(int k, int &w, int &h) const {
         const int lr = k / W;
         w = k - lr * W;
@@ -35,9 +65,9 @@ struct Bands {
 };
 
 // main.cpp:709-710 + camera.h:31-34, strict
-__device__ __forceinline__ f3 primary_dir(const Cam &c, int W, int H, int w, int h) {
-    const float s = __fdiv_rn((float)w, (float)(W - 1));
-    const float tt = __fdiv_rn((float)h, (float)(H - 1));
+__device__ __forceinline__ f3 primary_dir(const Cam &c, const Bands &b, int w, int h) {
+    float s, tt;
+    b.pixel_st(w, h, s, tt);
     const f3 o = strict::ld(c.o), llc = strict::ld(c.llc), hor = strict::ld(c.hor), ver = strict::ld(c.ver);
     return strict::normalize(strict::sub(strict::add(strict::add(llc, strict::mul(hor, s)), strict::mul(ver, tt)), o));
 }
@@ -201,9 +231,9 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             k = min(k, p.bands.n_px - 1);
             int w, h;
             p.bands.map(k, w, h);
-            const f3 d = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
-            // filter parameters: the reference's own (s,t) on the image plane (main.cpp:709-710)
-            rp[r] = __fdiv_rn((float)w, (float)(p.bands.W - 1)), rq[r] = __fdiv_rn((float)h, (float)(p.bands.H - 1));
+            const f3 d = primary_dir(p.cam, p.bands, w, h);
+            // filter parameters: the ray's own (s,t) on the image plane (main.cpp:709-710)
+            p.bands.pixel_st(w, h, rp[r], rq[r]);
             sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
             sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
             sm.t[r][tid] = FLT_MAX; // main.cpp:715-717
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(256) resolve_primary_kernel(Cam cam, Bands ban
         int w, h;
         bands.map(kpx, w, h);
         const f3 o = strict::ld(cam.o);
-        const f3 d = primary_dir(cam, bands.W, bands.H, w, h);
+        const f3 d = primary_dir(cam, bands, w, h);
         if (tri >= 0) {
             const float *q = tri_verts + 9 * (size_t)tri;
             strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v);
@@ -300,14 +330,6 @@ struct LightStepParams {
     int *dbg_occ;      // [n_px*L] or null
 };
 
-__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
-    x ^= x >> 16;
-    x *= 0x7feb352du;
-    x ^= x >> 15;
-    x *= 0x846ca68bu;
-    x ^= x >> 16;
-    return x;
-}
 // counter-based faceID: uniform in [0,F), keyed by (seed, image index, light)
 __host__ __device__ __forceinline__ int hash_faceid(uint32_t seed, uint32_t image_index, uint32_t light, uint32_t F) {
     uint32_t h = mix32((seed ^ 0x9e3779b9u) + image_index);
@@ -338,7 +360,7 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
             int w, h;
             p.bands.map(kpx, w, h);
             const f3 origin = strict::ld(p.cam.o);
-            const f3 dir = primary_dir(p.cam, p.bands.W, p.bands.H, w, h);
+            const f3 dir = primary_dir(p.cam, p.bands, w, h);
             const float *mat;
             f3 N;
             float t;
@@ -686,6 +708,16 @@ __global__ void quantise_kernel(const float *__restrict__ accum, int n_px, uint8
         for (int k = k0; k < min(k0 + 16, n_px); ++k)
             for (int c = 0; c < 3; ++c) rgb8[(size_t)k * 3 + c] = (uint8_t)quant(accum[(size_t)c * n_px + k]);
     }
+}
+
+// extension: sum of the per-sample colours (sample order fixed => deterministic), final mean
+__global__ void accumulate_kernel(const float *__restrict__ accum, float *__restrict__ total, size_t n3, int first, int last,
+                                  float n_samples) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    float v = first ? accum[i] : __fadd_rn(total[i], accum[i]);
+    if (last) v = __fdiv_rn(v, n_samples);
+    total[i] = v;
 }
 
 // hit mask in local pixel order (= the reference's scan order) for the mt19937 replay

@@ -74,6 +74,7 @@ struct tracer_scene_dev {
     float *hit_t = nullptr, *hit_v = nullptr, *carry = nullptr, *nrm = nullptr, *accum = nullptr, *ro = nullptr,
           *rd = nullptr, *re = nullptr, *rt = nullptr;
     uint8_t *rgb8 = nullptr, *mask = nullptr;
+    float *accum_total = nullptr;
     int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr;
     int maxF = 0;
     sweep::Counters *counters = nullptr;
@@ -90,7 +91,7 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
         dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->best), dev_free(s->best_occ), dev_free(s->list), dev_free(s->list_b);
         dev_free(s->faceid), dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
         dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
-        dev_free(s->dbg_occ);
+        dev_free(s->dbg_occ), dev_free(s->accum_total);
         s->ws_npx = 0;
         const size_t n = (size_t)n_px;
         int rc = 0;
@@ -231,7 +232,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
     dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables), dev_free(s->allcand_table);
     dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->best), dev_free(s->best_occ), dev_free(s->list), dev_free(s->list_b);
-    dev_free(s->faceid), dev_free(s->dbg_occ), dev_free(s->cnt_b);
+    dev_free(s->faceid), dev_free(s->dbg_occ), dev_free(s->cnt_b), dev_free(s->accum_total);
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
@@ -380,7 +381,16 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     tracer_render_opts o;
     std::memset(&o, 0, sizeof o);
     if (opts_in) std::memcpy(&o, opts_in, std::min<size_t>(sizeof o, opts_in->struct_size ? opts_in->struct_size : sizeof o));
-    if (o.samples_per_pixel > 1) return fail(TRACER_ERR_INVALID, "samples_per_pixel > 1 is not implemented yet");
+    // extension (parity unpinned): samples_per_pixel = n*n stratified jittered samples per pixel
+    int spp_n = 1;
+    if (o.samples_per_pixel > 1) {
+        spp_n = (int)std::lround(std::sqrt((double)o.samples_per_pixel));
+        if (spp_n * spp_n != o.samples_per_pixel || spp_n > 16)
+            return fail(TRACER_ERR_INVALID, "samples_per_pixel must be a square number <= 256");
+        if (o.rng_mode == TRACER_RNG_MT19937)
+            return fail(TRACER_ERR_INVALID, "TRACER_RNG_MT19937 reproduces the 1-sample serial path only");
+    }
+    const int S = spp_n * spp_n;
     const int band_count = o.band_count <= 1 ? 1 : o.band_count;
     const int band_rows = band_count > 1 ? o.band_rows : H;
     if (band_count > 1 && (band_rows <= 0 || o.band_index < 0 || o.band_index >= band_count))
@@ -406,6 +416,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     std::memcpy(dc.o, cam->origin, 12), std::memcpy(dc.llc, cam->lower_left_corner, 12);
     std::memcpy(dc.hor, cam->horizontal, 12), std::memcpy(dc.ver, cam->vertical, 12);
     trk::Bands bands{W, H, band_rows, band_count > 1 ? o.band_index : 0, band_count, n_px};
+    bands.spp_n = spp_n, bands.sample = 0, bands.seed = o.seed;
 
     // reach bound for shadow segments: len_k <= (k+1) * diag(bbox U eye)  (t carries over lights, main.cpp:764)
     double lo[3], hi[3], diag2 = 0;
@@ -438,7 +449,13 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
 
     const int n_tiles = s->n_pad / sweep::TILE;
+    double ms_primary_acc = 0, ms_shadow_acc = 0;
+    if (S > 1 && !s->accum_total && dev_alloc(&s->accum_total, 3 * (size_t)s->ws_npx)) return TRACER_ERR_NOMEM;
+    for (int smp = 0; smp < S; ++smp) {
+    bands.sample = smp;
+    const uint32_t seed_s = o.seed + (uint32_t)smp * 0x9e3779b1u; // faceID stream of this sample
     // ---- primary: raygen + closest hit ----------------------------------------------
+    CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
     CK_CUDA(cudaMemsetAsync(s->best, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
     CK_CUDA(cudaEventRecord(s->ev[1], st));
     {
@@ -458,7 +475,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaEventRecord(s->ev[2], st));
 
     // ---- faceIDs ------------------------------------------------------------------------
-    if (L > 0 && o.rng_mode == TRACER_RNG_EXPLICIT) {
+    if (smp == 0 && L > 0 && o.rng_mode == TRACER_RNG_EXPLICIT) {
         std::vector<int> loc((size_t)n_px * L);
         for (int k = 0; k < n_px; ++k) {
             int w, h;
@@ -467,7 +484,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         }
         CK_CUDA(cudaMemcpyAsync(s->faceid, loc.data(), loc.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CK_CUDA(cudaStreamSynchronize(st));
-    } else if (L > 0 && o.rng_mode == TRACER_RNG_MT19937) {
+    } else if (smp == 0 && L > 0 && o.rng_mode == TRACER_RNG_MT19937) {
         trk::hitmask_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->hit_tri, n_px, s->mask);
         CK_CUDA(cudaGetLastError());
         ++launches;
@@ -491,7 +508,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.tri_verts = s->tri_verts, lp.tri_normals = s->tri_normals, lp.tri_geom = s->tri_geom;
         lp.geom_has_normals = s->geom_has_normals, lp.geom_material = s->geom_material;
         lp.sphere_material = s->sphere_material, lp.spheres = s->spheres;
-        lp.rng_mode = o.rng_mode, lp.seed = o.seed, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
+        lp.rng_mode = o.rng_mode, lp.seed = seed_s, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
         lp.seg_count = s->seg_count, lp.counters = s->counters, lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
         if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
@@ -574,10 +591,27 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         }
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
     }
+    if (S > 1) { // sum the samples in a fixed order; the last pass divides by S
+        const size_t n3 = 3 * (size_t)n_px;
+        trk::accumulate_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(s->accum, s->accum_total, n3, smp == 0, smp == S - 1,
+                                                                              (float)S);
+        CK_CUDA(cudaGetLastError());
+        ++launches;
+        CK_CUDA(cudaStreamSynchronize(st));
+        float msx = 0;
+        cudaEventElapsedTime(&msx, s->ev[1], s->ev[2]);
+        ms_primary_acc += msx;
+        for (int k = 0; k < L; ++k) {
+            cudaEventElapsedTime(&msx, s->ev_shadow[2 * k], s->ev_shadow[2 * k + 1]);
+            ms_shadow_acc += msx;
+        }
+    }
+    } // samples
 
     // ---- quantise + pack ------------------------------------------------------------------
     uint8_t *dst8 = o.rgb_out_is_device ? rgb_out : s->rgb8;
-    trk::quantise_kernel<<<((n_px + 15) / 16 + 127) / 128, 128, 0, st>>>(s->accum, n_px, dst8);
+    const float *final_accum = S > 1 ? s->accum_total : s->accum;
+    trk::quantise_kernel<<<((n_px + 15) / 16 + 127) / 128, 128, 0, st>>>(final_accum, n_px, dst8);
     CK_CUDA(cudaGetLastError());
     ++launches;
     CK_CUDA(cudaEventRecord(s->ev[3], st));
@@ -592,7 +626,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     std::vector<float> acc;
     if (o.out_rgb) {
         acc.resize((size_t)n_px * 3);
-        CK_CUDA(cudaMemcpyAsync(acc.data(), s->accum, acc.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(cudaMemcpyAsync(acc.data(), final_accum, acc.size() * 4, cudaMemcpyDeviceToHost, st));
     }
     sweep::Counters hc;
     CK_CUDA(cudaMemcpyAsync(&hc, s->counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -605,15 +639,16 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     cudaEventElapsedTime(&ms, s->ev[0], s->ev[3]);
     s->stats.ms_total = ms;
     cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]);
-    s->stats.ms_primary = ms;
+    s->stats.ms_primary = S > 1 ? ms_primary_acc : ms;
     double sh = 0;
     for (int k = 0; k < L; ++k) {
         cudaEventElapsedTime(&ms, s->ev_shadow[2 * k], s->ev_shadow[2 * k + 1]);
         sh += ms;
     }
+    if (S > 1) sh = ms_shadow_acc;
     s->stats.ms_shadow = sh;
     s->stats.ms_other = s->stats.ms_total - s->stats.ms_primary - sh;
-    s->stats.n_primary_rays = n_px;
+    s->stats.n_primary_rays = (int64_t)n_px * S;
     s->stats.n_shadow_rays = (int64_t)hc.n_hits * L;
     s->stats.tests_primary = (int64_t)hc.tests_primary;
     s->stats.tests_shadow = (int64_t)hc.tests_shadow;

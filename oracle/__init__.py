@@ -221,6 +221,19 @@ class Restated:
         assert rc == 0
         return f
 
+    def render_spp(self, fs: FlatScene, cam12, W, H, seed, spp_n, n_threads=None):
+        """extension (parity unpinned): -> (rgb [P,3] float32 image order, rgb8 [H,W,3] PPM order)"""
+        n_threads = n_threads or os.cpu_count() or 1
+        s = self._scene(fs)
+        cam12 = np.ascontiguousarray(cam12, np.float32)
+        rgb = np.zeros((W * H, 3), np.float32)
+        rgb8 = np.zeros((H, W, 3), np.uint8)
+        self.lib.rst_render_spp.restype = C.c_int
+        rc = self.lib.rst_render_spp(C.byref(s), _ptr(cam12, C.c_float), W, H, C.c_uint32(seed), spp_n, n_threads,
+                                     _ptr(rgb, C.c_float), _ptr(rgb8, C.c_uint8))
+        assert rc == 0
+        return rgb, rgb8
+
     def render_pixels(self, fs: FlatScene, cam12, W, H, pw, ph, faceids, n_threads=None) -> OracleFrame:
         n_threads = n_threads or os.cpu_count() or 1
         s = self._scene(fs)

@@ -165,25 +165,40 @@ typedef struct {
     float t, v;
 } hit_rec;
 
-static inline v3 primary_dir(const float cam[12], int W, int H, int w, int h) {
-    /* main.cpp:709-710, camera.h:31-34 */
-    float s = (float)w / (W - 1);
-    float tt = (float)h / (H - 1);
+/* camera.h:31-34 for image-plane parameters (s, t) */
+static inline v3 dir_st(const float cam[12], float s, float tt) {
     v3 origin = ld3(cam), llc = ld3(cam + 3), hor = ld3(cam + 6), ver = ld3(cam + 9);
     return norm3(sub3(add3(add3(llc, mul3(hor, s)), mul3(ver, tt)), origin));
 }
 
-static hit_rec trace_primary(const rst_scene *sc, const float cam[12], int W, int H, int w, int h, int64_t *tests) {
+static inline v3 primary_dir(const float cam[12], int W, int H, int w, int h) {
+    /* main.cpp:709-710 */
+    float s = (float)w / (W - 1);
+    float tt = (float)h / (H - 1);
+    return dir_st(cam, s, tt);
+}
+
+static hit_rec trace_dir(const rst_scene *sc, const float cam[12], v3 dir, int64_t *tests) {
     hit_rec r;
     r.t = FLT_MAX; /* main.cpp:715-717 */
     r.v = 0;
-    r.tri = closest_hit(sc, ld3(cam), primary_dir(cam, W, H, w, h), &r.t, &r.v, tests);
+    r.tri = closest_hit(sc, ld3(cam), dir, &r.t, &r.v, tests);
     return r;
 }
 
+static hit_rec trace_primary(const rst_scene *sc, const float cam[12], int W, int H, int w, int h, int64_t *tests) {
+    return trace_dir(sc, cam, primary_dir(cam, W, H, w, h), tests);
+}
+
 /* ---- shading block, main.cpp:723-789 ------------------------------------- */
+static void shade_dir(const rst_scene *sc, const float cam[12], v3 dir, hit_rec hr, const int32_t *faceid, float rgb[3],
+                      int32_t *occ_tri, int64_t *tests);
 static void shade(const rst_scene *sc, const float cam[12], int W, int H, int w, int h, hit_rec hr,
                   const int32_t *faceid, float rgb[3], int32_t *occ_tri, int64_t *tests) {
+    shade_dir(sc, cam, primary_dir(cam, W, H, w, h), hr, faceid, rgb, occ_tri, tests);
+}
+static void shade_dir(const rst_scene *sc, const float cam[12], v3 dir, hit_rec hr, const int32_t *faceid, float rgb[3],
+                      int32_t *occ_tri, int64_t *tests) {
     rgb[0] = rgb[1] = rgb[2] = 0.f; /* vec3 ctor zero-fills, vec.h:44 */
     const int L = sc->n_lights;
     if (hr.tri < 0) {
@@ -192,7 +207,6 @@ static void shade(const rst_scene *sc, const float cam[12], int W, int H, int w,
     }
     const int n = n_tris_of(sc);
     v3 origin = ld3(cam);
-    v3 dir = primary_dir(cam, W, H, w, h);
     float t = hr.t;
     const float u = 0.f, v = hr.v;
     v3 N;
@@ -243,7 +257,7 @@ static void shade(const rst_scene *sc, const float cam[12], int W, int H, int w,
 
 /* main.cpp:679-684; u8 cannot hold the reference's negative / INT_MIN prints:
  * values are clamped into [0,255] (documented deviation for non-finite input). */
-static inline uint8_t quantise(float x) {
+static uint8_t quantise(float x) {
     x = (x > 1.f) ? 1.f : x;
     float y = x * 255;
     if (!(y >= 0.f)) return 0;
@@ -311,6 +325,99 @@ void rst_replay_faceids(const rst_scene *sc, int W, int H, uint32_t seed, const 
             }
         }
     }
+}
+
+/* ---- extension, parity unpinned: counter-based RNG and n x n stratified jitter ------------
+ * Restates the device's definitions (esctp1raytracer_b200/csrc/kernels.cuh: mix32, hash_faceid,
+ * Bands::pixel_st) so that the multi-sample path has a CPU checker; there is no reference code. */
+static uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+static int hash_faceid(uint32_t seed, uint32_t image_index, uint32_t light, uint32_t F) {
+    uint32_t h = mix32((seed ^ 0x9e3779b9u) + image_index);
+    h = mix32(h ^ (light * 0x85ebca6bu + 0xc2b2ae35u));
+    return (int)(((uint64_t)h * F) >> 32);
+}
+static void pixel_st(int W, int H, int w, int h, int spp_n, int sample, uint32_t seed, float *s, float *t) {
+    float fw = (float)w, fh = (float)h;
+    if (spp_n > 1) {
+        uint32_t h1 = mix32(mix32((seed ^ 0x51ed270bu) + (uint32_t)(h * W + w)) ^ ((uint32_t)sample * 0x9e3779b1u + 0x7f4a7c15u));
+        uint32_t h2 = mix32(h1 + 0x632be5abu);
+        float u1 = (float)(h1 >> 8) * 5.9604644775390625e-08f;
+        float u2 = (float)(h2 >> 8) * 5.9604644775390625e-08f;
+        float jx = ((float)(sample % spp_n) + u1) / (float)spp_n;
+        float jy = ((float)(sample / spp_n) + u2) / (float)spp_n;
+        fw = fw + (jx - 0.5f);
+        fh = fh + (jy - 0.5f);
+    }
+    *s = fw / (float)(W - 1);
+    *t = fh / (float)(H - 1);
+}
+
+typedef struct {
+    const rst_scene *sc;
+    const float *cam;
+    int W, H, spp_n, tid, n_threads;
+    uint32_t seed;
+    float *rgb;
+    uint8_t *rgb8;
+} spp_job;
+
+static uint8_t quantise(float x);
+
+static void *spp_worker(void *arg) {
+    spp_job *j = (spp_job *)arg;
+    const int L = j->sc->n_lights, S = j->spp_n * j->spp_n;
+    int64_t tests = 0;
+    for (int h = j->tid; h < j->H; h += j->n_threads) {
+        for (int w = 0; w < j->W; ++w) {
+            float total[3] = {0, 0, 0};
+            for (int smp = 0; smp < S; ++smp) {
+                float s, t, rgb[3];
+                int32_t fid[64];
+                pixel_st(j->W, j->H, w, h, j->spp_n, smp, j->seed, &s, &t);
+                v3 dir = dir_st(j->cam, s, t);
+                hit_rec hr = trace_dir(j->sc, j->cam, dir, &tests);
+                const uint32_t seed_s = j->seed + (uint32_t)smp * 0x9e3779b1u;
+                for (int l = 0; l < L; ++l) {
+                    int lg = j->sc->light_geom[l];
+                    uint32_t F = (uint32_t)(j->sc->geom_tri_offset[lg + 1] - j->sc->geom_tri_offset[lg]);
+                    fid[l] = hash_faceid(seed_s, (uint32_t)(h * j->W + w), (uint32_t)l, F);
+                }
+                shade_dir(j->sc, j->cam, dir, hr, fid, rgb, NULL, &tests);
+                for (int c = 0; c < 3; ++c) total[c] = smp == 0 ? rgb[c] : total[c] + rgb[c];
+            }
+            size_t i = (size_t)h * j->W + w, k = (size_t)(j->H - 1 - h) * j->W + w;
+            for (int c = 0; c < 3; ++c) {
+                float v = S > 1 ? total[c] / (float)S : total[c];
+                if (j->rgb) j->rgb[3 * i + c] = v;
+                if (j->rgb8) j->rgb8[3 * k + c] = quantise(v);
+            }
+        }
+    }
+    return NULL;
+}
+
+int rst_render_spp(const rst_scene *sc, const float cam[12], int W, int H, uint32_t seed, int spp_n, int n_threads, float *rgb,
+                   uint8_t *rgb8) {
+    if (sc->n_lights > 64 || spp_n < 1) return -1;
+    if (n_threads < 1) n_threads = 1;
+    spp_job *js = (spp_job *)malloc(sizeof(spp_job) * n_threads);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
+    for (int k = 0; k < n_threads; ++k) {
+        spp_job j = {sc, cam, W, H, spp_n, k, n_threads, seed, rgb, rgb8};
+        js[k] = j;
+        pthread_create(&th[k], NULL, spp_worker, &js[k]);
+    }
+    for (int k = 0; k < n_threads; ++k) pthread_join(th[k], NULL);
+    free(js);
+    free(th);
+    return 0;
 }
 
 /* ---- drivers --------------------------------------------------------------- */

@@ -65,6 +65,11 @@ int rst_render(const rst_scene *sc, const float cam[12], int W, int H, uint32_t 
 int rst_render_pixels(const rst_scene *sc, const float cam[12], int W, int H, int n, const int32_t *pw,
                       const int32_t *ph, const int32_t *faceids, int n_threads, rst_outputs *out);
 
+/* extension, parity unpinned (no reference code): spp_n x spp_n stratified jittered samples per pixel,
+ * counter-based faceIDs; rgb [P*3] image index order (mean over samples), rgb8 PPM order */
+int rst_render_spp(const rst_scene *sc, const float cam[12], int W, int H, uint32_t seed, int spp_n, int n_threads, float *rgb,
+                   uint8_t *rgb8);
+
 /* single-call known-answer entry: Moller-Trumbore exactly as ray_triangle.h:7-57 */
 int rst_intersect_triangle(const float orig[3], const float dir[3], const float v0[3], const float v1[3],
                            const float v2[3], float *t, float *u, float *v);

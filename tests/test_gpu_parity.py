@@ -244,12 +244,12 @@ def test_cli_host_flow_obj_to_ppm(renderer, restated, tmp_path):
     obj, mtl = tmp_path / "box.obj", tmp_path / "box.mtl"
     with open(mtl, "w") as f:
         for g in range(s.n_geoms):
-            m = s.geom_material[g]
+            m = [float(x) for x in s.geom_material[g]]
             f.write(f"newmtl m{g}\nKa {m[0]!r} {m[1]!r} {m[2]!r}\nKd {m[3]!r} {m[4]!r} {m[5]!r}\nKs {m[6]!r} {m[7]!r} {m[8]!r}\n"
                     f"Ke {m[9]!r} {m[10]!r} {m[11]!r}\nNs {m[12]!r}\n")
     with open(obj, "w") as f:
         f.write("mtllib box.mtl\n")
-        for v in s.tri_verts.reshape(-1, 3):
+        for v in s.tri_verts.reshape(-1, 3).tolist():
             f.write(f"v {v[0]!r} {v[1]!r} {v[2]!r}\n")
         for g in range(s.n_geoms):
             f.write(f"g geom{g}\nusemtl m{g}\n")
@@ -257,6 +257,7 @@ def test_cli_host_flow_obj_to_ppm(renderer, restated, tmp_path):
                 f.write(f"f {3 * t + 1} {3 * t + 2} {3 * t + 3}\n")
     loaded = Scene.load_obj(str(obj))
     assert np.array_equal(bits(loaded.tri_verts), bits(s.tri_verts)) and np.array_equal(loaded.light_geom, s.light_geom)
+    assert np.array_equal(bits(loaded.geom_material), bits(s.geom_material))
     out = tmp_path / "out.ppm"
     W, H, seed = 96, 72, 31
     cli = os.path.join(ROOT, "esctp1raytracer_b200", "tracer_cli.bin")
@@ -269,3 +270,23 @@ def test_cli_host_flow_obj_to_ppm(renderer, restated, tmp_path):
     got = np.array(tok[4:], dtype=np.int64).reshape(H, W, 3)
     o = restated.render(to_flat(loaded), restated.camera((0, 1, 2.9), (0, 1, 0), W, H), W, H, seed=seed)
     assert np.array_equal(got, o.rgb8)
+
+
+def test_multisample_jitter_extension(renderer, restated):
+    """n x n stratified jittered samples per pixel (BASELINE config 5; no reference code: parity unpinned,
+    oracle = our restatement).  Same strict arithmetic on both sides -> bit-equal mean colour."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, TracerError, scenes
+
+    s = scenes.soup_scene(3000, 12, 2, seed=4, edge=(0.05, 0.2), n_spheres=10)
+    W, H, seed = 64, 40, 17
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    for spp in (4, 9):
+        n = int(round(spp ** 0.5))
+        rgb, rgb8 = restated.render_spp(to_flat(s), cam.as_array(), W, H, seed, n)
+        out = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, samples_per_pixel=spp, debug=True)
+        assert np.array_equal(bits(out.rgb), bits(_to_ppm_order(rgb, W, H)))
+        assert np.array_equal(out.rgb8, rgb8)
+        assert out.stats["n_primary_rays"] == W * H * spp
+    with pytest.raises(TracerError):
+        renderer.trace(rs, cam, W, H, samples_per_pixel=5)  # not a square

@@ -128,3 +128,17 @@ def test_replay_consumes_three_draws_per_hit_light(restated):
     fid = restated.replay_faceids(fs, fr["W"], fr["H"], fr["seed"], fr["tri"] >= 0)
     assert np.array_equal(fid, fr["faceid"])
     assert (fid[fr["tri"] < 0] == -1).all()
+
+
+def test_spp_extension_reduces_to_single_sample(restated):
+    """rst_render_spp (unpinned extension) with 1 sample == the pinned path fed with the hash faceIDs"""
+    from esctp1raytracer_b200 import Camera, hash_faceids, scenes
+
+    s = scenes.box_scene()
+    W, H, seed = 48, 36, 5
+    cam = Camera.for_frame((0, 1, 2.9), (0, 1, 0), W, H).as_array()
+    rgb, rgb8 = restated.render_spp(to_flat(s), cam, W, H, seed, 1)
+    o = restated.render(to_flat(s), cam, W, H, faceid=hash_faceids(seed, W, H, s.faces_per_light))
+    assert np.array_equal(bits(rgb), bits(o.rgb)) and np.array_equal(rgb8, o.rgb8)
+    rgb4, _ = restated.render_spp(to_flat(s), cam, W, H, seed, 2)
+    assert not np.array_equal(rgb4, rgb) and abs(float(rgb4.mean()) - float(rgb.mean())) < 0.05
