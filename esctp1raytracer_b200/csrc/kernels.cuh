@@ -503,7 +503,10 @@ __global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const 
 
 // before each triangle chunk: live-ray counts per ray group -> ray-block offsets; reset the
 // survivors' counters and the work counter
-__global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block, int *blk_off, int *cnt_out, int *work) {
+// The triangle-slice count of the chunk is chosen here, on the device, from the live block count (so the
+// host never has to wait for it): enough (block, slice) items to keep every SM busy, >= 4 tiles per slice.
+__global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block, int n_tiles_chunk, int n_sms, int *blk_off,
+                                    int *cnt_out, int *work, int *n_slices_out) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int bo = 0;
         for (int j = 0; j < F; ++j) {
@@ -513,6 +516,9 @@ __global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block
         }
         blk_off[F] = bo;
         *work = 0;
+        const int possible = max(1, n_tiles_chunk / 4);
+        int sl = bo >= 6 * n_sms ? 1 : (6 * n_sms + max(bo, 1) - 1) / max(bo, 1);
+        *n_slices_out = max(1, min(sl, possible));
     }
 }
 
@@ -526,7 +532,8 @@ struct ShadowParams {
     const float4 *tables;  // face tables of the current light's vertices: group g=(j,f<6) at + (j*6+f)*table_stride
     const float4 *allcand; // table of group f == 6
     size_t table_stride;   // in float4
-    int tile_lo, tile_hi, n_slices, n_tris, F, n_px; // F = number of ray groups (light vertices * NFACE)
+    int tile_lo, tile_hi, n_tris, F, n_px; // F = number of ray groups (light vertices * NFACE)
+    const int *n_slices;                   // device: slices of this chunk (chunk_prefix_kernel)
     const float *tri_verts;
     const int *list_in, *seg_off, *cnt_in, *blk_off;
     PixelState px;
@@ -546,7 +553,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
     __syncthreads();
     const int n = p.n_px;
     const int total_blocks = p.blk_off[p.F];
-    const int n_items = total_blocks * p.n_slices;
+    const int n_slices = *p.n_slices;
+    const int n_items = total_blocks * n_slices;
     const int n_tiles = p.tile_hi - p.tile_lo;
     unsigned gtile = 0, n_strict = 0, n_miss = 0;
     unsigned long long tests = 0;
@@ -565,8 +573,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         __syncthreads();
         const int blk = sm.blk, j = sm.seg, slice = sm.base_out;
         if (blk < 0) break;
-        const int lo = p.tile_lo + (int)((long long)n_tiles * slice / p.n_slices);
-        const int hi = p.tile_lo + (int)((long long)n_tiles * (slice + 1) / p.n_slices);
+        const int lo = p.tile_lo + (int)((long long)n_tiles * slice / n_slices);
+        const int hi = p.tile_lo + (int)((long long)n_tiles * (slice + 1) / n_slices);
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
         float rp[R], rq[R];

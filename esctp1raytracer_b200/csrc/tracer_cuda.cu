@@ -75,7 +75,8 @@ struct tracer_scene_dev {
           *rd = nullptr, *re = nullptr, *rt = nullptr;
     uint8_t *rgb8 = nullptr, *mask = nullptr;
     float *accum_total = nullptr;
-    int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr;
+    int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr,
+        *n_slices = nullptr;
     int maxF = 0;
     sweep::Counters *counters = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -236,6 +237,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
+    dev_free(s->n_slices);
     dev_free(s->counters);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -362,6 +364,7 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     TRY(dev_alloc(&s->cursor, n_groups + 1));
     TRY(dev_alloc(&s->cnt_b, n_groups + 1));
     TRY(dev_alloc(&s->work, 1));
+    TRY(dev_alloc(&s->n_slices, 1));
     TRY(dev_alloc(&s->counters, 1));
     for (auto &e : s->ev) TRY_CUDA(cudaEventCreate(&e));
     s->ev_shadow.resize(2 * (size_t)std::max(1, s->n_lights));
@@ -530,16 +533,21 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         std::vector<int> h_cnt((size_t)F);
         const dim3 cgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
         bool live = true;
+        int Rk = 8;
         for (int c = 0; c < n_chunks; ++c) {
-            // live rays per ray group (a few ints): lets the host stop early and size the work items
-            CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
-            CK_CUDA(cudaStreamSynchronize(st));
-            int64_t n_live = 0;
-            int n_groups_live = 0;
-            for (int j = 0; j < F; ++j) n_live += h_cnt[j], n_groups_live += h_cnt[j] > 0;
-            if (n_live == 0) { // every shadow ray of this light already has its occluder
-                live = false;
-                break;
+            // The host looks at the live-ray counts only at the first chunk (which face tables to build, ray
+            // block size) and every 16th chunk (stop early); everything else is sized on the device, so
+            // the chunk launches queue back to back.
+            if (c % 16 == 0) {
+                CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+                CK_CUDA(cudaStreamSynchronize(st));
+                int64_t n_live = 0;
+                for (int j = 0; j < F; ++j) n_live += h_cnt[j];
+                if (n_live == 0) { // every shadow ray of this light already has its occluder
+                    live = false;
+                    break;
+                }
+                Rk = pick_decomp(n_live, n_tiles / n_chunks, g.n_sms, o.rays_per_thread, F).R;
             }
             if (c == 0) { // build (once) the face tables of the groups that actually have rays
                 for (int gi = 0; gi < F; ++gi) {
@@ -563,21 +571,17 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 }
             }
             const int tile_lo = (int)((int64_t)n_tiles * c / n_chunks), tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
-            const Decomp d = pick_decomp(n_live, tile_hi - tile_lo, g.n_sms, o.rays_per_thread, n_groups_live);
-            const int rpb = sweep::THREADS * d.R;
-            int n_blocks = 0;
-            for (int j = 0; j < F; ++j) n_blocks += (h_cnt[j] + rpb - 1) / rpb;
-            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, rpb, s->blk_off, cnt_out, s->work);
+            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::THREADS * Rk, tile_hi - tile_lo, g.n_sms, s->blk_off, cnt_out,
+                                                       s->work, s->n_slices);
             CK_CUDA(cudaGetLastError());
             trk::ShadowParams sp{};
             sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
             sp.allcand = s->allcand_table;
-            sp.tile_lo = tile_lo, sp.tile_hi = tile_hi, sp.n_slices = d.n_slices;
+            sp.tile_lo = tile_lo, sp.tile_hi = tile_hi, sp.n_slices = s->n_slices;
             sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
             sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            const int grid = std::min(n_blocks * d.n_slices, g.n_sms);
-            if (int rc = launch_shadow(d.R, o.exhaustive_strict != 0, sp, grid, st)) return rc;
+            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, sp, g.n_sms, st)) return rc;
             trk::compact_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, list_out, cnt_out);
             CK_CUDA(cudaGetLastError());
             launches += 3;
