@@ -233,7 +233,7 @@ class Renderer:
         if bands is not None:
             o.band_rows, o.band_index, o.band_count = bands
         o.exhaustive_strict = int(exhaustive)
-        o.rays_per_thread, o.shadow_chunks, o.samples_per_pixel = tuning
+        o.rays_per_thread, o.shadow_chunks, o.samples_per_pixel, o.bundle_cull = tuning
         dbg = {}
         if debug:
             L = scene.n_lights
@@ -245,7 +245,7 @@ class Renderer:
 
     def trace(self, scene, camera: Camera, width: int, height: int, *, rng_mode=RNG_HASH, seed=1, faceid=None,
               bands=None, exhaustive_strict=False, debug=False, out_device_ptr=None, stream=None,
-              rays_per_thread=0, shadow_chunks=0, samples_per_pixel=0) -> Frame:
+              rays_per_thread=0, shadow_chunks=0, samples_per_pixel=0, bundle_cull=False) -> Frame:
         """Render; ``scene`` is a Scene (one-shot: upload + render, the drop-in call) or a
         ResidentScene.  ``bands`` = (band_rows, band_index, band_count).  With
         ``out_device_ptr`` the packed rows are left in HBM at that address."""
@@ -254,7 +254,7 @@ class Renderer:
         n_px = rows * width
         keep = []
         o, dbg = self._opts(sc, width, height, rng_mode, seed, faceid, bands, exhaustive_strict, debug, n_px, keep,
-                            (rays_per_thread, shadow_chunks, samples_per_pixel))
+                            (rays_per_thread, shadow_chunks, samples_per_pixel, int(bundle_cull)))
         out = None
         if out_device_ptr is not None:
             o.rgb_out_is_device = 1

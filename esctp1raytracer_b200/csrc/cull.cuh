@@ -1,0 +1,157 @@
+// cull.cuh — OPTIONAL mode (opts.bundle_cull): hierarchical evaluation of the same conservative filter.
+//
+// The default sweeps (sweep.cuh) evaluate the three affine edge functions for every (ray, triangle)
+// pair: brute force, FP32-issue bound, the formulation BASELINE.json's north star prescribes.  Because
+// the edge functions are affine in the ray parameters (p,q), their maximum over an axis-aligned box of
+// (p,q) is attained at a corner:  max = A*pc + |A|*ph + B*qc + |B|*qh + C.  If that maximum is negative
+// for one of the three edges, NO ray inside the box can pass the filter.  So a bundle of rays that is
+// compact in (p,q) — a screen tile of primary rays, a cell of the light's cube face for shadow rays —
+// can reject a triangle for all of its rays with 12 FFMA, evaluated with one triangle per LANE instead
+// of one triangle per warp.  Every bundle still considers every triangle (there is no acceleration
+// structure and no build step), the survivors go through exactly the per-ray filter and the strict
+// path of the default mode, in index order, so results are bit-identical to the default mode
+// (tests/test_gpu_parity.py::test_bundle_cull_*).  What changes is the bound: the sweep becomes a
+// stream of the 48-byte rows through L2/shared memory (TMA), not FP32 issue.
+//
+// Levels: CTA box (all 512*R rays of the work item) tested by one thread per triangle of the staged
+// tile; the few survivors are then tested against each warp's box (warp-uniform), then per ray.
+#pragma once
+#include "sweep.cuh"
+
+namespace cull {
+
+constexpr int NC = 64;       // shadow rays are sorted into NC x NC cells per (light vertex, cube face)
+constexpr int CTA_WALK = 24; // CTA-box survivors per tile above which each warp culls the tile against its own box instead
+
+struct Box {
+    float pc, ph, qc, qh;
+};
+
+// sign word of the three edge-function maxima over the box: sign bit clear <=> all three >= 0
+__device__ __forceinline__ unsigned box_sign(const float4 rb, const float4 rc, const float4 rd, const Box b) {
+    const float x = fmaf(rb.x, b.pc, fmaf(fabsf(rb.x), b.ph, fmaf(rb.y, b.qc, fmaf(fabsf(rb.y), b.qh, rb.z))));
+    const float y = fmaf(rc.x, b.pc, fmaf(fabsf(rc.x), b.ph, fmaf(rc.y, b.qc, fmaf(fabsf(rc.y), b.qh, rc.z))));
+    const float z = fmaf(rd.x, b.pc, fmaf(fabsf(rd.x), b.ph, fmaf(rd.y, b.qc, fmaf(fabsf(rd.y), b.qh, rd.z))));
+    return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
+}
+
+// (min,max) ranges -> centre / half extent, slightly enlarged: the box evaluation rounds differently
+// from the per-ray evaluation, and must never be the stricter of the two
+__device__ __forceinline__ Box make_box(float pmin, float pmax, float qmin, float qmax) {
+    Box b;
+    b.pc = 0.5f * (pmin + pmax), b.qc = 0.5f * (qmin + qmax);
+    b.ph = 0.5f * (pmax - pmin) * 1.0001f + 1e-6f * (fabsf(b.pc) + 1.f);
+    b.qh = 0.5f * (qmax - qmin) * 1.0001f + 1e-6f * (fabsf(b.qc) + 1.f);
+    return b;
+}
+
+// warp box and CTA box of the rays held by this thread block (rp/rq of invalid rays must be duplicates
+// of valid ones).  scratch: 4 * THREADS/32 floats of shared memory.
+template <int R>
+__device__ __forceinline__ void bundle_boxes(const float (&rp)[R], const float (&rq)[R], float *scratch, Box &warp_box,
+                                             Box &cta_box) {
+    float pmin = rp[0], pmax = rp[0], qmin = rq[0], qmax = rq[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        pmin = fminf(pmin, rp[r]), pmax = fmaxf(pmax, rp[r]);
+        qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o)), pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+        qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o)), qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+    }
+    warp_box = make_box(pmin, pmax, qmin, qmax);
+    const int w = threadIdx.x >> 5, nw = sweep::THREADS / 32;
+    if ((threadIdx.x & 31) == 0) scratch[w] = pmin, scratch[nw + w] = pmax, scratch[2 * nw + w] = qmin, scratch[3 * nw + w] = qmax;
+    __syncthreads();
+    for (int i = 0; i < nw; ++i) {
+        pmin = fminf(pmin, scratch[i]), pmax = fmaxf(pmax, scratch[nw + i]);
+        qmin = fminf(qmin, scratch[2 * nw + i]), qmax = fmaxf(qmax, scratch[3 * nw + i]);
+    }
+    cta_box = make_box(pmin, pmax, qmin, qmax);
+    __syncthreads();
+}
+
+// ---- the culled sweep over tiles [tile_lo, tile_hi) -------------------------------------------------
+// cmask: TILE/32 words of shared memory.  Same TMA tile stream, same strict path as sweep::sweep_table.
+template <int R, bool ANYHIT>
+__device__ __forceinline__ void sweep_cull(sweep::Smem<R> &sm, unsigned *cmask, const float4 *__restrict__ table,
+                                           int tile_lo, int tile_hi, const float *__restrict__ tri_verts,
+                                           const float (&rp)[R], const float (&rq)[R], unsigned valid, unsigned &done,
+                                           unsigned &gtile, unsigned &n_strict, unsigned &n_tiles_swept, const Box cta_box,
+                                           const Box warp_box) {
+    using namespace sweep;
+    const int tid = threadIdx.x;
+    const int n_tiles = tile_hi - tile_lo;
+    const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
+    int last_issued = (n_tiles < STAGES ? n_tiles : STAGES) - 1;
+    if (tid == 0) {
+        for (int i = 0; i <= last_issued; ++i) {
+            const unsigned g = gtile + i;
+            mbar_expect_tx(&sm.full_bar[g % STAGES], TILE_BYTES);
+            tma_load_1d(sm.tile[g % STAGES], src + (size_t)i * TILE * 3, TILE_BYTES, &sm.full_bar[g % STAGES]);
+        }
+    }
+    bool stop = false;
+    int it = 0;
+    for (; it < n_tiles; ++it) {
+        const unsigned g = gtile + it;
+        const int s = g % STAGES;
+        mbar_wait(&sm.full_bar[s], (g / STAGES) & 1u);
+        const float4 *__restrict__ tp = sm.tile[s];
+        if (!stop && tid < TILE) { // level 0: one triangle per thread against the CTA box
+            const unsigned pass = (box_sign(tp[3 * tid], tp[3 * tid + 1], tp[3 * tid + 2], cta_box) >> 31) ^ 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if ((tid & 31) == 0) cmask[tid >> 5] = m;
+        }
+        __syncthreads();
+        if (!stop) {
+            ++n_tiles_swept;
+            int n_surv = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < TILE / 32; ++w8) n_surv += __popc(cmask[w8]);
+#pragma unroll 1
+            for (int w8 = 0; w8 < TILE / 32; ++w8) {
+                unsigned mm = cmask[w8];
+                if (n_surv > CTA_WALK && mm) {
+                    // the CTA box is not selective here (rays of the item are spread out): level 1 lane-parallel,
+                    // one triangle per lane against this warp's own box
+                    const int k = w8 * 32 + (tid & 31);
+                    const unsigned pass = ((mm >> (tid & 31)) & 1u) & ((box_sign(tp[3 * k], tp[3 * k + 1], tp[3 * k + 2], warp_box) >> 31) ^ 1u);
+                    mm = __ballot_sync(0xffffffffu, pass);
+                }
+                while (mm) { // survivors, in index order
+                    const int k = w8 * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
+                    if (n_surv <= CTA_WALK && (box_sign(rb, rc, rd, warp_box) >> 31)) continue; // level 1: warp box (warp-uniform)
+                    unsigned mask = 0;                                  // level 2: the per-ray filter of the default mode
+#pragma unroll
+                    for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                    mask &= valid & ~done;
+                    if (mask) {
+                        const unsigned nw = strict_tri<R, ANYHIT>(sm, tid, mask, (tile_lo + it) * TILE + k, tri_verts, n_strict);
+                        if (ANYHIT) done |= nw;
+                    }
+                }
+            }
+        }
+        const int all_done = __syncthreads_and((done | ~valid) == 0xffffffffu);
+        if (ANYHIT && all_done) stop = true;
+        if (!stop && it + STAGES < n_tiles) {
+            last_issued = it + STAGES;
+            if (tid == 0) {
+                mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
+                tma_load_1d(sm.tile[s], src + (size_t)last_issued * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
+            }
+        }
+        if (stop && it >= last_issued) {
+            ++it;
+            break;
+        }
+    }
+    gtile += it;
+}
+
+}  // namespace cull

@@ -9,6 +9,7 @@
 //   quantise_kernel      clamp + int(x*255) -> packed u8 RGB (main.cpp:679-684)
 //   assemble_bands_kernel  rank 0: band-packed rank buffers -> one frame
 #pragma once
+#include "cull.cuh"
 #include "sweep.cuh"
 
 namespace trk {
@@ -328,6 +329,7 @@ struct LightStepParams {
     int *seg_count;    // [F_k] histogram of rays per light vertex
     sweep::Counters *counters;
     int *dbg_occ;      // [n_px*L] or null
+    int cull_cells;    // 0: ray group = (faceID, cube face); NC: additionally the NC x NC cell of (p,q) (bundle-cull mode)
 };
 
 // counter-based faceID: uniform in [0,F), keyed by (seed, image index, light)
@@ -450,8 +452,18 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
                 const float db = c == 0 ? fd[2] : (c == 1 ? fd[0] : fd[1]); // axis (c+2)%3
                 p.px.re[kpx] = ok ? da * inv : 0.f;
                 p.px.re[n + kpx] = ok ? db * inv : 0.f;
-                p.px.rj[kpx] = fid * NFACE + face;
-                my_j = fid * NFACE + face;
+                int key = fid * NFACE + face;
+                if (p.cull_cells) { // sort key: group, then the Morton-ordered cell of (p,q) on the face
+                    const int nc = p.cull_cells;
+                    const int cx = ok ? min(nc - 1, max(0, (int)((da * inv + 1.f) * 0.5f * nc))) : 0;
+                    const int cy = ok ? min(nc - 1, max(0, (int)((db * inv + 1.f) * 0.5f * nc))) : 0;
+                    unsigned mx = cx, my = cy; // interleave (up to 8+8 bits)
+                    mx = (mx | (mx << 4)) & 0x0f0fu, mx = (mx | (mx << 2)) & 0x3333u, mx = (mx | (mx << 1)) & 0x5555u;
+                    my = (my | (my << 4)) & 0x0f0fu, my = (my | (my << 2)) & 0x3333u, my = (my | (my << 1)) & 0x5555u;
+                    key = key * (nc * nc) + (int)(mx | (my << 1));
+                }
+                p.px.rj[kpx] = key;
+                my_j = key;
             }
         }
     }
@@ -661,6 +673,213 @@ __global__ void shadow_spheres_kernel(const int *__restrict__ list, const int *_
                 break;
             }
     }
+}
+
+// ---------------------------------------------------------------------------------
+// OPTIONAL bundle-cull mode (cull.cuh): same results, hierarchical evaluation of the filter.
+struct PrimaryCullParams {
+    Cam cam;
+    Bands bands;
+    const float4 *table;
+    int n_tiles, n_tris, n_rows, tiles_x, tiles_y, n_slices;
+    const float *tri_verts;
+    unsigned long long *best;
+    sweep::Counters *counters;
+    int *work;
+};
+
+// work item = screen tile of 128 x 32 pixels (warp: 32 x 8) x triangle slice
+__global__ void __launch_bounds__(sweep::THREADS, 1) primary_cull_kernel(const PrimaryCullParams p) {
+    constexpr int R = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    __shared__ unsigned cmask[sweep::TILE / 32];
+    __shared__ float scratch[4 * sweep::THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        sweep::fence_barrier_init();
+    }
+    __syncthreads();
+    unsigned gtile = 0, n_strict = 0, n_swept = 0;
+    unsigned long long tests = 0;
+    const int n_blocks = p.tiles_x * p.tiles_y, n_items = n_blocks * p.n_slices;
+    const int W = p.bands.W;
+    for (;;) {
+        if (tid == 0) sm.blk = atomicAdd(p.work, 1);
+        __syncthreads();
+        const int item = sm.blk;
+        if (item >= n_items) break;
+        const int slice = item / n_blocks, blk = item - slice * n_blocks;
+        const int tile_lo = (int)((long long)p.n_tiles * slice / p.n_slices);
+        const int tile_hi = (int)((long long)p.n_tiles * (slice + 1) / p.n_slices);
+        const int ty = blk / p.tiles_x, tx = blk - ty * p.tiles_x;
+        const int x = tx * 128 + (warp & 3) * 32 + lane, y0 = ty * 32 + (warp >> 2) * 8;
+        float rp[R], rq[R];
+        int kp[R];
+        unsigned valid = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int ly = y0 + r;
+            if (x < W && ly < p.n_rows) valid |= 1u << r;
+            const int k = min(ly, p.n_rows - 1) * W + min(x, W - 1); // clamp: duplicates of valid rays keep the boxes tight
+            kp[r] = k;
+            int w, h;
+            p.bands.map(k, w, h);
+            const f3 d = primary_dir(p.cam, p.bands, w, h);
+            p.bands.pixel_st(w, h, rp[r], rq[r]);
+            sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
+            sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
+            sm.t[r][tid] = FLT_MAX;
+            sm.v[r][tid] = 0.f;
+            sm.tri[r][tid] = -1;
+        }
+        cull::Box wb, cb;
+        cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
+        unsigned done = 0;
+        cull::sweep_cull<R, false>(sm, cmask, p.table, tile_lo, tile_hi, p.tri_verts, rp, rq, valid, done, gtile, n_strict,
+                                   n_swept, cb, wb);
+        const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
+        tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int tri = sm.tri[r][tid];
+            if (((valid >> r) & 1u) && tri >= 0)
+                atomicMin(&p.best[kp[r]], ((unsigned long long)__float_as_uint(sm.t[r][tid]) << 32) | (unsigned)tri);
+        }
+        __syncthreads();
+    }
+    atomicAdd(&p.counters->tests_primary, tests);
+    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
+}
+
+// bins (group, cell) -> offsets; also the per-group segment offsets/counts and ray-block offsets
+__global__ void bins_prefix_kernel(const int *__restrict__ bin_count, int n_bins, int cells_per_group, int n_groups,
+                                   int rays_per_block, int n_tiles, int n_sms, int *__restrict__ bin_off, int *bin_cursor,
+                                   int *seg_off, int *seg_cnt, int *blk_off, int *work, int *n_slices_out) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x, per = (n_bins + 1023) / 1024;
+    const int b0 = min(t * per, n_bins), b1 = min(b0 + per, n_bins);
+    int s = 0;
+    for (int b = b0; b < b1; ++b) s += bin_count[b];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - s;
+    for (int b = b0; b < b1; ++b) {
+        bin_off[b] = run;
+        bin_cursor[b] = 0;
+        run += bin_count[b];
+    }
+    if (t == 1023) bin_off[n_bins] = part[1023];
+    __syncthreads();
+    if (t == 0) {
+        int bo = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            const int a = bin_off[g * cells_per_group], e = bin_off[(g + 1) * cells_per_group];
+            seg_off[g] = a, seg_cnt[g] = e - a, blk_off[g] = bo;
+            bo += (e - a + rays_per_block - 1) / rays_per_block;
+        }
+        seg_off[n_groups] = bin_off[n_bins];
+        blk_off[n_groups] = bo;
+        *work = 0;
+        const int possible = max(1, n_tiles / 4);
+        int sl = bo >= 6 * n_sms ? 1 : (6 * n_sms + max(bo, 1) - 1) / max(bo, 1);
+        *n_slices_out = max(1, min(sl, possible));
+    }
+}
+
+struct ShadowCullParams {
+    const float4 *tables;
+    const float4 *allcand;
+    size_t table_stride;
+    int n_tiles, n_tris, n_groups, n_px, cells_per_group;
+    const int *n_slices;
+    const float *tri_verts;
+    const int *list, *seg_off, *seg_cnt, *blk_off;
+    PixelState px;
+    sweep::Counters *counters;
+    int *work;
+};
+
+// work item = 512*8 consecutive rays of the cell-sorted list of one (light vertex, face) group x triangle slice
+__global__ void __launch_bounds__(sweep::THREADS, 1) shadow_cull_kernel(const ShadowCullParams p) {
+    constexpr int R = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    __shared__ unsigned cmask[sweep::TILE / 32];
+    __shared__ float scratch[4 * sweep::THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        sweep::fence_barrier_init();
+    }
+    __syncthreads();
+    const int n = p.n_px;
+    const int total_blocks = p.blk_off[p.n_groups];
+    const int n_slices = *p.n_slices;
+    const int n_items = total_blocks * n_slices;
+    unsigned gtile = 0, n_strict = 0;
+    unsigned long long tests = 0;
+    for (;;) {
+        if (tid == 0) {
+            const int it = atomicAdd(p.work, 1);
+            int j = 0, b = 0, sl = 0;
+            if (it < n_items) {
+                sl = it / total_blocks, b = it - sl * total_blocks;
+                while (b >= p.blk_off[j + 1]) ++j;
+            }
+            sm.blk = it < n_items ? b : -1;
+            sm.seg = j;
+            sm.base_out = sl;
+        }
+        __syncthreads();
+        const int blk = sm.blk, j = sm.seg, slice = sm.base_out;
+        if (blk < 0) break;
+        const int lo = (int)((long long)p.n_tiles * slice / n_slices), hi = (int)((long long)p.n_tiles * (slice + 1) / n_slices);
+        const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
+        const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane;
+        float rp[R], rq[R];
+        int kp[R];
+        unsigned valid = 0, done = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int e = base + r * 32; // a warp holds 32*R consecutive rays of the sorted list: a compact cell range
+            if (e < seg_end) valid |= 1u << r;
+            e = min(e, seg_end - 1);
+            const int k = p.list[e];
+            kp[r] = k;
+            rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
+            sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
+            sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
+            sm.t[r][tid] = p.px.rt[k];
+            sm.v[r][tid] = 0.f;
+            sm.tri[r][tid] = -1;
+            const unsigned long long seen = p.px.best_occ[k];
+            if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
+        }
+        cull::Box wb, cb;
+        cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
+        unsigned swept = 0;
+        const int face = j % NFACE;
+        const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
+        cull::sweep_cull<R, true>(sm, cmask, tab, lo, hi, p.tri_verts, rp, rq, valid, done, gtile, n_strict, swept, cb, wb);
+        tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int tri = sm.tri[r][tid];
+            if (((valid >> r) & 1u) && tri >= 0)
+                atomicMin(&p.px.best_occ[kp[r]], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(sm.t[r][tid]));
+        }
+        __syncthreads();
+    }
+    atomicAdd(&p.counters->tests_shadow, tests);
+    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
 }
 
 // ---------------------------------------------------------------------------------

@@ -75,6 +75,7 @@ struct tracer_scene_dev {
           *rd = nullptr, *re = nullptr, *rt = nullptr;
     uint8_t *rgb8 = nullptr, *mask = nullptr;
     float *accum_total = nullptr;
+    int *bin_count = nullptr, *bin_off = nullptr, *bin_cursor = nullptr;
     int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr,
         *n_slices = nullptr;
     int maxF = 0;
@@ -237,7 +238,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
-    dev_free(s->n_slices);
+    dev_free(s->n_slices), dev_free(s->bin_count), dev_free(s->bin_off), dev_free(s->bin_cursor);
     dev_free(s->counters);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -461,7 +462,22 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
     CK_CUDA(cudaMemsetAsync(s->best, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
     CK_CUDA(cudaEventRecord(s->ev[1], st));
-    {
+    if (o.bundle_cull) { // OPTIONAL bundle-cull mode: screen tiles of 128 x 32 pixels
+        trk::PrimaryCullParams p{};
+        p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris, p.n_rows = n_rows;
+        p.tiles_x = (W + 127) / 128, p.tiles_y = (n_rows + 31) / 32;
+        const int blocks = p.tiles_x * p.tiles_y;
+        p.n_slices = blocks >= 6 * g.n_sms ? 1 : std::max(1, std::min((6 * g.n_sms + blocks - 1) / blocks, std::max(1, n_tiles / 4)));
+        p.tri_verts = s->tri_verts, p.best = s->best, p.counters = s->counters, p.work = s->work;
+        const size_t smem = sizeof(sweep::Smem<8>);
+        CK_CUDA(cudaFuncSetAttribute(trk::primary_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, g.n_sms), sweep::THREADS, smem, st>>>(p);
+        CK_CUDA(cudaGetLastError());
+        trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
+                                                                        s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
+        CK_CUDA(cudaGetLastError());
+        launches += 2;
+    } else {
         const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0);
         trk::PrimaryParams p{};
         p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
@@ -501,6 +517,34 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     }
 
     // ---- lights: (finish k-1, set up k) -> group by light vertex -> first-occluder sweep ----
+    const bool cull = o.bundle_cull != 0;
+    const int cells = cull::NC * cull::NC;
+    if (cull && !s->bin_count) {
+        const size_t n_bins = (size_t)s->maxF * trk::NFACE * cells + 2;
+        if (dev_alloc(&s->bin_count, n_bins) || dev_alloc(&s->bin_off, n_bins) || dev_alloc(&s->bin_cursor, n_bins)) return TRACER_ERR_NOMEM;
+    }
+    auto build_face_tables = [&](int k, const std::vector<int> &group_cnt) -> int { // lazily, for groups that have rays
+        for (int gi = 0; gi < (int)group_cnt.size(); ++gi) {
+            if (!group_cnt[gi]) continue;
+            const int face = gi % trk::NFACE, vtx = s->h_light_vbase[k] + gi / trk::NFACE;
+            if (face == trk::NFACE - 1) {
+                if (!s->allcand_built) {
+                    trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table);
+                    CK_CUDA(cudaGetLastError());
+                    s->allcand_built = true, ++launches;
+                }
+                continue;
+            }
+            double &built = s->table_lmax[(size_t)vtx * 6 + face];
+            const double need = (k + 1) * diag;
+            if (built >= need) continue;
+            built = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
+            const trk::TableParam tp = face_param(&s->h_light_verts[3 * (size_t)vtx], face, built);
+            if (int rc = build_table(s, tp, s->light_tables + ((size_t)vtx * 6 + face) * s->table_stride, st)) return rc;
+            ++launches;
+        }
+        return 0;
+    };
     trk::PixelState px{s->best, s->best_occ, s->hit_tri, s->hit_t, s->hit_v, s->carry, s->nrm, s->accum,
                        s->ro,   s->rd,       s->re,      s->rt,    s->rj};
     for (int k = 0; k <= L; ++k) {
@@ -512,13 +556,52 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.geom_has_normals = s->geom_has_normals, lp.geom_material = s->geom_material;
         lp.sphere_material = s->sphere_material, lp.spheres = s->spheres;
         lp.rng_mode = o.rng_mode, lp.seed = seed_s, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
-        lp.seg_count = s->seg_count, lp.counters = s->counters, lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
-        if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
+        lp.seg_count = cull ? s->bin_count : s->seg_count, lp.counters = s->counters;
+        lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
+        lp.cull_cells = cull ? cull::NC : 0;
+        if (k < L && !cull) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
+        if (k < L && cull)
+            CK_CUDA(cudaMemsetAsync(s->bin_count, 0, sizeof(int) * ((size_t)s->h_light_F[k] * trk::NFACE * cells + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
         CK_CUDA(cudaGetLastError());
         ++launches;
         if (k == L) break;
         const int F = s->h_light_F[k] * trk::NFACE; // ray groups: (light vertex, cube face)
+        if (cull) {
+            // OPTIONAL bundle-cull mode: rays sorted by (group, cell), one culled sweep over all triangles per light
+            const int n_bins = F * cells, rpb = sweep::THREADS * 8;
+            trk::bins_prefix_kernel<<<1, 1024, 0, st>>>(s->bin_count, n_bins, cells, F, rpb, n_tiles, g.n_sms, s->bin_off, s->bin_cursor,
+                                                        s->seg_off, s->cursor, s->blk_off, s->work, s->n_slices);
+            CK_CUDA(cudaGetLastError());
+            trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->bin_off, s->bin_cursor, s->list);
+            CK_CUDA(cudaGetLastError());
+            CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
+            std::vector<int> gcnt((size_t)F);
+            CK_CUDA(cudaMemcpyAsync(gcnt.data(), s->cursor, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+            CK_CUDA(cudaStreamSynchronize(st));
+            CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
+            if (int rc = build_face_tables(k, gcnt)) return rc;
+            trk::ShadowCullParams sp{};
+            sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
+            sp.allcand = s->allcand_table, sp.n_tiles = n_tiles, sp.n_tris = s->n_tris, sp.n_groups = F, sp.n_px = n_px;
+            sp.cells_per_group = cells, sp.n_slices = s->n_slices, sp.tri_verts = s->tri_verts;
+            sp.list = s->list, sp.seg_off = s->seg_off, sp.seg_cnt = s->cursor, sp.blk_off = s->blk_off, sp.px = px;
+            sp.counters = s->counters, sp.work = s->work;
+            const size_t smem = sizeof(sweep::Smem<8>);
+            CK_CUDA(cudaFuncSetAttribute(trk::shadow_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trk::shadow_cull_kernel<<<g.n_sms, sweep::THREADS, smem, st>>>(sp);
+            CK_CUDA(cudaGetLastError());
+            launches += 3;
+            if (s->n_spheres > 0) {
+                const dim3 sgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
+                trk::shadow_spheres_kernel<<<sgrid, 256, 0, st>>>(s->list, s->seg_off, s->cursor, F, px, n_px, s->spheres, s->n_spheres,
+                                                                   s->n_tris);
+                CK_CUDA(cudaGetLastError());
+                ++launches;
+            }
+            CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
+            continue;
+        }
         trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
         CK_CUDA(cudaGetLastError());
         trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
@@ -549,27 +632,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 }
                 Rk = pick_decomp(n_live, n_tiles / n_chunks, g.n_sms, o.rays_per_thread, F).R;
             }
-            if (c == 0) { // build (once) the face tables of the groups that actually have rays
-                for (int gi = 0; gi < F; ++gi) {
-                    if (!h_cnt[gi]) continue;
-                    const int face = gi % trk::NFACE, vtx = s->h_light_vbase[k] + gi / trk::NFACE;
-                    if (face == trk::NFACE - 1) {
-                        if (!s->allcand_built) {
-                            trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table);
-                            CK_CUDA(cudaGetLastError());
-                            s->allcand_built = true, ++launches;
-                        }
-                        continue;
-                    }
-                    double &built = s->table_lmax[(size_t)vtx * 6 + face];
-                    const double need = (k + 1) * diag;
-                    if (built >= need) continue;
-                    built = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
-                    const trk::TableParam tp = face_param(&s->h_light_verts[3 * (size_t)vtx], face, built);
-                    if (int rc = build_table(s, tp, s->light_tables + ((size_t)vtx * 6 + face) * s->table_stride, st)) return rc;
-                    ++launches;
-                }
-            }
+            if (c == 0)
+                if (int rc = build_face_tables(k, h_cnt)) return rc;
             const int tile_lo = (int)((int64_t)n_tiles * c / n_chunks), tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
             trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::THREADS * Rk, tile_hi - tile_lo, g.n_sms, s->blk_off, cnt_out,
                                                        s->work, s->n_slices);

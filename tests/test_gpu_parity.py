@@ -290,3 +290,53 @@ def test_multisample_jitter_extension(renderer, restated):
         assert out.stats["n_primary_rays"] == W * H * spp
     with pytest.raises(TracerError):
         renderer.trace(rs, cam, W, H, samples_per_pixel=5)  # not a square
+
+
+def _same_frames(a, b):
+    assert np.array_equal(a.rgb8, b.rgb8)
+    assert np.array_equal(a.tri, b.tri) and np.array_equal(bits(a.t), bits(b.t)) and np.array_equal(bits(a.v), bits(b.v))
+    assert np.array_equal(a.occ_tri, b.occ_tri) and np.array_equal(bits(a.rgb), bits(b.rgb))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_bundle_cull_golden(renderer, name):
+    """OPTIONAL bundle-cull mode against the reference's own frames."""
+    from esctp1raytracer_b200 import RNG_EXPLICIT
+
+    fs, fr = load_golden(name)
+    W, H = fr["W"], fr["H"]
+    out = renderer.trace(renderer.upload(to_scene(fs)), _cam(fr), W, H, rng_mode=RNG_EXPLICIT, faceid=fr["faceid"], debug=True,
+                         bundle_cull=True)
+    _check_frame(out, W, H, fr["tri"], fr["t"], fr["v"], fr["rgb"], fr["q"], bool(fs.geom_material[:, 6:9].any()))
+
+
+def test_bundle_cull_identical_to_default(renderer):
+    """hierarchical evaluation of the same filter: every debug output bit-identical to the default mode"""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+
+    cases = [
+        (scenes.soup_scene(20000, 40, 4, seed=5), 96, 64, (0, 1, 3)),
+        (scenes.soup_scene(6000, 20, 2, seed=9, edge=(0.05, 0.2), with_normals=True, specular=True, n_spheres=30), 80, 60, (0, 1, 3)),
+        (scenes.coplanar_scene(), 120, 90, (0, 1, 2.9)),
+        (scenes.soup_scene(60000, 60, 4, seed=1), 333, 187, (0.3, 1.2, 2.7)),  # ragged tile edges
+    ]
+    for s, W, H, eye in cases:
+        cam = Camera.for_frame(eye, (0, 1, 0), W, H)
+        rs = renderer.upload(s)
+        a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True)
+        b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=True)
+        _same_frames(a, b)
+        assert b.stats["tests_shadow_ref"] == a.stats["tests_shadow_ref"] and b.stats["n_shadow_rays"] == a.stats["n_shadow_rays"]
+    # bands and multi-sample in cull mode
+    s, W, H = cases[0][0], 100, 77
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    full = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=4).rgb8
+    frame = np.zeros_like(full)
+    for r in range(3):
+        part = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=4, bands=(8, r, 3), bundle_cull=True).rgb8
+        frame[[pr for pr in range(H) if (pr // 8) % 3 == r]] = part
+    assert np.array_equal(frame, full)
+    a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=4, samples_per_pixel=4)
+    b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=4, samples_per_pixel=4, bundle_cull=True)
+    assert np.array_equal(a.rgb8, b.rgb8)

@@ -29,7 +29,7 @@ for n, W, H, L in cases:
     for it in range(3):
         t0 = time.time()
         out = r.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=1, rays_per_thread=int(os.environ.get('TRACER_RAYS', '0')),
-                      shadow_chunks=int(os.environ.get('TRACER_CHUNKS', '0')))
+                      shadow_chunks=int(os.environ.get('TRACER_CHUNKS', '0')), bundle_cull=bool(os.environ.get('TRACER_CULL')))
         wall = time.time() - t0
     st = out.stats
     ffma = 6.0
