@@ -154,4 +154,110 @@ __device__ __forceinline__ void sweep_cull(sweep::Smem<R> &sm, unsigned *cmask, 
     gtile += it;
 }
 
+// ---- wavefront variant: the culled sweep only EMITS the surviving (ray, triangle) pairs -----------------
+// In bundle-cull mode a tile of 256 triangles costs a few hundred cycles, so an in-line strict evaluation
+// (L2 round trip for the vertices + FP64 divide, one or two lanes active) would dominate and stall the
+// whole CTA at the tile barrier.  Instead the sweep appends ray<<32|triangle to a global buffer; the
+// buffer is sorted (ray major, triangle minor = the reference's iteration order per ray) and one thread
+// per ray then walks its candidates in order with the strict arithmetic (kernels.cuh: strict_*_from_candidates).
+constexpr int CTILE = 512;  // triangles per stage in emit mode: one per thread at level 0
+constexpr int CSTAGES = 4;
+constexpr uint32_t CTILE_BYTES = CTILE * 3 * sizeof(float4);
+
+struct __align__(128) EmitSmem {
+    float4 tile[CSTAGES][CTILE * 3];
+    uint64_t full_bar[CSTAGES];
+    unsigned cmask[CTILE / 32];
+    float scratch[4 * sweep::THREADS / 32];
+    int blk, seg, slice;
+};
+
+struct Emitter {
+    unsigned long long *buf, *count;
+    unsigned long long cap;
+};
+
+// tile_lo/tile_hi in units of CTILE triangles.  One barrier per tile in the common case (no survivor of the
+// CTA box in the tile): __syncthreads_or both publishes "any survivor" and proves that every thread is done
+// with the previous tile's stage, which thread 0 then refills.
+template <int R>
+__device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
+                                                const float (&rp)[R], const float (&rq)[R], unsigned valid,
+                                                const int (&ray_id)[R], unsigned &gtile, const Box cta_box, const Box warp_box,
+                                                const Emitter em) {
+    using namespace sweep;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_tiles = tile_hi - tile_lo;
+    const float4 *__restrict__ src = table + (size_t)tile_lo * CTILE * 3;
+    if (tid == 0) {
+        for (int i = 0; i < (n_tiles < CSTAGES ? n_tiles : CSTAGES); ++i) {
+            const unsigned g = gtile + i;
+            mbar_expect_tx(&sm.full_bar[g % CSTAGES], CTILE_BYTES);
+            tma_load_1d(sm.tile[g % CSTAGES], src + (size_t)i * CTILE * 3, CTILE_BYTES, &sm.full_bar[g % CSTAGES]);
+        }
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+        const unsigned g = gtile + it;
+        const int s = g % CSTAGES;
+        mbar_wait(&sm.full_bar[s], (g / CSTAGES) & 1u);
+        const float4 *__restrict__ tp = sm.tile[s];
+        // level 0: one triangle per thread against the CTA box
+        const unsigned pass = (box_sign(tp[3 * tid], tp[3 * tid + 1], tp[3 * tid + 2], cta_box) >> 31) ^ 1u;
+        const int any = __syncthreads_or((int)pass);
+        if (tid == 0 && it >= 1 && it - 1 + CSTAGES < n_tiles) { // the stage of the previous tile is free now
+            const unsigned gp = g - 1;
+            mbar_expect_tx(&sm.full_bar[gp % CSTAGES], CTILE_BYTES);
+            tma_load_1d(sm.tile[gp % CSTAGES], src + (size_t)(it - 1 + CSTAGES) * CTILE * 3, CTILE_BYTES, &sm.full_bar[gp % CSTAGES]);
+        }
+        if (!any) continue;
+        const unsigned m0 = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) sm.cmask[tid >> 5] = m0;
+        __syncthreads();
+        int n_surv = 0;
+#pragma unroll
+        for (int w = 0; w < CTILE / 32; ++w) n_surv += __popc(sm.cmask[w]);
+#pragma unroll 1
+        for (int w = 0; w < CTILE / 32; ++w) {
+            unsigned mm = sm.cmask[w];
+            if (!mm) continue;
+            if (n_surv > CTA_WALK) { // level 1 lane-parallel: one triangle per lane against this warp's box
+                const int k = w * 32 + lane;
+                const unsigned p1 = ((mm >> lane) & 1u) & ((box_sign(tp[3 * k], tp[3 * k + 1], tp[3 * k + 2], warp_box) >> 31) ^ 1u);
+                mm = __ballot_sync(0xffffffffu, p1);
+            }
+            while (mm) { // survivors, in index order (warp-uniform loop)
+                const int k = w * 32 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
+                if (n_surv <= CTA_WALK && (box_sign(rb, rc, rd, warp_box) >> 31)) continue; // level 1, warp-uniform
+                unsigned mask = 0;                                                          // level 2: per-ray filter
+#pragma unroll
+                for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                mask &= valid;
+                if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+                const int mine = __popc(mask); // warp-aggregated append
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(em.count, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - mine);
+                const unsigned tri = (unsigned)((tile_lo + it) * CTILE + k);
+                while (mask) {
+                    const int r = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (base < em.cap) em.buf[base] = ((unsigned long long)(unsigned)ray_id[r] << 32) | tri;
+                    ++base;
+                }
+            }
+        }
+    }
+    gtile += n_tiles;
+    __syncthreads(); // all stages consumed before the next item's prologue refills them
+}
+
 }  // namespace cull

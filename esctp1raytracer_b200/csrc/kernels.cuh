@@ -682,26 +682,23 @@ struct PrimaryCullParams {
     Bands bands;
     const float4 *table;
     int n_tiles, n_tris, n_rows, tiles_x, tiles_y, n_slices;
-    const float *tri_verts;
-    unsigned long long *best;
+    cull::Emitter em;
     sweep::Counters *counters;
     int *work;
 };
 
-// work item = screen tile of 128 x 32 pixels (warp: 32 x 8) x triangle slice
-__global__ void __launch_bounds__(sweep::THREADS, 1) primary_cull_kernel(const PrimaryCullParams p) {
+// work item = screen tile of 128 x 32 pixels (warp: 32 x 8) x triangle slice; emits candidate pairs
+__global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const PrimaryCullParams p) {
     constexpr int R = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
-    __shared__ unsigned cmask[sweep::TILE / 32];
-    __shared__ float scratch[4 * sweep::THREADS / 32];
+    cull::EmitSmem &sm = *reinterpret_cast<cull::EmitSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < cull::CSTAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
         sweep::fence_barrier_init();
     }
     __syncthreads();
-    unsigned gtile = 0, n_strict = 0, n_swept = 0;
+    unsigned gtile = 0;
     unsigned long long tests = 0;
     const int n_blocks = p.tiles_x * p.tiles_y, n_items = n_blocks * p.n_slices;
     const int W = p.bands.W;
@@ -726,31 +723,44 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_cull_kernel(const P
             kp[r] = k;
             int w, h;
             p.bands.map(k, w, h);
-            const f3 d = primary_dir(p.cam, p.bands, w, h);
             p.bands.pixel_st(w, h, rp[r], rq[r]);
-            sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
-            sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
-            sm.t[r][tid] = FLT_MAX;
-            sm.v[r][tid] = 0.f;
-            sm.tri[r][tid] = -1;
         }
         cull::Box wb, cb;
-        cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
-        unsigned done = 0;
-        cull::sweep_cull<R, false>(sm, cmask, p.table, tile_lo, tile_hi, p.tri_verts, rp, rq, valid, done, gtile, n_strict,
-                                   n_swept, cb, wb);
-        const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
+        cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
+        cull::sweep_cull_emit<R>(sm, p.table, tile_lo, tile_hi, rp, rq, valid, kp, gtile, cb, wb, p.em);
+        const int t_lo = min(tile_lo * cull::CTILE, p.n_tris), t_hi = min(tile_hi * cull::CTILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int tri = sm.tri[r][tid];
-            if (((valid >> r) & 1u) && tri >= 0)
-                atomicMin(&p.best[kp[r]], ((unsigned long long)__float_as_uint(sm.t[r][tid]) << 32) | (unsigned)tri);
-        }
         __syncthreads();
     }
     atomicAdd(&p.counters->tests_primary, tests);
-    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
+}
+
+// One thread per ray: walk the ray's candidates (sorted: triangle index ascending = the reference's iteration
+// order) with the strict arithmetic.  Closest hit: cpp_intersect semantics (main.cpp:176-192).
+__global__ void strict_primary_from_candidates(const unsigned long long *__restrict__ cand, unsigned long long n, Cam cam,
+                                               Bands bands, const float *__restrict__ tri_verts, unsigned long long *best,
+                                               sweep::Counters *counters) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_strict = 0;
+    if (i < n) {
+        const unsigned ray = (unsigned)(cand[i] >> 32);
+        if (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray) { // head of this ray's run
+            int w, h;
+            bands.map((int)ray, w, h);
+            const f3 o = strict::ld(cam.o), d = primary_dir(cam, bands, w, h);
+            float t = FLT_MAX, v = 0.f; // main.cpp:715-717
+            int tri = -1;
+            for (unsigned long long j = i; j < n && (unsigned)(cand[j] >> 32) == ray; ++j) {
+                const int tr = (int)(unsigned)(cand[j] & 0xffffffffu);
+                const float *q = tri_verts + 9 * (size_t)tr;
+                ++n_strict;
+                if (strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v)) tri = tr;
+            }
+            if (tri >= 0) best[ray] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri;
+        }
+    }
+    for (int o2 = 16; o2; o2 >>= 1) n_strict += __shfl_down_sync(0xffffffffu, n_strict, o2);
+    if ((threadIdx.x & 31) == 0 && n_strict) atomicAdd(&counters->strict_evals, (unsigned long long)n_strict);
 }
 
 // bins (group, cell) -> offsets; also the per-group segment offsets/counts and ray-block offsets
@@ -800,23 +810,21 @@ struct ShadowCullParams {
     size_t table_stride;
     int n_tiles, n_tris, n_groups, n_px, cells_per_group;
     const int *n_slices;
-    const float *tri_verts;
     const int *list, *seg_off, *seg_cnt, *blk_off;
     PixelState px;
+    cull::Emitter em;
     sweep::Counters *counters;
     int *work;
 };
 
 // work item = 512*8 consecutive rays of the cell-sorted list of one (light vertex, face) group x triangle slice
-__global__ void __launch_bounds__(sweep::THREADS, 1) shadow_cull_kernel(const ShadowCullParams p) {
+__global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const ShadowCullParams p) {
     constexpr int R = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
-    __shared__ unsigned cmask[sweep::TILE / 32];
-    __shared__ float scratch[4 * sweep::THREADS / 32];
+    cull::EmitSmem &sm = *reinterpret_cast<cull::EmitSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < cull::CSTAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
         sweep::fence_barrier_init();
     }
     __syncthreads();
@@ -824,7 +832,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_cull_kernel(const Sh
     const int total_blocks = p.blk_off[p.n_groups];
     const int n_slices = *p.n_slices;
     const int n_items = total_blocks * n_slices;
-    unsigned gtile = 0, n_strict = 0;
+    unsigned gtile = 0;
     unsigned long long tests = 0;
     for (;;) {
         if (tid == 0) {
@@ -836,17 +844,17 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_cull_kernel(const Sh
             }
             sm.blk = it < n_items ? b : -1;
             sm.seg = j;
-            sm.base_out = sl;
+            sm.slice = sl;
         }
         __syncthreads();
-        const int blk = sm.blk, j = sm.seg, slice = sm.base_out;
+        const int blk = sm.blk, j = sm.seg, slice = sm.slice;
         if (blk < 0) break;
         const int lo = (int)((long long)p.n_tiles * slice / n_slices), hi = (int)((long long)p.n_tiles * (slice + 1) / n_slices);
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane;
         float rp[R], rq[R];
         int kp[R];
-        unsigned valid = 0, done = 0;
+        unsigned valid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int e = base + r * 32; // a warp holds 32*R consecutive rays of the sorted list: a compact cell range
@@ -855,31 +863,43 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_cull_kernel(const Sh
             const int k = p.list[e];
             kp[r] = k;
             rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
-            sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
-            sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
-            sm.t[r][tid] = p.px.rt[k];
-            sm.v[r][tid] = 0.f;
-            sm.tri[r][tid] = -1;
-            const unsigned long long seen = p.px.best_occ[k];
-            if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
         }
         cull::Box wb, cb;
-        cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
-        unsigned swept = 0;
+        cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
         const int face = j % NFACE;
         const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-        cull::sweep_cull<R, true>(sm, cmask, tab, lo, hi, p.tri_verts, rp, rq, valid, done, gtile, n_strict, swept, cb, wb);
-        tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int tri = sm.tri[r][tid];
-            if (((valid >> r) & 1u) && tri >= 0)
-                atomicMin(&p.px.best_occ[kp[r]], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(sm.t[r][tid]));
-        }
+        cull::sweep_cull_emit<R>(sm, tab, lo, hi, rp, rq, valid, kp, gtile, cb, wb, p.em);
+        tests += (unsigned long long)(hi - lo) * cull::CTILE * __popc(valid);
         __syncthreads();
     }
     atomicAdd(&p.counters->tests_shadow, tests);
-    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
+}
+
+// One thread per shadow ray: occlusion() semantics (main.cpp:314-329) over the ray's sorted candidates:
+// the first accepted face in order ends the ray and leaves t = t2 behind.
+__global__ void strict_shadow_from_candidates(const unsigned long long *__restrict__ cand, unsigned long long n, PixelState px,
+                                              int n_px, const float *__restrict__ tri_verts, sweep::Counters *counters) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_strict = 0;
+    if (i < n) {
+        const unsigned ray = (unsigned)(cand[i] >> 32);
+        if (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray) {
+            const f3 o = strict::mk(px.ro[ray], px.ro[n_px + ray], px.ro[2 * (size_t)n_px + ray]);
+            const f3 d = strict::mk(px.rd[ray], px.rd[n_px + ray], px.rd[2 * (size_t)n_px + ray]);
+            float t = px.rt[ray], v;
+            for (unsigned long long j = i; j < n && (unsigned)(cand[j] >> 32) == ray; ++j) {
+                const int tr = (int)(unsigned)(cand[j] & 0xffffffffu);
+                const float *q = tri_verts + 9 * (size_t)tr;
+                ++n_strict;
+                if (strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v)) {
+                    px.best_occ[ray] = ((unsigned long long)(unsigned)tr << 32) | __float_as_uint(t);
+                    break;
+                }
+            }
+        }
+    }
+    for (int o2 = 16; o2; o2 >>= 1) n_strict += __shfl_down_sync(0xffffffffu, n_strict, o2);
+    if ((threadIdx.x & 31) == 0 && n_strict) atomicAdd(&counters->strict_evals, (unsigned long long)n_strict);
 }
 
 // ---------------------------------------------------------------------------------

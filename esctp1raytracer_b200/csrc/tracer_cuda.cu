@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "../../include/tracer_cuda.h"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kernels.cuh"
 
 extern "C" int tracer__mt19937_scan(uint32_t seed, int32_t n_lights, const int32_t *faces_per_light, int64_t n_px,
@@ -76,6 +78,10 @@ struct tracer_scene_dev {
     uint8_t *rgb8 = nullptr, *mask = nullptr;
     float *accum_total = nullptr;
     int *bin_count = nullptr, *bin_off = nullptr, *bin_cursor = nullptr;
+    // bundle-cull mode: candidate (ray<<32|triangle) buffers, their count, radix-sort scratch
+    unsigned long long *cand_a = nullptr, *cand_b = nullptr, *cand_count = nullptr;
+    size_t cand_cap = 0, sort_bytes = 0;
+    void *sort_tmp = nullptr;
     int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr,
         *n_slices = nullptr;
     int maxF = 0;
@@ -239,6 +245,8 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
     dev_free(s->n_slices), dev_free(s->bin_count), dev_free(s->bin_off), dev_free(s->bin_cursor);
+    dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count);
+    if (s->sort_tmp) cudaFree(s->sort_tmp);
     dev_free(s->counters);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -267,7 +275,7 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     CK_CUDA(cudaSetDevice(g.device));
     auto *s = new tracer_scene_dev();
     s->n_geoms = G, s->n_tris = N, s->n_lights = sc->n_lights, s->n_spheres = sc->n_spheres;
-    s->n_pad = std::max(1, (N + sweep::TILE - 1) / sweep::TILE) * sweep::TILE;
+    s->n_pad = std::max(1, (N + cull::CTILE - 1) / cull::CTILE) * cull::CTILE; // multiple of both tile sizes
     s->table_stride = (size_t)s->n_pad * 3;
 #define TRY(x)                         \
     do {                               \
@@ -453,6 +461,33 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
 
     const int n_tiles = s->n_pad / sweep::TILE;
+    const bool cull = o.bundle_cull != 0;
+    const int cells = cull::NC * cull::NC;
+    if (cull) { // candidate buffers: 24 per ray + slack (a few per ray are typical), sorted with a radix sort
+        const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
+        if (cap > s->cand_cap) {
+            dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count);
+            if (s->sort_tmp) cudaFree(s->sort_tmp);
+            s->sort_tmp = nullptr, s->cand_cap = 0;
+            if (dev_alloc(&s->cand_a, cap) || dev_alloc(&s->cand_b, cap) || dev_alloc(&s->cand_count, 1)) return TRACER_ERR_NOMEM;
+            CK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, s->sort_bytes, s->cand_a, s->cand_b, cap, 0, 64, st));
+            CK_CUDA(cudaMalloc(&s->sort_tmp, s->sort_bytes));
+            s->cand_cap = cap;
+        }
+    }
+    int ray_bits = 1;
+    while (((int64_t)1 << ray_bits) < n_px) ++ray_bits;
+    // candidates emitted by a culled sweep -> count (host), sorted ray-major / triangle-minor in cand_b
+    auto sort_candidates = [&](unsigned long long &n_cand) -> int {
+        CK_CUDA(cudaMemcpyAsync(&n_cand, s->cand_count, sizeof n_cand, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(cudaStreamSynchronize(st));
+        if (n_cand > s->cand_cap)
+            return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow (" + std::to_string(n_cand) + " pairs); use the default mode");
+        if (n_cand)
+            CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n_cand, 0, 32 + ray_bits, st));
+        ++launches;
+        return 0;
+    };
     double ms_primary_acc = 0, ms_shadow_acc = 0;
     if (S > 1 && !s->accum_total && dev_alloc(&s->accum_total, 3 * (size_t)s->ws_npx)) return TRACER_ERR_NOMEM;
     for (int smp = 0; smp < S; ++smp) {
@@ -462,21 +497,31 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
     CK_CUDA(cudaMemsetAsync(s->best, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
     CK_CUDA(cudaEventRecord(s->ev[1], st));
-    if (o.bundle_cull) { // OPTIONAL bundle-cull mode: screen tiles of 128 x 32 pixels
+    if (cull) { // OPTIONAL bundle-cull mode: screen tiles of 128 x 32 pixels -> candidates -> sort -> strict
         trk::PrimaryCullParams p{};
-        p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris, p.n_rows = n_rows;
+        const int c_tiles = s->n_pad / cull::CTILE;
+        p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = c_tiles, p.n_tris = s->n_tris, p.n_rows = n_rows;
         p.tiles_x = (W + 127) / 128, p.tiles_y = (n_rows + 31) / 32;
         const int blocks = p.tiles_x * p.tiles_y;
-        p.n_slices = blocks >= 6 * g.n_sms ? 1 : std::max(1, std::min((6 * g.n_sms + blocks - 1) / blocks, std::max(1, n_tiles / 4)));
-        p.tri_verts = s->tri_verts, p.best = s->best, p.counters = s->counters, p.work = s->work;
-        const size_t smem = sizeof(sweep::Smem<8>);
+        p.n_slices = blocks >= 12 * g.n_sms ? 1 : std::max(1, std::min((12 * g.n_sms + blocks - 1) / blocks, std::max(1, c_tiles / 8)));
+        p.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
+        p.counters = s->counters, p.work = s->work;
+        CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
+        const size_t smem = sizeof(cull::EmitSmem);
         CK_CUDA(cudaFuncSetAttribute(trk::primary_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, g.n_sms), sweep::THREADS, smem, st>>>(p);
+        trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, 2 * g.n_sms), sweep::THREADS, smem, st>>>(p);
         CK_CUDA(cudaGetLastError());
+        unsigned long long n_cand = 0;
+        if (int rc = sort_candidates(n_cand)) return rc;
+        if (n_cand) {
+            trk::strict_primary_from_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(s->cand_b, n_cand, dc, bands, s->tri_verts,
+                                                                                                 s->best, s->counters);
+            CK_CUDA(cudaGetLastError());
+        }
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
                                                                         s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
         CK_CUDA(cudaGetLastError());
-        launches += 2;
+        launches += 3;
     } else {
         const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0);
         trk::PrimaryParams p{};
@@ -517,8 +562,6 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     }
 
     // ---- lights: (finish k-1, set up k) -> group by light vertex -> first-occluder sweep ----
-    const bool cull = o.bundle_cull != 0;
-    const int cells = cull::NC * cull::NC;
     if (cull && !s->bin_count) {
         const size_t n_bins = (size_t)s->maxF * trk::NFACE * cells + 2;
         if (dev_alloc(&s->bin_count, n_bins) || dev_alloc(&s->bin_off, n_bins) || dev_alloc(&s->bin_cursor, n_bins)) return TRACER_ERR_NOMEM;
@@ -570,7 +613,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         if (cull) {
             // OPTIONAL bundle-cull mode: rays sorted by (group, cell), one culled sweep over all triangles per light
             const int n_bins = F * cells, rpb = sweep::THREADS * 8;
-            trk::bins_prefix_kernel<<<1, 1024, 0, st>>>(s->bin_count, n_bins, cells, F, rpb, n_tiles, g.n_sms, s->bin_off, s->bin_cursor,
+            trk::bins_prefix_kernel<<<1, 1024, 0, st>>>(s->bin_count, n_bins, cells, F, rpb, s->n_pad / cull::CTILE, 2 * g.n_sms, s->bin_off, s->bin_cursor,
                                                         s->seg_off, s->cursor, s->blk_off, s->work, s->n_slices);
             CK_CUDA(cudaGetLastError());
             trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->bin_off, s->bin_cursor, s->list);
@@ -583,15 +626,24 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             if (int rc = build_face_tables(k, gcnt)) return rc;
             trk::ShadowCullParams sp{};
             sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
-            sp.allcand = s->allcand_table, sp.n_tiles = n_tiles, sp.n_tris = s->n_tris, sp.n_groups = F, sp.n_px = n_px;
-            sp.cells_per_group = cells, sp.n_slices = s->n_slices, sp.tri_verts = s->tri_verts;
+            sp.allcand = s->allcand_table, sp.n_tiles = s->n_pad / cull::CTILE, sp.n_tris = s->n_tris, sp.n_groups = F, sp.n_px = n_px;
+            sp.cells_per_group = cells, sp.n_slices = s->n_slices;
             sp.list = s->list, sp.seg_off = s->seg_off, sp.seg_cnt = s->cursor, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            const size_t smem = sizeof(sweep::Smem<8>);
+            sp.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
+            CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
+            const size_t smem = sizeof(cull::EmitSmem);
             CK_CUDA(cudaFuncSetAttribute(trk::shadow_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            trk::shadow_cull_kernel<<<g.n_sms, sweep::THREADS, smem, st>>>(sp);
+            trk::shadow_cull_kernel<<<2 * g.n_sms, sweep::THREADS, smem, st>>>(sp);
             CK_CUDA(cudaGetLastError());
-            launches += 3;
+            unsigned long long n_cand = 0;
+            if (int rc = sort_candidates(n_cand)) return rc;
+            if (n_cand) {
+                trk::strict_shadow_from_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(s->cand_b, n_cand, px, n_px,
+                                                                                                    s->tri_verts, s->counters);
+                CK_CUDA(cudaGetLastError());
+            }
+            launches += 4;
             if (s->n_spheres > 0) {
                 const dim3 sgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
                 trk::shadow_spheres_kernel<<<sgrid, 256, 0, st>>>(s->list, s->seg_off, s->cursor, F, px, n_px, s->spheres, s->n_spheres,
