@@ -172,10 +172,25 @@ struct __align__(128) EmitSmem {
     int blk, seg, slice;
 };
 
+// Candidate output.  Each warp owns a private chunk of the global buffer (one atomicAdd per CHUNK entries,
+// so no atomic latency inside the tile loop: a warp stalled on an atomic would stall its whole CTA at the next
+// tile barrier); the unused tail of a warp's last chunk is filled with the all-ones sentinel, which sorts last.
+constexpr unsigned CHUNK = 1024;
+constexpr unsigned long long SENTINEL = 0xffffffffffffffffull;
 struct Emitter {
     unsigned long long *buf, *count;
     unsigned long long cap;
 };
+struct WarpChunk { // warp-uniform
+    unsigned long long base;
+    unsigned used;
+};
+__device__ __forceinline__ void chunk_close(const Emitter em, const WarpChunk wc) {
+    const int lane = threadIdx.x & 31;
+    if (wc.used >= CHUNK) return;
+    for (unsigned i = wc.used + lane; i < CHUNK; i += 32)
+        if (wc.base + i < em.cap) em.buf[wc.base + i] = SENTINEL;
+}
 
 // tile_lo/tile_hi in units of CTILE triangles.  One barrier per tile in the common case (no survivor of the
 // CTA box in the tile): __syncthreads_or both publishes "any survivor" and proves that every thread is done
@@ -184,11 +199,12 @@ template <int R>
 __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
                                                 const float (&rp)[R], const float (&rq)[R], unsigned valid,
                                                 const int (&ray_id)[R], unsigned &gtile, const Box cta_box, const Box warp_box,
-                                                const Emitter em) {
+                                                const Emitter em, WarpChunk &wc, sweep::Counters *diag) {
     using namespace sweep;
     const int tid = threadIdx.x, lane = tid & 31;
     const int n_tiles = tile_hi - tile_lo;
     const float4 *__restrict__ src = table + (size_t)tile_lo * CTILE * 3;
+    unsigned d_l0 = 0, d_l1 = 0, d_any = 0, d_fb = 0;
     if (tid == 0) {
         for (int i = 0; i < (n_tiles < CSTAGES ? n_tiles : CSTAGES); ++i) {
             const unsigned g = gtile + i;
@@ -216,6 +232,7 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
         int n_surv = 0;
 #pragma unroll
         for (int w = 0; w < CTILE / 32; ++w) n_surv += __popc(sm.cmask[w]);
+        d_l0 += n_surv, ++d_any, d_fb += n_surv > CTA_WALK;
 #pragma unroll 1
         for (int w = 0; w < CTILE / 32; ++w) {
             unsigned mm = sm.cmask[w];
@@ -231,6 +248,7 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
                 const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
                 if (n_surv <= CTA_WALK && (box_sign(rb, rc, rd, warp_box) >> 31)) continue; // level 1, warp-uniform
                 unsigned mask = 0;                                                          // level 2: per-ray filter
+                ++d_l1;
 #pragma unroll
                 for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
                 mask &= valid;
@@ -243,9 +261,14 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
                     if (lane >= o) incl += y;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(em.count, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - mine);
+                if (wc.used + (unsigned)total > CHUNK) { // rare: take a fresh chunk (the only atomic)
+                    chunk_close(em, wc);
+                    unsigned long long nb = 0;
+                    if (lane == 0) nb = atomicAdd(em.count, (unsigned long long)CHUNK);
+                    wc.base = __shfl_sync(0xffffffffu, nb, 0), wc.used = 0;
+                }
+                unsigned long long base = wc.base + wc.used + (unsigned long long)(incl - mine);
+                wc.used += (unsigned)total;
                 const unsigned tri = (unsigned)((tile_lo + it) * CTILE + k);
                 while (mask) {
                     const int r = __ffs(mask) - 1;
@@ -257,6 +280,11 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
         }
     }
     gtile += n_tiles;
+    if (diag && lane == 0) {
+        if (tid == 0) atomicAdd(&diag->cull_l0, (unsigned long long)d_l0), atomicAdd(&diag->cull_tiles_any, (unsigned long long)d_any),
+            atomicAdd(&diag->cull_tiles_fallback, (unsigned long long)d_fb);
+        atomicAdd(&diag->cull_l1, (unsigned long long)d_l1);
+    }
     __syncthreads(); // all stages consumed before the next item's prologue refills them
 }
 

@@ -700,6 +700,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
     __syncthreads();
     unsigned gtile = 0;
     unsigned long long tests = 0;
+    cull::WarpChunk wc{0, cull::CHUNK}; // no chunk yet
     const int n_blocks = p.tiles_x * p.tiles_y, n_items = n_blocks * p.n_slices;
     const int W = p.bands.W;
     for (;;) {
@@ -727,11 +728,12 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
         }
         cull::Box wb, cb;
         cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
-        cull::sweep_cull_emit<R>(sm, p.table, tile_lo, tile_hi, rp, rq, valid, kp, gtile, cb, wb, p.em);
+        cull::sweep_cull_emit<R>(sm, p.table, tile_lo, tile_hi, rp, rq, valid, kp, gtile, cb, wb, p.em, wc, nullptr);
         const int t_lo = min(tile_lo * cull::CTILE, p.n_tris), t_hi = min(tile_hi * cull::CTILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
         __syncthreads();
     }
+    cull::chunk_close(p.em, wc);
     atomicAdd(&p.counters->tests_primary, tests);
 }
 
@@ -744,7 +746,7 @@ __global__ void strict_primary_from_candidates(const unsigned long long *__restr
     unsigned n_strict = 0;
     if (i < n) {
         const unsigned ray = (unsigned)(cand[i] >> 32);
-        if (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray) { // head of this ray's run
+        if (ray != 0xffffffffu && (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray)) { // head of this ray's run
             int w, h;
             bands.map((int)ray, w, h);
             const f3 o = strict::ld(cam.o), d = primary_dir(cam, bands, w, h);
@@ -798,8 +800,10 @@ __global__ void bins_prefix_kernel(const int *__restrict__ bin_count, int n_bins
         seg_off[n_groups] = bin_off[n_bins];
         blk_off[n_groups] = bo;
         *work = 0;
-        const int possible = max(1, n_tiles / 4);
-        int sl = bo >= 6 * n_sms ? 1 : (6 * n_sms + max(bo, 1) - 1) / max(bo, 1);
+        // many more items than CTA slots: the cost of an item varies a lot with how selective its boxes are,
+        // and the longest item bounds the tail of the launch
+        const int possible = max(1, n_tiles / 16);
+        int sl = bo >= 24 * n_sms ? 1 : (24 * n_sms + max(bo, 1) - 1) / max(bo, 1);
         *n_slices_out = max(1, min(sl, possible));
     }
 }
@@ -834,6 +838,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const Sh
     const int n_items = total_blocks * n_slices;
     unsigned gtile = 0;
     unsigned long long tests = 0;
+    cull::WarpChunk wc{0, cull::CHUNK}; // no chunk yet
     for (;;) {
         if (tid == 0) {
             const int it = atomicAdd(p.work, 1);
@@ -868,10 +873,11 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const Sh
         cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
         const int face = j % NFACE;
         const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-        cull::sweep_cull_emit<R>(sm, tab, lo, hi, rp, rq, valid, kp, gtile, cb, wb, p.em);
+        cull::sweep_cull_emit<R>(sm, tab, lo, hi, rp, rq, valid, kp, gtile, cb, wb, p.em, wc, p.counters);
         tests += (unsigned long long)(hi - lo) * cull::CTILE * __popc(valid);
         __syncthreads();
     }
+    cull::chunk_close(p.em, wc);
     atomicAdd(&p.counters->tests_shadow, tests);
 }
 
@@ -883,7 +889,7 @@ __global__ void strict_shadow_from_candidates(const unsigned long long *__restri
     unsigned n_strict = 0;
     if (i < n) {
         const unsigned ray = (unsigned)(cand[i] >> 32);
-        if (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray) {
+        if (ray != 0xffffffffu && (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray)) {
             const f3 o = strict::mk(px.ro[ray], px.ro[n_px + ray], px.ro[2 * (size_t)n_px + ray]);
             const f3 d = strict::mk(px.rd[ray], px.rd[n_px + ray], px.rd[2 * (size_t)n_px + ray]);
             float t = px.rt[ray], v;

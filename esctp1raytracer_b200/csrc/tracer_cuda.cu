@@ -484,7 +484,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         if (n_cand > s->cand_cap)
             return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow (" + std::to_string(n_cand) + " pairs); use the default mode");
         if (n_cand)
-            CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n_cand, 0, 32 + ray_bits, st));
+            CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n_cand, 0, 33 + ray_bits, st));
         ++launches;
         return 0;
     };
@@ -776,6 +776,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.strict_evals = (int64_t)hc.strict_evals;
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.kernel_launches = launches;
+    if (getenv("TRACER_CULL_DIAG"))
+        fprintf(stderr, "cull diag (shadow): l0 survivors %llu, tiles with any %llu, fallback tiles %llu, l1 warp-passes %llu, item-tiles %llu\n", hc.cull_l0,
+                hc.cull_tiles_any, hc.cull_tiles_fallback, hc.cull_l1, (unsigned long long)(hc.tests_shadow / 4096 / cull::CTILE));
     return TRACER_OK;
 }
 
