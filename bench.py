@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cull", action="store_true", help="skip the extra measurement of the optional bundle-cull mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,6 +246,29 @@ def main():
     rays = tot["n_primary_rays"] + tot["n_shadow_rays"]
     value = rays / (ms * 1e-3) / 1e6
     launches = int(tot["kernel_launches"]) + (args.steps if world > 1 else 0)
+
+    # ---- extra: the OPTIONAL bundle-cull mode (same frame, hierarchical evaluation of the same filter) ------
+    cull_extra = None
+    if not args.no_cull:
+        frame_ref, _ = tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed)
+        for _ in range(2):
+            frame_c, _ = tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=True)
+        same = bool(torch.equal(frame_ref, frame_c)) if rank == 0 else True
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(args.steps):
+            tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=True)
+        c1.record()
+        barrier()
+        cms = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+        cull_extra = {"value": rays / (float(cms[0]) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(cms[0]) / args.steps,
+                      "frame_identical_to_default_mode": same,
+                      "note": "opts.bundle_cull: bundle box -> warp box -> per-ray filter -> strict; every bundle still tests every "
+                              "triangle, results bit-identical; bound by the L2 stream of the 48-byte rows, not FP32 issue. "
+                              "Reported beside the headline, which stays on the brute-force per-ray formulation of the north star."}
 
     # ---- e2e: the drop-in call with host buffers --------------------------------------------
     e2e = None
@@ -324,7 +348,7 @@ def main():
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
                         "streams": "filter tables (48 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
             },
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "optional_bundle_cull_mode": cull_extra,
             "rays_per_step": rays / args.steps, "strict_evals_per_step": tot["strict_evals"] / args.steps,
         }
         print(json.dumps(line))

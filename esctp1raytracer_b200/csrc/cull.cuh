@@ -15,12 +15,13 @@
 //
 // Levels: CTA box (all 512*R rays of the work item) tested by one thread per triangle of the staged
 // tile; the few survivors are then tested against each warp's box (warp-uniform), then per ray.
+// Shadow rays are first ordered by (light vertex, cube face, Morton code of (p,q)) with a radix sort so
+// that consecutive rays form compact bundles.
 #pragma once
 #include "sweep.cuh"
 
 namespace cull {
 
-constexpr int NC = 64;       // shadow rays are sorted into NC x NC cells per (light vertex, cube face)
 constexpr int CTA_WALK = 24; // CTA-box survivors per tile above which each warp culls the tile against its own box instead
 
 struct Box {
@@ -73,88 +74,7 @@ __device__ __forceinline__ void bundle_boxes(const float (&rp)[R], const float (
     __syncthreads();
 }
 
-// ---- the culled sweep over tiles [tile_lo, tile_hi) -------------------------------------------------
-// cmask: TILE/32 words of shared memory.  Same TMA tile stream, same strict path as sweep::sweep_table.
-template <int R, bool ANYHIT>
-__device__ __forceinline__ void sweep_cull(sweep::Smem<R> &sm, unsigned *cmask, const float4 *__restrict__ table,
-                                           int tile_lo, int tile_hi, const float *__restrict__ tri_verts,
-                                           const float (&rp)[R], const float (&rq)[R], unsigned valid, unsigned &done,
-                                           unsigned &gtile, unsigned &n_strict, unsigned &n_tiles_swept, const Box cta_box,
-                                           const Box warp_box) {
-    using namespace sweep;
-    const int tid = threadIdx.x;
-    const int n_tiles = tile_hi - tile_lo;
-    const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
-    int last_issued = (n_tiles < STAGES ? n_tiles : STAGES) - 1;
-    if (tid == 0) {
-        for (int i = 0; i <= last_issued; ++i) {
-            const unsigned g = gtile + i;
-            mbar_expect_tx(&sm.full_bar[g % STAGES], TILE_BYTES);
-            tma_load_1d(sm.tile[g % STAGES], src + (size_t)i * TILE * 3, TILE_BYTES, &sm.full_bar[g % STAGES]);
-        }
-    }
-    bool stop = false;
-    int it = 0;
-    for (; it < n_tiles; ++it) {
-        const unsigned g = gtile + it;
-        const int s = g % STAGES;
-        mbar_wait(&sm.full_bar[s], (g / STAGES) & 1u);
-        const float4 *__restrict__ tp = sm.tile[s];
-        if (!stop && tid < TILE) { // level 0: one triangle per thread against the CTA box
-            const unsigned pass = (box_sign(tp[3 * tid], tp[3 * tid + 1], tp[3 * tid + 2], cta_box) >> 31) ^ 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if ((tid & 31) == 0) cmask[tid >> 5] = m;
-        }
-        __syncthreads();
-        if (!stop) {
-            ++n_tiles_swept;
-            int n_surv = 0;
-#pragma unroll
-            for (int w8 = 0; w8 < TILE / 32; ++w8) n_surv += __popc(cmask[w8]);
-#pragma unroll 1
-            for (int w8 = 0; w8 < TILE / 32; ++w8) {
-                unsigned mm = cmask[w8];
-                if (n_surv > CTA_WALK && mm) {
-                    // the CTA box is not selective here (rays of the item are spread out): level 1 lane-parallel,
-                    // one triangle per lane against this warp's own box
-                    const int k = w8 * 32 + (tid & 31);
-                    const unsigned pass = ((mm >> (tid & 31)) & 1u) & ((box_sign(tp[3 * k], tp[3 * k + 1], tp[3 * k + 2], warp_box) >> 31) ^ 1u);
-                    mm = __ballot_sync(0xffffffffu, pass);
-                }
-                while (mm) { // survivors, in index order
-                    const int k = w8 * 32 + __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
-                    if (n_surv <= CTA_WALK && (box_sign(rb, rc, rd, warp_box) >> 31)) continue; // level 1: warp box (warp-uniform)
-                    unsigned mask = 0;                                  // level 2: the per-ray filter of the default mode
-#pragma unroll
-                    for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
-                    mask &= valid & ~done;
-                    if (mask) {
-                        const unsigned nw = strict_tri<R, ANYHIT>(sm, tid, mask, (tile_lo + it) * TILE + k, tri_verts, n_strict);
-                        if (ANYHIT) done |= nw;
-                    }
-                }
-            }
-        }
-        const int all_done = __syncthreads_and((done | ~valid) == 0xffffffffu);
-        if (ANYHIT && all_done) stop = true;
-        if (!stop && it + STAGES < n_tiles) {
-            last_issued = it + STAGES;
-            if (tid == 0) {
-                mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
-                tma_load_1d(sm.tile[s], src + (size_t)last_issued * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
-            }
-        }
-        if (stop && it >= last_issued) {
-            ++it;
-            break;
-        }
-    }
-    gtile += it;
-}
-
-// ---- wavefront variant: the culled sweep only EMITS the surviving (ray, triangle) pairs -----------------
+// ---- the culled sweep only EMITS the surviving (ray, triangle) pairs (wavefront organisation) ----------
 // In bundle-cull mode a tile of 256 triangles costs a few hundred cycles, so an in-line strict evaluation
 // (L2 round trip for the vertices + FP64 divide, one or two lanes active) would dominate and stall the
 // whole CTA at the tile barrier.  Instead the sweep appends ray<<32|triangle to a global buffer; the

@@ -329,7 +329,8 @@ struct LightStepParams {
     int *seg_count;    // [F_k] histogram of rays per light vertex
     sweep::Counters *counters;
     int *dbg_occ;      // [n_px*L] or null
-    int cull_cells;    // 0: ray group = (faceID, cube face); NC: additionally the NC x NC cell of (p,q) (bundle-cull mode)
+    int cull_cells;    // != 0: bundle-cull mode, also write the 64-bit sort key (group << 32 | Morton code of (p,q))
+    unsigned long long *rkey; // [n_px] sort keys (bundle-cull mode), all-ones for pixels without a shadow ray
 };
 
 // counter-based faceID: uniform in [0,F), keyed by (seed, image index, light)
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
     const int kpx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = kpx < p.bands.n_px;
     int my_j = -1;
-    unsigned long long ref_tests = 0;
+    unsigned long long ref_tests = 0, rkey_mine = KEY_NONE;
     unsigned n_hit = 0;
     if (in_range) {
         const int n = p.bands.n_px;
@@ -452,21 +453,20 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
                 const float db = c == 0 ? fd[2] : (c == 1 ? fd[0] : fd[1]); // axis (c+2)%3
                 p.px.re[kpx] = ok ? da * inv : 0.f;
                 p.px.re[n + kpx] = ok ? db * inv : 0.f;
-                int key = fid * NFACE + face;
-                if (p.cull_cells) { // sort key: group, then the Morton-ordered cell of (p,q) on the face
-                    const int nc = p.cull_cells;
-                    const int cx = ok ? min(nc - 1, max(0, (int)((da * inv + 1.f) * 0.5f * nc))) : 0;
-                    const int cy = ok ? min(nc - 1, max(0, (int)((db * inv + 1.f) * 0.5f * nc))) : 0;
-                    unsigned mx = cx, my = cy; // interleave (up to 8+8 bits)
-                    mx = (mx | (mx << 4)) & 0x0f0fu, mx = (mx | (mx << 2)) & 0x3333u, mx = (mx | (mx << 1)) & 0x5555u;
-                    my = (my | (my << 4)) & 0x0f0fu, my = (my | (my << 2)) & 0x3333u, my = (my | (my << 1)) & 0x5555u;
-                    key = key * (nc * nc) + (int)(mx | (my << 1));
+                const int key = fid * NFACE + face;
+                if (p.cull_cells) { // sort key: ray group, then the 16+16-bit Morton code of (p,q) on the face
+                    unsigned mx = ok ? (unsigned)fminf(65535.f, fmaxf(0.f, (da * inv + 1.f) * 32767.5f)) : 0u;
+                    unsigned my = ok ? (unsigned)fminf(65535.f, fmaxf(0.f, (db * inv + 1.f) * 32767.5f)) : 0u;
+                    mx = (mx | (mx << 8)) & 0x00ff00ffu, mx = (mx | (mx << 4)) & 0x0f0f0f0fu, mx = (mx | (mx << 2)) & 0x33333333u, mx = (mx | (mx << 1)) & 0x55555555u;
+                    my = (my | (my << 8)) & 0x00ff00ffu, my = (my | (my << 4)) & 0x0f0f0f0fu, my = (my | (my << 2)) & 0x33333333u, my = (my | (my << 1)) & 0x55555555u;
+                    rkey_mine = ((unsigned long long)(unsigned)key << 32) | (mx | (my << 1));
                 }
                 p.px.rj[kpx] = key;
                 my_j = key;
             }
         }
     }
+    if (p.k < p.L && p.cull_cells && in_range) p.rkey[kpx] = rkey_mine;
     if (p.k < p.L) { // histogram of rays per light vertex, warp-aggregated
         const unsigned active = __ballot_sync(0xffffffffu, my_j >= 0);
         if (my_j >= 0) {
@@ -518,7 +518,7 @@ __global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const 
 // The triangle-slice count of the chunk is chosen here, on the device, from the live block count (so the
 // host never has to wait for it): enough (block, slice) items to keep every SM busy, >= 4 tiles per slice.
 __global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block, int n_tiles_chunk, int n_sms, int *blk_off,
-                                    int *cnt_out, int *work, int *n_slices_out) {
+                                    int *cnt_out, int *work, int *n_slices_out, int items_per_sm = 6, int min_tiles = 4) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int bo = 0;
         for (int j = 0; j < F; ++j) {
@@ -528,10 +528,15 @@ __global__ void chunk_prefix_kernel(const int *cnt_in, int F, int rays_per_block
         }
         blk_off[F] = bo;
         *work = 0;
-        const int possible = max(1, n_tiles_chunk / 4);
-        int sl = bo >= 6 * n_sms ? 1 : (6 * n_sms + max(bo, 1) - 1) / max(bo, 1);
+        const int possible = max(1, n_tiles_chunk / min_tiles);
+        int sl = bo >= items_per_sm * n_sms ? 1 : (items_per_sm * n_sms + max(bo, 1) - 1) / max(bo, 1);
         *n_slices_out = max(1, min(sl, possible));
     }
+}
+
+__global__ void iota_kernel(int *a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
 }
 
 // ---------------------------------------------------------------------------------
@@ -763,49 +768,6 @@ __global__ void strict_primary_from_candidates(const unsigned long long *__restr
     }
     for (int o2 = 16; o2; o2 >>= 1) n_strict += __shfl_down_sync(0xffffffffu, n_strict, o2);
     if ((threadIdx.x & 31) == 0 && n_strict) atomicAdd(&counters->strict_evals, (unsigned long long)n_strict);
-}
-
-// bins (group, cell) -> offsets; also the per-group segment offsets/counts and ray-block offsets
-__global__ void bins_prefix_kernel(const int *__restrict__ bin_count, int n_bins, int cells_per_group, int n_groups,
-                                   int rays_per_block, int n_tiles, int n_sms, int *__restrict__ bin_off, int *bin_cursor,
-                                   int *seg_off, int *seg_cnt, int *blk_off, int *work, int *n_slices_out) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x, per = (n_bins + 1023) / 1024;
-    const int b0 = min(t * per, n_bins), b1 = min(b0 + per, n_bins);
-    int s = 0;
-    for (int b = b0; b < b1; ++b) s += bin_count[b];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = t >= o ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int run = part[t] - s;
-    for (int b = b0; b < b1; ++b) {
-        bin_off[b] = run;
-        bin_cursor[b] = 0;
-        run += bin_count[b];
-    }
-    if (t == 1023) bin_off[n_bins] = part[1023];
-    __syncthreads();
-    if (t == 0) {
-        int bo = 0;
-        for (int g = 0; g < n_groups; ++g) {
-            const int a = bin_off[g * cells_per_group], e = bin_off[(g + 1) * cells_per_group];
-            seg_off[g] = a, seg_cnt[g] = e - a, blk_off[g] = bo;
-            bo += (e - a + rays_per_block - 1) / rays_per_block;
-        }
-        seg_off[n_groups] = bin_off[n_bins];
-        blk_off[n_groups] = bo;
-        *work = 0;
-        // many more items than CTA slots: the cost of an item varies a lot with how selective its boxes are,
-        // and the longest item bounds the tail of the launch
-        const int possible = max(1, n_tiles / 16);
-        int sl = bo >= 24 * n_sms ? 1 : (24 * n_sms + max(bo, 1) - 1) / max(bo, 1);
-        *n_slices_out = max(1, min(sl, possible));
-    }
 }
 
 struct ShadowCullParams {

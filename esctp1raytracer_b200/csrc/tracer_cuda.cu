@@ -77,9 +77,12 @@ struct tracer_scene_dev {
           *rd = nullptr, *re = nullptr, *rt = nullptr;
     uint8_t *rgb8 = nullptr, *mask = nullptr;
     float *accum_total = nullptr;
-    int *bin_count = nullptr, *bin_off = nullptr, *bin_cursor = nullptr;
     // bundle-cull mode: candidate (ray<<32|triangle) buffers, their count, radix-sort scratch
-    unsigned long long *cand_a = nullptr, *cand_b = nullptr, *cand_count = nullptr;
+    unsigned long long *cand_a = nullptr, *cand_b = nullptr, *cand_count = nullptr, *rkey = nullptr, *rkey_sorted = nullptr;
+    int *iota = nullptr;
+    size_t pair_bytes = 0;
+    void *pair_tmp = nullptr;
+    int rkey_npx = 0;
     size_t cand_cap = 0, sort_bytes = 0;
     void *sort_tmp = nullptr;
     int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr,
@@ -244,9 +247,10 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
     dev_free(s->ro), dev_free(s->rd), dev_free(s->re), dev_free(s->rt), dev_free(s->rgb8), dev_free(s->mask);
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
-    dev_free(s->n_slices), dev_free(s->bin_count), dev_free(s->bin_off), dev_free(s->bin_cursor);
-    dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count);
+    dev_free(s->n_slices);
+    dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count), dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
     if (s->sort_tmp) cudaFree(s->sort_tmp);
+    if (s->pair_tmp) cudaFree(s->pair_tmp);
     dev_free(s->counters);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -462,7 +466,6 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
 
     const int n_tiles = s->n_pad / sweep::TILE;
     const bool cull = o.bundle_cull != 0;
-    const int cells = cull::NC * cull::NC;
     if (cull) { // candidate buffers: 24 per ray + slack (a few per ray are typical), sorted with a radix sort
         const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
         if (cap > s->cand_cap) {
@@ -474,6 +477,17 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             CK_CUDA(cudaMalloc(&s->sort_tmp, s->sort_bytes));
             s->cand_cap = cap;
         }
+    }
+    if (cull && s->rkey_npx < n_px) { // shadow rays are ordered by (group, Morton code) with a radix sort of (key, pixel) pairs
+        dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
+        if (s->pair_tmp) cudaFree(s->pair_tmp);
+        s->pair_tmp = nullptr;
+        if (dev_alloc(&s->rkey, (size_t)n_px) || dev_alloc(&s->rkey_sorted, (size_t)n_px) || dev_alloc(&s->iota, (size_t)n_px)) return TRACER_ERR_NOMEM;
+        CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0, 64, st));
+        CK_CUDA(cudaMalloc(&s->pair_tmp, s->pair_bytes));
+        trk::iota_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->iota, n_px);
+        CK_CUDA(cudaGetLastError());
+        s->rkey_npx = n_px;
     }
     int ray_bits = 1;
     while (((int64_t)1 << ray_bits) < n_px) ++ray_bits;
@@ -562,10 +576,6 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     }
 
     // ---- lights: (finish k-1, set up k) -> group by light vertex -> first-occluder sweep ----
-    if (cull && !s->bin_count) {
-        const size_t n_bins = (size_t)s->maxF * trk::NFACE * cells + 2;
-        if (dev_alloc(&s->bin_count, n_bins) || dev_alloc(&s->bin_off, n_bins) || dev_alloc(&s->bin_cursor, n_bins)) return TRACER_ERR_NOMEM;
-    }
     auto build_face_tables = [&](int k, const std::vector<int> &group_cnt) -> int { // lazily, for groups that have rays
         for (int gi = 0; gi < (int)group_cnt.size(); ++gi) {
             if (!group_cnt[gi]) continue;
@@ -599,25 +609,28 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.geom_has_normals = s->geom_has_normals, lp.geom_material = s->geom_material;
         lp.sphere_material = s->sphere_material, lp.spheres = s->spheres;
         lp.rng_mode = o.rng_mode, lp.seed = seed_s, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
-        lp.seg_count = cull ? s->bin_count : s->seg_count, lp.counters = s->counters;
+        lp.seg_count = s->seg_count, lp.counters = s->counters;
         lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
-        lp.cull_cells = cull ? cull::NC : 0;
-        if (k < L && !cull) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
-        if (k < L && cull)
-            CK_CUDA(cudaMemsetAsync(s->bin_count, 0, sizeof(int) * ((size_t)s->h_light_F[k] * trk::NFACE * cells + 1), st));
+        lp.cull_cells = cull ? 1 : 0, lp.rkey = s->rkey;
+        if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
         CK_CUDA(cudaGetLastError());
         ++launches;
         if (k == L) break;
         const int F = s->h_light_F[k] * trk::NFACE; // ray groups: (light vertex, cube face)
         if (cull) {
-            // OPTIONAL bundle-cull mode: rays sorted by (group, cell), one culled sweep over all triangles per light
-            const int n_bins = F * cells, rpb = sweep::THREADS * 8;
-            trk::bins_prefix_kernel<<<1, 1024, 0, st>>>(s->bin_count, n_bins, cells, F, rpb, s->n_pad / cull::CTILE, 2 * g.n_sms, s->bin_off, s->bin_cursor,
-                                                        s->seg_off, s->cursor, s->blk_off, s->work, s->n_slices);
+            // OPTIONAL bundle-cull mode: rays sorted by (group, Morton code of (p,q)), one culled sweep over all triangles per light
+            const int rpb = sweep::THREADS * 8;
+            int group_bits = 1;
+            while ((1 << group_bits) < F) ++group_bits;
+            trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
             CK_CUDA(cudaGetLastError());
-            trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->bin_off, s->bin_cursor, s->list);
+            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, rpb, s->n_pad / cull::CTILE, 2 * g.n_sms, s->blk_off, s->cnt_b, s->work,
+                                                       s->n_slices, 24, 16);
             CK_CUDA(cudaGetLastError());
+            CK_CUDA(cub::DeviceRadixSort::SortPairs(s->pair_tmp, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0,
+                                                    32 + group_bits + 1, st));
+            CK_CUDA(cudaMemcpyAsync(s->cursor, s->seg_count, sizeof(int) * F, cudaMemcpyDeviceToDevice, st));
             CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
             std::vector<int> gcnt((size_t)F);
             CK_CUDA(cudaMemcpyAsync(gcnt.data(), s->cursor, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
@@ -627,7 +640,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             trk::ShadowCullParams sp{};
             sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
             sp.allcand = s->allcand_table, sp.n_tiles = s->n_pad / cull::CTILE, sp.n_tris = s->n_tris, sp.n_groups = F, sp.n_px = n_px;
-            sp.cells_per_group = cells, sp.n_slices = s->n_slices;
+            sp.cells_per_group = 0, sp.n_slices = s->n_slices;
             sp.list = s->list, sp.seg_off = s->seg_off, sp.seg_cnt = s->cursor, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
             sp.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
