@@ -4,7 +4,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/tracer_cuda.h"
@@ -39,17 +42,72 @@ int fail(int code, const std::string &msg) {
             return fail(TRACER_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
     } while (0)
 
+// Device-memory pool: the drop-in call (tracer_cuda_render) creates and destroys a resident scene per
+// frame; cudaMalloc/cudaFree of a few GB of tables and workspace would cost more than the upload itself.
+// Freed blocks are kept (up to a quarter of the device memory) and handed out again by size.
+struct Pool {
+    std::mutex mu;
+    std::unordered_map<void *, size_t> live;     // pointer -> bytes of blocks handed out
+    std::multimap<size_t, void *> free_blocks;   // bytes -> pointer
+    size_t cached = 0, limit = 0;
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 2 + (1 << 20)) {
+            void *p = it->second;
+            cached -= it->first;
+            live[p] = it->first;
+            free_blocks.erase(it);
+            return p;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            release_all_locked(); // make room and retry once
+            if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        }
+        live[p] = bytes;
+        return p;
+    }
+    void release(void *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.find(p);
+        if (it == live.end()) {
+            cudaFree(p);
+            return;
+        }
+        const size_t bytes = it->second;
+        live.erase(it);
+        if (cached + bytes <= limit) {
+            free_blocks.insert({bytes, p});
+            cached += bytes;
+        } else {
+            cudaFree(p);
+        }
+    }
+    void release_all_locked() {
+        for (auto &kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached = 0;
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> lk(mu);
+        release_all_locked();
+    }
+} g_pool;
+
 template <typename T>
 int dev_alloc(T **p, size_t n) {
-    *p = nullptr;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
-    if (e != cudaSuccess) return fail(TRACER_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *p = (T *)g_pool.alloc(n * sizeof(T));
+    if (!*p) return fail(TRACER_ERR_NOMEM, "device memory allocation of " + std::to_string((n * sizeof(T)) >> 20) + " MiB failed");
     return 0;
 }
 template <typename T>
 void dev_free(T *&p) {
-    if (p) cudaFree(p);
+    g_pool.release((void *)p);
     p = nullptr;
 }
 
@@ -212,11 +270,13 @@ int tracer_cuda_init(int device_ordinal) {
     if (!g.stream) CK_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     g.device = device_ordinal;
     g.n_sms = g.prop.multiProcessorCount;
+    g_pool.limit = g.prop.totalGlobalMem / 4;
     g.inited = true;
     return TRACER_OK;
 }
 
 void tracer_cuda_shutdown(void) {
+    g_pool.release_all();
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.inited = false;
@@ -249,8 +309,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
     dev_free(s->n_slices);
     dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count), dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
-    if (s->sort_tmp) cudaFree(s->sort_tmp);
-    if (s->pair_tmp) cudaFree(s->pair_tmp);
+    g_pool.release(s->sort_tmp), g_pool.release(s->pair_tmp);
     dev_free(s->counters);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -470,21 +529,21 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
         if (cap > s->cand_cap) {
             dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count);
-            if (s->sort_tmp) cudaFree(s->sort_tmp);
+            g_pool.release(s->sort_tmp);
             s->sort_tmp = nullptr, s->cand_cap = 0;
             if (dev_alloc(&s->cand_a, cap) || dev_alloc(&s->cand_b, cap) || dev_alloc(&s->cand_count, 1)) return TRACER_ERR_NOMEM;
             CK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, s->sort_bytes, s->cand_a, s->cand_b, cap, 0, 64, st));
-            CK_CUDA(cudaMalloc(&s->sort_tmp, s->sort_bytes));
+            if (!(s->sort_tmp = g_pool.alloc(s->sort_bytes))) return fail(TRACER_ERR_NOMEM, "sort scratch");
             s->cand_cap = cap;
         }
     }
     if (cull && s->rkey_npx < n_px) { // shadow rays are ordered by (group, Morton code) with a radix sort of (key, pixel) pairs
         dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
-        if (s->pair_tmp) cudaFree(s->pair_tmp);
+        g_pool.release(s->pair_tmp);
         s->pair_tmp = nullptr;
         if (dev_alloc(&s->rkey, (size_t)n_px) || dev_alloc(&s->rkey_sorted, (size_t)n_px) || dev_alloc(&s->iota, (size_t)n_px)) return TRACER_ERR_NOMEM;
         CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0, 64, st));
-        CK_CUDA(cudaMalloc(&s->pair_tmp, s->pair_bytes));
+        if (!(s->pair_tmp = g_pool.alloc(s->pair_bytes))) return fail(TRACER_ERR_NOMEM, "sort scratch");
         trk::iota_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->iota, n_px);
         CK_CUDA(cudaGetLastError());
         s->rkey_npx = n_px;
