@@ -43,7 +43,11 @@ WORKLOADS = {
     "c3": (7_088, 9, 1, 0, 1920, 1080),       # triangle count of CornellBox-Water, synthetic geometry
     "c1": (36, 7, 1, 0, 1024, 768),           # size of the default Cornell scene (box_scene)
     "small": (100_000, 100, 4, 100, 1280, 720),
+    # BASELINE.json configs[4]: 7680x4320, 16 spp jittered primary rays, 1 light, triangle-count sweep via --tris
+    # (extension, parity unpinned; not a bench line: run with --workload c5 --tris N [--mode cull])
+    "c5": (1_000_000, 1000, 1, 0, 7680, 4320),
 }
+WORKLOAD_SPP = {"c5": 16}
 
 
 def make_scene(name, args):
@@ -176,6 +180,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="skip the extra measurement of the optional bundle-cull mode")
+    ap.add_argument("--mode", default="brute", choices=["brute", "cull"],
+                    help="which mode `value` measures; the default is the north star's brute-force formulation")
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel (extension); default: the workload's")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,6 +206,10 @@ def main():
     scene, W, H = make_scene(args.workload, args)
     cam = Camera.for_frame(EYE, LOOK, W, H)
     seed = 42
+    spp = args.spp or WORKLOAD_SPP.get(args.workload, 0)
+    main_cull = args.mode == "cull"
+    import functools
+    tdist_render = functools.partial(tdist.render_frame, samples_per_pixel=spp)
 
     def barrier():
         if world > 1:
@@ -214,7 +225,7 @@ def main():
     # ---- value: resident scene, frame stays in HBM ------------------------------------------
     rs = renderer.upload(scene)
     for _ in range(args.warmup):
-        tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed)
+        tdist_render(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=main_cull)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -224,7 +235,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        frame, st = tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed)
+        frame, st = tdist_render(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=main_cull)
         for k, v in st.items():
             acc[k] = acc.get(k, 0) + v
     ev1.record()
@@ -249,16 +260,16 @@ def main():
 
     # ---- extra: the OPTIONAL bundle-cull mode (same frame, hierarchical evaluation of the same filter) ------
     cull_extra = None
-    if not args.no_cull:
-        frame_ref, _ = tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed)
+    if not args.no_cull and not main_cull:
+        frame_ref, _ = tdist_render(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed)
         for _ in range(2):
-            frame_c, _ = tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=True)
+            frame_c, _ = tdist_render(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=True)
         same = bool(torch.equal(frame_ref, frame_c)) if rank == 0 else True
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for _ in range(args.steps):
-            tdist.render_frame(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=True)
+            tdist_render(renderer, rs, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=True)
         c1.record()
         barrier()
         cms = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device="cuda")
@@ -282,7 +293,7 @@ def main():
             ta = time.perf_counter()
             r2 = renderer.upload(scene)  # host -> HBM every step
             tb = time.perf_counter()
-            fr, _ = tdist.render_frame(renderer, r2, cam, W, H, rank=rank, world=world, seed=seed)
+            fr, _ = tdist_render(renderer, r2, cam, W, H, rank=rank, world=world, seed=seed, bundle_cull=main_cull)
             tc = time.perf_counter()
             if rank == 0:
                 host_frame.copy_(fr, non_blocking=False)  # HBM -> host read of the result
@@ -331,7 +342,7 @@ def main():
         line = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, scene, W, H),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.workload, scene, W, H), spp=max(1, spp), mode=args.mode),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
