@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
     sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1), sm.consumed[s] = 0;
         sweep::fence_barrier_init();
     }
     __syncthreads();

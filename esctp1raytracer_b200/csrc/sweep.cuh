@@ -113,6 +113,7 @@ struct __align__(128) Smem {
     int tri[R][THREADS];
     uint64_t full_bar[STAGES];
     int blk, seg, scan[THREADS / 32], base_out;
+    int consumed[STAGES]; // closest-hit sweeps: warps that have finished the tile in this stage
 };
 
 struct Counters {
@@ -242,9 +243,27 @@ __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restric
 #endif
             }
         }
+        if (!ANYHIT) {
+            // Closest hit never stops early, so no block-wide barrier is needed per tile: every warp counts
+            // itself out of stage s, and the LAST one refills it.  Warps run up to STAGES-1 tiles apart, which
+            // absorbs the skew of the (rare, long) strict evaluations instead of stalling 15 warps behind one.
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                __threadfence_block(); // this warp's reads of the stage are done before the count is visible
+                if (atomicAdd(&sm.consumed[s], 1) == THREADS / 32 - 1) {
+                    sm.consumed[s] = 0;
+                    __threadfence_block();
+                    if (it + STAGES < n_tiles) {
+                        mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
+                        tma_load_1d(sm.tile[s], src + (size_t)(it + STAGES) * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
+                    }
+                }
+            }
+            continue;
+        }
         // everyone is done with stage s (also: have all rays of the CTA found their occluder?)
         const int all_done = __syncthreads_and((done | ~valid) == 0xffffffffu);
-        if (ANYHIT && all_done) stop = true;
+        if (all_done) stop = true;
         if (!stop && it + STAGES < n_tiles) {
             last_issued = it + STAGES;
             if (tid == 0) {
