@@ -40,14 +40,15 @@ EYE, LOOK = (0.0, 1.0, 3.0), (0.0, 1.0, 0.0)
 WORKLOADS = {
     # name: (n_tris, n_geoms, n_lights, n_spheres, W, H)
     "c4": (1_000_000, 1000, 4, 1000, 3840, 2160),
-    "c3": (7_088, 9, 1, 0, 1920, 1080),       # triangle count of CornellBox-Water, synthetic geometry
-    "c1": (36, 7, 1, 0, 1024, 768),           # size of the default Cornell scene (box_scene)
+    "c3": (7_088, 9, 1, 0, 1920, 1080),       # CornellBox-Water as loaded by the reference (tests/golden/cornell_water.npz)
+    "c1": (36, 7, 1, 0, 1024, 768),           # CornellBox-Original, the reference's default run (tests/golden/cornell_original.npz)
     "small": (100_000, 100, 4, 100, 1280, 720),
     # BASELINE.json configs[4]: 7680x4320, 16 spp jittered primary rays, 1 light, triangle-count sweep via --tris
     # (extension, parity unpinned; not a bench line: run with --workload c5 --tris N [--mode cull])
     "c5": (1_000_000, 1000, 1, 0, 7680, 4320),
 }
 WORKLOAD_SPP = {"c5": 16}
+GOLDEN_MODELS = {"c1": "cornell_original.npz", "c3": "cornell_water.npz"}
 
 
 def make_scene(name, args):
@@ -56,8 +57,10 @@ def make_scene(name, args):
     n_tris, n_geoms, n_lights, n_spheres, W, H = WORKLOADS[name]
     n_tris = args.tris or n_tris
     W, H = args.width or W, args.height or H
-    if name == "c1":
-        return scenes.box_scene(), W, H
+    if name in GOLDEN_MODELS and not args.tris:
+        global EYE, LOOK
+        sc, EYE, LOOK = scenes.from_npz(os.path.join(ROOT, "tests", "golden", GOLDEN_MODELS[name]))
+        return sc, W, H
     return scenes.soup_scene(n_tris, min(n_geoms, max(8, n_tris // 100)), n_lights, n_spheres=n_spheres, seed=42), W, H
 
 
@@ -139,7 +142,7 @@ def run_reference(args, rank):
     scene, W, H = make_scene(args.workload, args)
     threads = os.cpu_count() or 1
     per_px = scene.n_tris * 3.0 / 55e6  # ~55 M tests/s/core
-    n_px = int(max(threads, min(4096, (20.0 * threads / max(1, args.steps + args.warmup)) / max(per_px, 1e-6))))
+    n_px = int(max(threads, min(W * H, (20.0 * threads / max(1, args.steps + args.warmup)) / max(per_px, 1e-6))))
     for _ in range(args.warmup):
         cpu_sample(scene, W, H, max(threads, n_px // 4), threads)
     vals, secs = [], 0.0
@@ -159,7 +162,8 @@ def run_reference(args, rank):
 
 
 def workload_config(name, scene, W, H):
-    return {"workload": f"{name}: synthetic {scene.n_tris}-triangle + {len(scene.sphere_cr)}-sphere scene at {W}x{H}, "
+    kind = f"reference model {GOLDEN_MODELS[name][:-4]}" if name in GOLDEN_MODELS and scene.n_tris == WORKLOADS[name][0] else "synthetic"
+    return {"workload": f"{name}: {kind} {scene.n_tris}-triangle + {len(scene.sphere_cr)}-sphere scene at {W}x{H}, "
                         f"{scene.n_lights} lights, brute force over all objects",
             "n_tris": scene.n_tris, "n_spheres": int(len(scene.sphere_cr)), "width": W, "height": H,
             "n_lights": scene.n_lights, "spp": 1, "l2_policy": "inputs larger than L2 are not needed: the per-frame working "
@@ -217,7 +221,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- FP32 peak of this GPU, measured now ----------------------------------------------
-    peaks = {v: renderer.fp32_peak(v, 5)[0] for v in (0, 1, 2, 3)}
+    # variants 0/3 scalar FFMA chains, 1 packed FFMA2 chains.  (Variant 2, an instruction-mix kernel, is not a
+    # peak: the compiler hoists part of its FFMAs, so its flop count over-states what was executed.)
+    peaks = {v: renderer.fp32_peak(v, 5)[0] for v in (0, 1, 3)}
     peak_tflops = max(peaks.values())
     info = renderer.device_info()
     nominal = info["sm_count"] * 128 * 2 * info["clock_khz"] * 1e3 / 1e12
@@ -338,7 +344,7 @@ def main():
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             per_px = scene.n_tris * 3.0 / 55e6
-            cpu = cpu_sample(scene, W, H, int(max(threads, min(4096, 15.0 * threads / max(per_px, 1e-6)))), threads)
+            cpu = cpu_sample(scene, W, H, int(max(threads, min(W * H, 15.0 * threads / max(per_px, 1e-6)))), threads)
         line = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",

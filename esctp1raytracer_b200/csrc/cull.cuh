@@ -112,6 +112,35 @@ __device__ __forceinline__ void chunk_close(const Emitter em, const WarpChunk wc
         if (wc.base + i < em.cap) em.buf[wc.base + i] = SENTINEL;
 }
 
+// warp-aggregated append of (ray, triangle) pairs: bit r of `mask` = this lane's ray r is a candidate for `tri`.
+// Called by all 32 lanes (mask may be 0 in some of them).
+template <int R>
+__device__ __forceinline__ void emit_pairs(const Emitter em, WarpChunk &wc, unsigned mask, const int (&ray_id)[R], unsigned tri) {
+    const int lane = threadIdx.x & 31;
+    const int mine = __popc(mask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (wc.used + (unsigned)total > CHUNK) { // rare: take a fresh chunk (the only atomic)
+        chunk_close(em, wc);
+        unsigned long long nb = 0;
+        if (lane == 0) nb = atomicAdd(em.count, (unsigned long long)CHUNK);
+        wc.base = __shfl_sync(0xffffffffu, nb, 0), wc.used = 0;
+    }
+    unsigned long long base = wc.base + wc.used + (unsigned long long)(incl - mine);
+    wc.used += (unsigned)total;
+    while (mask) {
+        const int r = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (base < em.cap) em.buf[base] = ((unsigned long long)(unsigned)ray_id[r] << 32) | tri;
+        ++base;
+    }
+}
+
 // tile_lo/tile_hi in units of CTILE triangles.  One barrier per tile in the common case (no survivor of the
 // CTA box in the tile): __syncthreads_or both publishes "any survivor" and proves that every thread is done
 // with the previous tile's stage, which thread 0 then refills.
@@ -173,29 +202,7 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
                 for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
                 mask &= valid;
                 if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
-                const int mine = __popc(mask); // warp-aggregated append
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (wc.used + (unsigned)total > CHUNK) { // rare: take a fresh chunk (the only atomic)
-                    chunk_close(em, wc);
-                    unsigned long long nb = 0;
-                    if (lane == 0) nb = atomicAdd(em.count, (unsigned long long)CHUNK);
-                    wc.base = __shfl_sync(0xffffffffu, nb, 0), wc.used = 0;
-                }
-                unsigned long long base = wc.base + wc.used + (unsigned long long)(incl - mine);
-                wc.used += (unsigned)total;
-                const unsigned tri = (unsigned)((tile_lo + it) * CTILE + k);
-                while (mask) {
-                    const int r = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    if (base < em.cap) em.buf[base] = ((unsigned long long)(unsigned)ray_id[r] << 32) | tri;
-                    ++base;
-                }
+                emit_pairs<R>(em, wc, mask, ray_id, (unsigned)((tile_lo + it) * CTILE + k));
             }
         }
     }
@@ -206,6 +213,145 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
         atomicAdd(&diag->cull_l1, (unsigned long long)d_l1);
     }
     __syncthreads(); // all stages consumed before the next item's prologue refills them
+}
+
+// ---- two-phase organisation of the same hierarchy ("block lists") ---------------------------------------
+// The streaming sweep above spends most of its time on per-tile bookkeeping (mbarrier wait, CTA-wide vote,
+// stage refill) although the level-0 test itself is ~15 instructions per triangle.  The two-phase form
+// separates the levels into dense kernels:
+//   phase A  cull_l0_kernel: EVERY (ray block, triangle) pair — still no acceleration structure, no build
+//            step — with one triangle per thread held in registers and the block boxes broadcast from
+//            shared memory; survivors are appended as block<<32|triangle and radix-sorted;
+//   phase B  walk_block_list: each warp of the ray block walks the block's (short) survivor list 32 triangles
+//            at a time against its own warp box, then per ray, and emits ray<<32|triangle candidates.
+// The candidates then take the same sort + strict path as before, so results stay bit-identical.
+struct BlockBoxes {
+    Box cta;
+    Box warp[sweep::THREADS / 32];
+};
+
+struct L0Params {
+    const float4 *tables;  // group j -> tables + ((j / nface) * 6 + j % nface) * table_stride; nface == 0: one table
+    const float4 *allcand; // group with j % nface == nface - 1
+    size_t table_stride;
+    int n_groups, nface, n_tris;
+    const int *blk_off; // [n_groups + 1] ray blocks of each group (device)
+    const BlockBoxes *boxes;
+    unsigned long long *keys, *count;
+    unsigned long long cap;
+    sweep::Counters *diag;
+};
+
+__device__ __forceinline__ const float4 *group_table(const float4 *tables, const float4 *allcand, size_t stride, int nface, int j) {
+    if (nface == 0) return tables;
+    const int face = j % nface;
+    return face == nface - 1 ? allcand : tables + (size_t)((j / nface) * 6 + face) * stride;
+}
+
+constexpr int L0_THREADS = 256;
+constexpr int L0_STAGE = 256; // keys staged per warp in shared memory between flushes (one global atomic per flush)
+__global__ void __launch_bounds__(L0_THREADS) cull_l0_kernel(const L0Params p) {
+    __shared__ Box sbox[L0_THREADS];
+    __shared__ unsigned long long stage[L0_THREADS / 32][L0_STAGE];
+    const int j = blockIdx.y;
+    const int b_lo = p.blk_off[j], b_hi = p.blk_off[j + 1];
+    if (b_lo >= b_hi) return;
+    const float4 *__restrict__ tab = group_table(p.tables, p.allcand, p.table_stride, p.nface, j);
+    const int tri = blockIdx.x * L0_THREADS + threadIdx.x, lane = threadIdx.x & 31;
+    unsigned long long *__restrict__ st = stage[threadIdx.x >> 5];
+    const bool live = tri < p.n_tris;
+    float4 rb = make_float4(0.f, 0.f, -1.f, 0.f), rc = rb, rd = rb;
+    if (live) rb = tab[3 * (size_t)tri], rc = tab[3 * (size_t)tri + 1], rd = tab[3 * (size_t)tri + 2];
+    unsigned fill = 0, n_pass = 0; // warp-uniform
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.count, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned k = lane; k < fill; k += 32)
+            if (base + k < p.cap) p.keys[base + k] = st[k];
+        __syncwarp();
+        n_pass += fill, fill = 0;
+    };
+    for (int b0 = b_lo; b0 < b_hi; b0 += L0_THREADS) {
+        __syncthreads();
+        if (b0 + (int)threadIdx.x < b_hi) sbox[threadIdx.x] = p.boxes[b0 + threadIdx.x].cta;
+        __syncthreads();
+        const int nb = min(L0_THREADS, b_hi - b0);
+#pragma unroll 2
+        for (int i = 0; i < nb; ++i) {
+            const bool pass = live && !(box_sign(rb, rc, rd, sbox[i]) >> 31);
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                if (pass) st[fill + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)(b0 + i) << 32) | (unsigned)tri;
+                fill += __popc(m);
+                if (fill > L0_STAGE - 32) flush();
+            }
+        }
+    }
+    if (fill) flush();
+    if (p.diag && lane == 0 && n_pass) atomicAdd(&p.diag->cull_l0, (unsigned long long)n_pass);
+}
+
+// first index i in [0, n) with keys[i] >= key
+__device__ __forceinline__ unsigned long long lower_bound_key(const unsigned long long *__restrict__ keys, unsigned long long n,
+                                                              unsigned long long key) {
+    unsigned long long lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// phase B: the block's sorted survivor list keys[lo, hi) (low word = triangle).  The CTA stages LTILE rows at a
+// time in shared memory (each row gathered from the table ONCE per block); every warp then tests the staged rows
+// against its own box, one row per lane, and the rows that pass go through the per-ray filter (row broadcast
+// from shared memory); candidates are appended through the warp's chunk.
+constexpr int LTILE = sweep::THREADS;
+struct ListSmem {
+    float4 row[LTILE * 3];
+    unsigned tri[LTILE];
+};
+template <int R>
+__device__ __forceinline__ void walk_block_list(ListSmem &sm, const unsigned long long *__restrict__ keys, unsigned long long lo,
+                                                unsigned long long hi, const float4 *__restrict__ table, const float (&rp)[R],
+                                                const float (&rq)[R], unsigned valid, const int (&ray_id)[R], const Box warp_box,
+                                                const Emitter em, WarpChunk &wc, unsigned &d_l1) {
+    using sweep::edge_sign;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (unsigned long long i0 = lo; i0 < hi; i0 += LTILE) {
+        const int n = (int)((hi - i0) < (unsigned long long)LTILE ? (hi - i0) : (unsigned long long)LTILE);
+        __syncthreads(); // previous tile fully consumed
+        if (tid < n) {
+            const unsigned t = (unsigned)keys[i0 + tid];
+            sm.tri[tid] = t;
+            sm.row[3 * tid] = __ldg(&table[3 * (size_t)t]);
+            sm.row[3 * tid + 1] = __ldg(&table[3 * (size_t)t + 1]);
+            sm.row[3 * tid + 2] = __ldg(&table[3 * (size_t)t + 2]);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            bool pass = false;
+            if (k < n) pass = !(box_sign(sm.row[3 * k], sm.row[3 * k + 1], sm.row[3 * k + 2], warp_box) >> 31);
+            unsigned mm = __ballot_sync(0xffffffffu, pass);
+            while (mm) { // warp-box survivors in index order
+                const int e = k0 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float4 rb = sm.row[3 * e], rc = sm.row[3 * e + 1], rd = sm.row[3 * e + 2];
+                unsigned mask = 0;
+                ++d_l1;
+#pragma unroll
+                for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                mask &= valid;
+                if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+                emit_pairs<R>(em, wc, mask, ray_id, sm.tri[e]);
+            }
+        }
+    }
 }
 
 }  // namespace cull

@@ -3,7 +3,9 @@
 // independent FMA chains on every SM, enough warps to fill all four schedulers.
 //   variant 0: scalar FFMA, 16 independent chains per thread
 //   variant 1: packed FFMA2 (fma.rn.f32x2), 8 independent 2-wide chains per thread
-//   variant 2: the renderer's instruction mix (9 FFMA + min3/max per pair, no memory)
+//   variant 2: an early instruction-mix probe (9 FFMA + min3/max per pair, no memory).  NOT a peak: ptxas
+//              hoists part of the loop-invariant FFMAs, so the nominal flop count over-states what ran;
+//              bench.py ignores it
 //   variant 3: scalar FFMA, every chain with its own multiplier and addend registers
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -692,12 +692,32 @@ struct PrimaryCullParams {
     int *work;
 };
 
+// rays of block blk of the primary tiling: 128 x 32 pixels per block, 32 x 8 per warp, R = 8 rows per thread
+template <int R>
+__device__ __forceinline__ void load_primary_bundle(const PrimaryCullParams &p, int blk, float (&rp)[R], float (&rq)[R], int (&kp)[R],
+                                                    unsigned &valid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = p.bands.W;
+    const int ty = blk / p.tiles_x, tx = blk - ty * p.tiles_x;
+    const int x = tx * 128 + (warp & 3) * 32 + lane, y0 = ty * 32 + (warp >> 2) * 8;
+    valid = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int ly = y0 + r;
+        if (x < W && ly < p.n_rows) valid |= 1u << r;
+        const int k = min(ly, p.n_rows - 1) * W + min(x, W - 1); // clamp: duplicates of valid rays keep the boxes tight
+        kp[r] = k;
+        int w, h;
+        p.bands.map(k, w, h);
+        p.bands.pixel_st(w, h, rp[r], rq[r]);
+    }
+}
+
 // work item = screen tile of 128 x 32 pixels (warp: 32 x 8) x triangle slice; emits candidate pairs
 __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const PrimaryCullParams p) {
     constexpr int R = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cull::EmitSmem &sm = *reinterpret_cast<cull::EmitSmem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < cull::CSTAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
         sweep::fence_barrier_init();
@@ -707,7 +727,6 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
     unsigned long long tests = 0;
     cull::WarpChunk wc{0, cull::CHUNK}; // no chunk yet
     const int n_blocks = p.tiles_x * p.tiles_y, n_items = n_blocks * p.n_slices;
-    const int W = p.bands.W;
     for (;;) {
         if (tid == 0) sm.blk = atomicAdd(p.work, 1);
         __syncthreads();
@@ -716,21 +735,10 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
         const int slice = item / n_blocks, blk = item - slice * n_blocks;
         const int tile_lo = (int)((long long)p.n_tiles * slice / p.n_slices);
         const int tile_hi = (int)((long long)p.n_tiles * (slice + 1) / p.n_slices);
-        const int ty = blk / p.tiles_x, tx = blk - ty * p.tiles_x;
-        const int x = tx * 128 + (warp & 3) * 32 + lane, y0 = ty * 32 + (warp >> 2) * 8;
         float rp[R], rq[R];
         int kp[R];
         unsigned valid = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int ly = y0 + r;
-            if (x < W && ly < p.n_rows) valid |= 1u << r;
-            const int k = min(ly, p.n_rows - 1) * W + min(x, W - 1); // clamp: duplicates of valid rays keep the boxes tight
-            kp[r] = k;
-            int w, h;
-            p.bands.map(k, w, h);
-            p.bands.pixel_st(w, h, rp[r], rq[r]);
-        }
+        load_primary_bundle<R>(p, blk, rp, rq, kp, valid);
         cull::Box wb, cb;
         cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
         cull::sweep_cull_emit<R>(sm, p.table, tile_lo, tile_hi, rp, rq, valid, kp, gtile, cb, wb, p.em, wc, nullptr);
@@ -783,18 +791,36 @@ struct ShadowCullParams {
     int *work;
 };
 
+// rays of block blk of group j: 512*R consecutive rays of the (group, Morton)-sorted list, 32*R consecutive per warp
+template <int R>
+__device__ __forceinline__ void load_shadow_bundle(const ShadowCullParams &p, int blk, int j, float (&rp)[R], float (&rq)[R],
+                                                   int (&kp)[R], unsigned &valid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n_px;
+    const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
+    const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane;
+    valid = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int e = base + r * 32; // a warp holds 32*R consecutive rays of the sorted list: a compact cell range
+        if (e < seg_end) valid |= 1u << r;
+        e = min(e, seg_end - 1);
+        const int k = p.list[e];
+        kp[r] = k;
+        rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
+    }
+}
+
 // work item = 512*8 consecutive rays of the cell-sorted list of one (light vertex, face) group x triangle slice
 __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const ShadowCullParams p) {
     constexpr int R = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cull::EmitSmem &sm = *reinterpret_cast<cull::EmitSmem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < cull::CSTAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
         sweep::fence_barrier_init();
     }
     __syncthreads();
-    const int n = p.n_px;
     const int total_blocks = p.blk_off[p.n_groups];
     const int n_slices = *p.n_slices;
     const int n_items = total_blocks * n_slices;
@@ -817,20 +843,10 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const Sh
         const int blk = sm.blk, j = sm.seg, slice = sm.slice;
         if (blk < 0) break;
         const int lo = (int)((long long)p.n_tiles * slice / n_slices), hi = (int)((long long)p.n_tiles * (slice + 1) / n_slices);
-        const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
-        const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane;
         float rp[R], rq[R];
         int kp[R];
         unsigned valid = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int e = base + r * 32; // a warp holds 32*R consecutive rays of the sorted list: a compact cell range
-            if (e < seg_end) valid |= 1u << r;
-            e = min(e, seg_end - 1);
-            const int k = p.list[e];
-            kp[r] = k;
-            rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
-        }
+        load_shadow_bundle<R>(p, blk, j, rp, rq, kp, valid);
         cull::Box wb, cb;
         cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
         const int face = j % NFACE;
@@ -868,6 +884,116 @@ __global__ void strict_shadow_from_candidates(const unsigned long long *__restri
     }
     for (int o2 = 16; o2; o2 >>= 1) n_strict += __shfl_down_sync(0xffffffffu, n_strict, o2);
     if ((threadIdx.x & 31) == 0 && n_strict) atomicAdd(&counters->strict_evals, (unsigned long long)n_strict);
+}
+
+// ---- two-phase bundle cull (cull.cuh: "block lists") -----------------------------------------------
+// boxes of every ray block (CTA box for phase A, warp boxes for phase B), from exactly the rays the block holds
+__global__ void __launch_bounds__(sweep::THREADS) primary_boxes_kernel(const PrimaryCullParams p, cull::BlockBoxes *__restrict__ out,
+                                                                       int *__restrict__ blk_off) {
+    constexpr int R = 8;
+    __shared__ float scratch[4 * sweep::THREADS / 32];
+    const int blk = blockIdx.x;
+    float rp[R], rq[R];
+    int kp[R];
+    unsigned valid;
+    load_primary_bundle<R>(p, blk, rp, rq, kp, valid);
+    cull::Box wb, cb;
+    cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
+    if ((threadIdx.x & 31) == 0) out[blk].warp[threadIdx.x >> 5] = wb;
+    if (threadIdx.x == 0) out[blk].cta = cb;
+    if (blk == 0 && threadIdx.x == 0) blk_off[0] = 0, blk_off[1] = p.tiles_x * p.tiles_y; // one group
+}
+
+__global__ void __launch_bounds__(sweep::THREADS) shadow_boxes_kernel(const ShadowCullParams p, cull::BlockBoxes *__restrict__ out) {
+    constexpr int R = 8;
+    __shared__ float scratch[4 * sweep::THREADS / 32];
+    const int blk = blockIdx.x;
+    if (blk >= p.blk_off[p.n_groups]) return;
+    int j = 0;
+    while (blk >= p.blk_off[j + 1]) ++j;
+    float rp[R], rq[R];
+    int kp[R];
+    unsigned valid;
+    load_shadow_bundle<R>(p, blk, j, rp, rq, kp, valid);
+    cull::Box wb, cb;
+    cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
+    if ((threadIdx.x & 31) == 0) out[blk].warp[threadIdx.x >> 5] = wb;
+    if (threadIdx.x == 0) out[blk].cta = cb;
+}
+
+struct BlockLists {
+    const cull::BlockBoxes *boxes;
+    const unsigned long long *keys; // sorted block<<32|triangle survivors of phase A
+    unsigned long long n_keys;
+};
+
+// phase B.  Work item = a fixed-size segment of the sorted key array (so a ray block with a very long survivor
+// list — e.g. a shadow-ray block that straddles a Morton-order jump and has a huge box — is spread over many
+// CTAs, and short lists share one); inside a segment every run of equal block ids is one walk_block_list call.
+constexpr unsigned long long CULL_SEG = 8192;
+
+struct PrimaryBundles {
+    PrimaryCullParams p;
+    template <int R>
+    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], int (&kp)[R], unsigned &valid) const {
+        load_primary_bundle<R>(p, blk, rp, rq, kp, valid);
+        return p.table;
+    }
+};
+struct ShadowBundles {
+    ShadowCullParams p;
+    template <int R>
+    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], int (&kp)[R], unsigned &valid) const {
+        int j = 0;
+        while (blk >= p.blk_off[j + 1]) ++j;
+        load_shadow_bundle<R>(p, blk, j, rp, rq, kp, valid);
+        return cull::group_table(p.tables, p.allcand, p.table_stride, NFACE, j);
+    }
+};
+
+template <class Bundles>
+__device__ __forceinline__ void cull2_body(const Bundles &bd, const BlockLists bl, int *work, const cull::Emitter em,
+                                           sweep::Counters *counters) {
+    constexpr int R = 8;
+    __shared__ cull::ListSmem lsm;
+    __shared__ int s_item;
+    __shared__ unsigned long long s_end;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const unsigned long long n_items = (bl.n_keys + CULL_SEG - 1) / CULL_SEG;
+    unsigned d_l1 = 0;
+    cull::WarpChunk wc{0, cull::CHUNK}; // no chunk yet
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work, 1);
+        __syncthreads();
+        const unsigned long long item = (unsigned long long)s_item;
+        if (item >= n_items) break;
+        unsigned long long pos = item * CULL_SEG;
+        const unsigned long long end = min(bl.n_keys, pos + CULL_SEG);
+        while (pos < end) {
+            const int blk = (int)(bl.keys[pos] >> 32);
+            if (tid == 0) s_end = pos + cull::lower_bound_key(bl.keys + pos, end - pos, (unsigned long long)(unsigned)(blk + 1) << 32);
+            __syncthreads();
+            const unsigned long long run_end = s_end;
+            float rp[R], rq[R];
+            int kp[R];
+            unsigned valid;
+            const float4 *tab = bd.template load<R>(blk, rp, rq, kp, valid);
+            const cull::Box wb = bl.boxes[blk].warp[warp];
+            cull::walk_block_list<R>(lsm, bl.keys, pos, run_end, tab, rp, rq, valid, kp, wb, em, wc, d_l1);
+            pos = run_end;
+            __syncthreads(); // s_end is rewritten by the next run
+        }
+    }
+    cull::chunk_close(em, wc);
+    if ((tid & 31) == 0) atomicAdd(&counters->cull_l1, (unsigned long long)d_l1);
+}
+
+__global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull2_kernel(const PrimaryCullParams p, const BlockLists bl) {
+    cull2_body(PrimaryBundles{p}, bl, p.work, p.em, p.counters);
+}
+
+__global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull2_kernel(const ShadowCullParams p, const BlockLists bl) {
+    cull2_body(ShadowBundles{p}, bl, p.work, p.em, p.counters);
 }
 
 // ---------------------------------------------------------------------------------

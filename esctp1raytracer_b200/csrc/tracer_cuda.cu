@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -137,6 +138,8 @@ struct tracer_scene_dev {
     float *accum_total = nullptr;
     // bundle-cull mode: candidate (ray<<32|triangle) buffers, their count, radix-sort scratch
     unsigned long long *cand_a = nullptr, *cand_b = nullptr, *cand_count = nullptr, *rkey = nullptr, *rkey_sorted = nullptr;
+    cull::BlockBoxes *boxes = nullptr; // two-phase bundle cull: boxes of every ray block
+    size_t boxes_cap = 0;
     int *iota = nullptr;
     size_t pair_bytes = 0;
     void *pair_tmp = nullptr;
@@ -213,6 +216,18 @@ int launch_shadow(int R, bool ex, const trk::ShadowParams &p, int grid, cudaStre
 struct Decomp {
     int R, n_blocks, n_slices;
 };
+// (ray block, triangle slice) work items wanted per SM.  The tail of a sweep is at most one item long, but
+// every item pays for its own ray set-up: closest-hit items compute their rays (cheap) and are cut fine,
+// shadow items gather theirs from the pixel state and stay coarser.  (TRACER_ITEMS_PER_SM overrides both:
+// development knob.)
+int items_per_sm(bool closest) {
+    static const int forced = [] {
+        const char *e = std::getenv("TRACER_ITEMS_PER_SM");
+        return e ? std::atoi(e) : 0;
+    }();
+    return forced > 0 ? forced : closest ? 32 : 12;
+}
+
 Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks) {
     const int slices_possible = std::max(1, n_tiles / 4); // at least 4 tiles per slice
     auto blocks_for = [&](int R) {
@@ -227,8 +242,9 @@ Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int ext
             if ((int64_t)d.n_blocks * slices_possible >= 4 * (int64_t)n_sms) break;
         }
     }
-    const int64_t want = (6 * (int64_t)n_sms + d.n_blocks - 1) / std::max(1, d.n_blocks);
-    d.n_slices = d.n_blocks >= 6 * n_sms ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want, slices_possible));
+    const int64_t ips = items_per_sm(true);
+    const int64_t want = (ips * (int64_t)n_sms + d.n_blocks - 1) / std::max(1, d.n_blocks);
+    d.n_slices = d.n_blocks >= ips * n_sms ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want, slices_possible));
     return d;
 }
 
@@ -309,6 +325,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
     dev_free(s->n_slices);
     dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count), dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
+    dev_free(s->boxes);
     g_pool.release(s->sort_tmp), g_pool.release(s->pair_tmp);
     dev_free(s->counters);
     for (auto &e : s->ev)
@@ -561,6 +578,42 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         ++launches;
         return 0;
     };
+    // two-phase bundle cull (cull.cuh "block lists"): phase A emits block<<32|triangle into cand_a; the sorted
+    // keys land in cand_b, which phase B reads while it emits its ray<<32|triangle candidates into cand_a again.
+    // Returns the number of keys, or -1 when the survivor lists would not fit (then the streaming kernels run).
+    const bool two_phase = cull && o.bundle_cull != 2;
+    int64_t host_tests_primary = 0, host_tests_shadow = 0; // pairs considered by two-phase sweeps (every block x every triangle)
+    auto ensure_boxes = [&](size_t n_blocks) -> int {
+        if (n_blocks <= s->boxes_cap) return 0;
+        dev_free(s->boxes);
+        s->boxes_cap = 0;
+        if (dev_alloc(&s->boxes, n_blocks)) return TRACER_ERR_NOMEM;
+        s->boxes_cap = n_blocks;
+        return 0;
+    };
+    auto block_lists = [&](cull::L0Params lp, int max_blocks, long long &n_keys) -> int {
+        lp.boxes = s->boxes, lp.keys = s->cand_a, lp.count = s->cand_count, lp.cap = (unsigned long long)s->cand_cap;
+        lp.n_tris = s->n_tris, lp.diag = s->counters;
+        CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
+        const dim3 grid((unsigned)((s->n_tris + cull::L0_THREADS - 1) / cull::L0_THREADS), (unsigned)lp.n_groups);
+        cull::cull_l0_kernel<<<grid, cull::L0_THREADS, 0, st>>>(lp);
+        CK_CUDA(cudaGetLastError());
+        unsigned long long n = 0;
+        CK_CUDA(cudaMemcpyAsync(&n, s->cand_count, sizeof n, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(cudaStreamSynchronize(st));
+        CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
+        launches += 2;
+        if (getenv("TRACER_CULL_DIAG")) fprintf(stderr, "cull diag: phase A kept %llu (block, triangle) pairs over %d groups, <= %d blocks\n", n, lp.n_groups, max_blocks);
+        if (n > s->cand_cap) {
+            n_keys = -1;
+            return 0;
+        }
+        int blk_bits = 1;
+        while ((1 << blk_bits) < max_blocks) ++blk_bits;
+        if (n) CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n, 0, 32 + blk_bits, st));
+        n_keys = (long long)n;
+        return 0;
+    };
     double ms_primary_acc = 0, ms_shadow_acc = 0;
     if (S > 1 && !s->accum_total && dev_alloc(&s->accum_total, 3 * (size_t)s->ws_npx)) return TRACER_ERR_NOMEM;
     for (int smp = 0; smp < S; ++smp) {
@@ -579,11 +632,26 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.n_slices = blocks >= 12 * g.n_sms ? 1 : std::max(1, std::min((12 * g.n_sms + blocks - 1) / blocks, std::max(1, c_tiles / 8)));
         p.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
         p.counters = s->counters, p.work = s->work;
-        CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
-        const size_t smem = sizeof(cull::EmitSmem);
-        CK_CUDA(cudaFuncSetAttribute(trk::primary_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, 2 * g.n_sms), sweep::THREADS, smem, st>>>(p);
-        CK_CUDA(cudaGetLastError());
+        long long n_keys = -1;
+        if (two_phase) {
+            if (int rc = ensure_boxes((size_t)blocks)) return rc;
+            trk::primary_boxes_kernel<<<blocks, sweep::THREADS, 0, st>>>(p, s->boxes, s->blk_off);
+            CK_CUDA(cudaGetLastError());
+            cull::L0Params lp{};
+            lp.tables = s->eye_table, lp.n_groups = 1, lp.nface = 0, lp.blk_off = s->blk_off;
+            if (int rc = block_lists(lp, blocks, n_keys)) return rc;
+        }
+        if (n_keys >= 0) {
+            trk::primary_cull2_kernel<<<2 * g.n_sms, sweep::THREADS, 0, st>>>(p, trk::BlockLists{s->boxes, s->cand_b, (unsigned long long)n_keys});
+            CK_CUDA(cudaGetLastError());
+            host_tests_primary += (int64_t)n_px * s->n_tris;
+        } else {
+            CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
+            const size_t smem = sizeof(cull::EmitSmem);
+            CK_CUDA(cudaFuncSetAttribute(trk::primary_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, 2 * g.n_sms), sweep::THREADS, smem, st>>>(p);
+            CK_CUDA(cudaGetLastError());
+        }
         unsigned long long n_cand = 0;
         if (int rc = sort_candidates(n_cand)) return rc;
         if (n_cand) {
@@ -703,11 +771,28 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.list = s->list, sp.seg_off = s->seg_off, sp.seg_cnt = s->cursor, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
             sp.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
-            CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
-            const size_t smem = sizeof(cull::EmitSmem);
-            CK_CUDA(cudaFuncSetAttribute(trk::shadow_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            trk::shadow_cull_kernel<<<2 * g.n_sms, sweep::THREADS, smem, st>>>(sp);
-            CK_CUDA(cudaGetLastError());
+            long long n_keys = -1;
+            if (two_phase) {
+                const int max_blocks = n_px / rpb + F + 1;
+                if (int rc = ensure_boxes((size_t)max_blocks)) return rc;
+                trk::shadow_boxes_kernel<<<max_blocks, sweep::THREADS, 0, st>>>(sp, s->boxes);
+                CK_CUDA(cudaGetLastError());
+                cull::L0Params lp{};
+                lp.tables = sp.tables, lp.allcand = sp.allcand, lp.table_stride = sp.table_stride;
+                lp.n_groups = F, lp.nface = trk::NFACE, lp.blk_off = s->blk_off;
+                if (int rc = block_lists(lp, max_blocks, n_keys)) return rc;
+            }
+            if (n_keys >= 0) {
+                trk::shadow_cull2_kernel<<<2 * g.n_sms, sweep::THREADS, 0, st>>>(sp, trk::BlockLists{s->boxes, s->cand_b, (unsigned long long)n_keys});
+                CK_CUDA(cudaGetLastError());
+                for (int c : gcnt) host_tests_shadow += (int64_t)c * s->n_pad;
+            } else {
+                CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
+                const size_t smem = sizeof(cull::EmitSmem);
+                CK_CUDA(cudaFuncSetAttribute(trk::shadow_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                trk::shadow_cull_kernel<<<2 * g.n_sms, sweep::THREADS, smem, st>>>(sp);
+                CK_CUDA(cudaGetLastError());
+            }
             unsigned long long n_cand = 0;
             if (int rc = sort_candidates(n_cand)) return rc;
             if (n_cand) {
@@ -760,7 +845,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 if (int rc = build_face_tables(k, h_cnt)) return rc;
             const int tile_lo = (int)((int64_t)n_tiles * c / n_chunks), tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
             trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::THREADS * Rk, tile_hi - tile_lo, g.n_sms, s->blk_off, cnt_out,
-                                                       s->work, s->n_slices);
+                                                       s->work, s->n_slices, items_per_sm(false), 4);
             CK_CUDA(cudaGetLastError());
             trk::ShadowParams sp{};
             sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
@@ -842,8 +927,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.ms_other = s->stats.ms_total - s->stats.ms_primary - sh;
     s->stats.n_primary_rays = (int64_t)n_px * S;
     s->stats.n_shadow_rays = (int64_t)hc.n_hits * L;
-    s->stats.tests_primary = (int64_t)hc.tests_primary;
-    s->stats.tests_shadow = (int64_t)hc.tests_shadow;
+    s->stats.tests_primary = (int64_t)hc.tests_primary + host_tests_primary;
+    s->stats.tests_shadow = (int64_t)hc.tests_shadow + host_tests_shadow;
     s->stats.tests_shadow_ref = (int64_t)hc.tests_shadow_ref;
     s->stats.strict_evals = (int64_t)hc.strict_evals;
     s->stats.filter_misses = (int64_t)hc.filter_misses;

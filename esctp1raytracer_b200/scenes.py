@@ -4,6 +4,9 @@
   spirit of the Cornell models the reference is run on (scripts/run.sh:28-30).
 * ``soup_scene`` — BASELINE.json config 4/5: n triangles in G geometries, L quad
   lights under the ceiling, optional analytic spheres (extension).
+* ``from_npz``   — a flat scene stored by tests/golden/make_golden.py: the reference's own
+  ``model::loadobj`` output for one of its shipped OBJ models (the models themselves live in
+  the reference tree and do not travel to the GPU box).
 """
 from __future__ import annotations
 
@@ -145,3 +148,12 @@ def soup_scene(n_tris=1_000_000, n_geoms=1000, n_lights=4, n_spheres=0, seed=42,
         smat[:, 12] = 10.0
     return Scene(np.array(off), verts, mats, np.arange(1, 1 + n_lights), tri_normals=normals, geom_has_normals=has_n,
                  sphere_cr=sph, sphere_material=smat)
+
+
+def from_npz(path):
+    """Scene + (eye, look) from a fixture written by tests/golden/make_golden.py."""
+    d = np.load(path)
+    sc = Scene(d["geom_tri_offset"], d["tri_verts"], d["geom_material"], d["light_geom"],
+               tri_normals=d["tri_normals"] if "tri_normals" in d.files else None,
+               geom_has_normals=d["geom_has_normals"] if "geom_has_normals" in d.files else None)
+    return sc, tuple(float(x) for x in d["eye"]), tuple(float(x) for x in d["look"])

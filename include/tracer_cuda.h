@@ -112,7 +112,8 @@ typedef struct tracer_render_opts {
     int32_t rays_per_thread;   /* tuning: 0 = auto, else 2, 4 or 8 rays per thread in the sweeps */
     int32_t shadow_chunks;     /* tuning: 0 = auto; triangle chunks between shadow-ray compactions */
     int32_t bundle_cull;       /* OPTIONAL mode: hierarchical (bundle box -> warp box -> ray) evaluation of the same
-                                  conservative filter; identical results, L2/smem-stream bound instead of FP32 bound */
+                                  conservative filter; identical results.  1 = two-phase (dense block-box pass, then
+                                  per-block survivor lists), 2 = single streaming sweep (also the fall-back of 1) */
 
     /* optional debug outputs, HOST pointers, indexed like the output rows
      * (local pixel k = local_row*W + w), any may be NULL */

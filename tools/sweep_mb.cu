@@ -251,6 +251,46 @@ __global__ void __launch_bounds__(512, 1) k_2d(const float4 *tile_g, int reps, f
     if (hits == 123456789) out[0] = hits;
 }
 
+
+// V7: 2-D rows, saturating rows + product accumulate: everything in the FMA pipe (no LOP3).
+// rows are pre-scaled so that a true candidate saturates to exactly 1: ind = x'*y'*z', acc += ind over the batch
+template <int R, int NACC, int BATCH, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_sat(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE * 3];
+    for (int i = threadIdx.x; i < TILE * 3; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float px[R], py[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) px[r] = seed * (threadIdx.x + 1) * (r + 1), py[r] = seed * (threadIdx.x + 7) * (r + 3);
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TILE; b += BATCH) {
+            float acc[NACC];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+#pragma unroll UNROLL
+            for (int k = 0; k < BATCH; ++k) {
+                const float4 rb = tile[3 * (b + k)], rc = tile[3 * (b + k) + 1], rd = tile[3 * (b + k) + 2];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float x = __saturatef(fmaf(px[r], rb.x, fmaf(py[r], rb.y, rb.z)));
+                    const float y = __saturatef(fmaf(px[r], rc.x, fmaf(py[r], rc.y, rc.z)));
+                    const float z = __saturatef(fmaf(px[r], rd.x, fmaf(py[r], rd.y, rd.z)));
+                    acc[r % NACC] = fmaf(x * y, z, acc[r % NACC]);
+                }
+            }
+            float s = acc[0];
+#pragma unroll
+            for (int a = 1; a < NACC; ++a) s += acc[a];
+            if (s >= 1.f) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
 // VP: the production data path (TMA tile stream + mbarrier + per-tile barrier) without the strict path
 template <int R>
 __global__ void __launch_bounds__(sweep::THREADS, 1) k_prod(const float4 *table, int n_tiles, int n_blocks, int *work, float *out, float seed) {
@@ -355,6 +395,11 @@ int main() {
     run("2D LOP3 R=8 b8 u4", [&] { k_2d<8, 1, 0, 8, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
     run("2D LOP3 R=8 b16 u4 256thr", [&] { k_2d<8, 1, 0, 16, 4><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
     run("2D LOP3 R=8 b16 u4 384thr", [&] { k_2d<8, 1, 0, 16, 4><<<sms, 384>>>(tile_g, reps, out, seed); }, PAIRS(384, 8));
+    printf("-- k_sat: saturating rows + product accumulate (8 FMA-pipe ops / pair, no LOP3); same 18-flop-equiv column\n");
+#define ST(R, N, B, U) run("SAT R=" #R " acc" #N " b" #B " u" #U, [&] { k_sat<R, N, B, U><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, R));
+    ST(8, 1, 16, 4) ST(8, 2, 16, 4) ST(8, 4, 16, 4) ST(8, 8, 16, 4) ST(8, 2, 16, 2) ST(8, 2, 32, 4) ST(8, 2, 16, 8) ST(10, 2, 16, 4) ST(12, 2, 16, 2) ST(6, 2, 16, 4) ST(4, 2, 16, 4)
+    run("SAT R=8 acc2 b16 u4 256thr", [&] { k_sat<8, 2, 16, 4><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
+    run("SAT R=8 acc2 b16 u4 384thr", [&] { k_sat<8, 2, 16, 4><<<sms, 384>>>(tile_g, reps, out, seed); }, PAIRS(384, 8));
     {   // production data path
         const int n_tiles = 400;
         std::vector<float> ht((size_t)n_tiles * TILE * 12, 0.f);
