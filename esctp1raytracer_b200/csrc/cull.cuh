@@ -46,6 +46,18 @@ __device__ __forceinline__ Box make_box(float pmin, float pmax, float qmin, floa
     return b;
 }
 
+// box of the R rays held by one thread
+template <int R>
+__device__ __forceinline__ Box lane_box_of(const float (&rp)[R], const float (&rq)[R]) {
+    float pmin = rp[0], pmax = rp[0], qmin = rq[0], qmax = rq[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        pmin = fminf(pmin, rp[r]), pmax = fmaxf(pmax, rp[r]);
+        qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+    }
+    return make_box(pmin, pmax, qmin, qmax);
+}
+
 // warp box and CTA box of the rays held by this thread block (rp/rq of invalid rays must be duplicates
 // of valid ones).  scratch: 4 * THREADS/32 floats of shared memory.
 template <int R>
@@ -221,7 +233,7 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
 // separates the levels into dense kernels:
 //   phase A  cull_l0_kernel: EVERY (ray block, triangle) pair — still no acceleration structure, no build
 //            step — with one triangle per thread held in registers and the block boxes broadcast from
-//            shared memory; survivors are appended as block<<32|triangle and radix-sorted;
+//            shared memory; survivors are appended as block<<tri_bits|triangle and radix-sorted;
 //   phase B  walk_block_list: each warp of the ray block walks the block's (short) survivor list 32 triangles
 //            at a time against its own warp box, then per ray, and emits ray<<32|triangle candidates.
 // The candidates then take the same sort + strict path as before, so results stay bit-identical.
@@ -235,6 +247,7 @@ struct L0Params {
     const float4 *allcand; // group with j % nface == nface - 1
     size_t table_stride;
     int n_groups, nface, n_tris;
+    int tri_bits;       // keys are block << tri_bits | triangle: fewer radix passes than a 32-bit split
     const int *blk_off; // [n_groups + 1] ray blocks of each group (device)
     const BlockBoxes *boxes;
     unsigned long long *keys, *count;
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(L0_THREADS) cull_l0_kernel(const L0Params p) {
             const bool pass = live && !(box_sign(rb, rc, rd, sbox[i]) >> 31);
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
-                if (pass) st[fill + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)(b0 + i) << 32) | (unsigned)tri;
+                if (pass) st[fill + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)(b0 + i) << p.tri_bits) | (unsigned)tri;
                 fill += __popc(m);
                 if (fill > L0_STAGE - 32) flush();
             }
@@ -305,7 +318,7 @@ __device__ __forceinline__ unsigned long long lower_bound_key(const unsigned lon
     return lo;
 }
 
-// phase B: the block's sorted survivor list keys[lo, hi) (low word = triangle).  The CTA stages LTILE rows at a
+// phase B: the block's sorted survivor list keys[lo, hi) (low tri_bits = triangle).  The CTA stages LTILE rows at a
 // time in shared memory (each row gathered from the table ONCE per block); every warp then tests the staged rows
 // against its own box, one row per lane, and the rows that pass go through the per-ray filter (row broadcast
 // from shared memory); candidates are appended through the warp's chunk.
@@ -316,16 +329,16 @@ struct ListSmem {
 };
 template <int R>
 __device__ __forceinline__ void walk_block_list(ListSmem &sm, const unsigned long long *__restrict__ keys, unsigned long long lo,
-                                                unsigned long long hi, const float4 *__restrict__ table, const float (&rp)[R],
+                                                unsigned long long hi, unsigned tri_mask, const float4 *__restrict__ table, const float (&rp)[R],
                                                 const float (&rq)[R], unsigned valid, const int (&ray_id)[R], const Box warp_box,
-                                                const Emitter em, WarpChunk &wc, unsigned &d_l1) {
+                                                const Box lane_box, const Emitter em, WarpChunk &wc, unsigned &d_l1) {
     using sweep::edge_sign;
     const int tid = threadIdx.x, lane = tid & 31;
     for (unsigned long long i0 = lo; i0 < hi; i0 += LTILE) {
         const int n = (int)((hi - i0) < (unsigned long long)LTILE ? (hi - i0) : (unsigned long long)LTILE);
         __syncthreads(); // previous tile fully consumed
         if (tid < n) {
-            const unsigned t = (unsigned)keys[i0 + tid];
+            const unsigned t = (unsigned)keys[i0 + tid] & tri_mask;
             sm.tri[tid] = t;
             sm.row[3 * tid] = __ldg(&table[3 * (size_t)t]);
             sm.row[3 * tid + 1] = __ldg(&table[3 * (size_t)t + 1]);
@@ -344,9 +357,11 @@ __device__ __forceinline__ void walk_block_list(ListSmem &sm, const unsigned lon
                 const float4 rb = sm.row[3 * e], rc = sm.row[3 * e + 1], rd = sm.row[3 * e + 2];
                 unsigned mask = 0;
                 ++d_l1;
+                if (!(box_sign(rb, rc, rd, lane_box) >> 31)) { // level 2: the box of this lane's own R rays
 #pragma unroll
-                for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
-                mask &= valid;
+                    for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                    mask &= valid;
+                }
                 if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
                 emit_pairs<R>(em, wc, mask, ray_id, sm.tri[e]);
             }

@@ -750,29 +750,35 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
     atomicAdd(&p.counters->tests_primary, tests);
 }
 
-// One thread per ray: walk the ray's candidates (sorted: triangle index ascending = the reference's iteration
-// order) with the strict arithmetic.  Closest hit: cpp_intersect semantics (main.cpp:176-192).
-__global__ void strict_primary_from_candidates(const unsigned long long *__restrict__ cand, unsigned long long n, Cam cam,
-                                               Bands bands, const float *__restrict__ tri_verts, unsigned long long *best,
-                                               sweep::Counters *counters) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per candidate pair, in whatever order the culled sweep emitted them.  Closest hit (cpp_intersect,
+// main.cpp:176-192) is the lexicographic minimum of (t, index) over all valid hits and the first occluder
+// (occlusion(), main.cpp:314-329) the minimum index over all valid hits, so — exactly like the triangle slices
+// of the default mode — every pair is evaluated independently with the reference's arithmetic and merged with
+// a 64-bit atomicMin; no sort of the candidates is needed.  *count may exceed cap (entries beyond cap were
+// dropped by the emitter): that is reported through counters->cull_overflow and fails the frame.
+__global__ void strict_primary_pairs(const unsigned long long *__restrict__ cand, const unsigned long long *__restrict__ count,
+                                     unsigned long long cap, Cam cam, Bands bands, const float *__restrict__ tri_verts,
+                                     unsigned long long *best, sweep::Counters *counters) {
+    unsigned long long n = *count;
+    if (n > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->cull_overflow, 1ull);
+        n = cap;
+    }
     unsigned n_strict = 0;
-    if (i < n) {
-        const unsigned ray = (unsigned)(cand[i] >> 32);
-        if (ray != 0xffffffffu && (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray)) { // head of this ray's run
-            int w, h;
-            bands.map((int)ray, w, h);
-            const f3 o = strict::ld(cam.o), d = primary_dir(cam, bands, w, h);
-            float t = FLT_MAX, v = 0.f; // main.cpp:715-717
-            int tri = -1;
-            for (unsigned long long j = i; j < n && (unsigned)(cand[j] >> 32) == ray; ++j) {
-                const int tr = (int)(unsigned)(cand[j] & 0xffffffffu);
-                const float *q = tri_verts + 9 * (size_t)tr;
-                ++n_strict;
-                if (strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v)) tri = tr;
-            }
-            if (tri >= 0) best[ray] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri;
-        }
+    const f3 o = strict::ld(cam.o);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = cand[i];
+        const unsigned ray = (unsigned)(key >> 32);
+        if (ray == 0xffffffffu) continue; // unused tail of a warp's chunk
+        const int tr = (int)(unsigned)(key & 0xffffffffu);
+        int w, h;
+        bands.map((int)ray, w, h);
+        const f3 d = primary_dir(cam, bands, w, h);
+        const float *q = tri_verts + 9 * (size_t)tr;
+        float t = FLT_MAX, v = 0.f; // main.cpp:715-717
+        ++n_strict;
+        if (strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v))
+            atomicMin(&best[ray], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tr);
     }
     for (int o2 = 16; o2; o2 >>= 1) n_strict += __shfl_down_sync(0xffffffffu, n_strict, o2);
     if ((threadIdx.x & 31) == 0 && n_strict) atomicAdd(&counters->strict_evals, (unsigned long long)n_strict);
@@ -797,11 +803,11 @@ __device__ __forceinline__ void load_shadow_bundle(const ShadowCullParams &p, in
                                                    int (&kp)[R], unsigned &valid) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n_px;
     const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
-    const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane;
+    const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane * R;
     valid = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        int e = base + r * 32; // a warp holds 32*R consecutive rays of the sorted list: a compact cell range
+        int e = base + r; // a warp holds 32*R consecutive rays of the sorted list, a lane R consecutive ones: compact cell ranges
         if (e < seg_end) valid |= 1u << r;
         e = min(e, seg_end - 1);
         const int k = p.list[e];
@@ -859,28 +865,28 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const Sh
     atomicAdd(&p.counters->tests_shadow, tests);
 }
 
-// One thread per shadow ray: occlusion() semantics (main.cpp:314-329) over the ray's sorted candidates:
-// the first accepted face in order ends the ray and leaves t = t2 behind.
-__global__ void strict_shadow_from_candidates(const unsigned long long *__restrict__ cand, unsigned long long n, PixelState px,
-                                              int n_px, const float *__restrict__ tri_verts, sweep::Counters *counters) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+// shadow rays: one thread per candidate pair; an accepted pair leaves t = t2 behind (the multi-light carry)
+__global__ void strict_shadow_pairs(const unsigned long long *__restrict__ cand, const unsigned long long *__restrict__ count,
+                                    unsigned long long cap, PixelState px, int n_px, const float *__restrict__ tri_verts,
+                                    sweep::Counters *counters) {
+    unsigned long long n = *count;
+    if (n > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->cull_overflow, 1ull);
+        n = cap;
+    }
     unsigned n_strict = 0;
-    if (i < n) {
-        const unsigned ray = (unsigned)(cand[i] >> 32);
-        if (ray != 0xffffffffu && (i == 0 || (unsigned)(cand[i - 1] >> 32) != ray)) {
-            const f3 o = strict::mk(px.ro[ray], px.ro[n_px + ray], px.ro[2 * (size_t)n_px + ray]);
-            const f3 d = strict::mk(px.rd[ray], px.rd[n_px + ray], px.rd[2 * (size_t)n_px + ray]);
-            float t = px.rt[ray], v;
-            for (unsigned long long j = i; j < n && (unsigned)(cand[j] >> 32) == ray; ++j) {
-                const int tr = (int)(unsigned)(cand[j] & 0xffffffffu);
-                const float *q = tri_verts + 9 * (size_t)tr;
-                ++n_strict;
-                if (strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v)) {
-                    px.best_occ[ray] = ((unsigned long long)(unsigned)tr << 32) | __float_as_uint(t);
-                    break;
-                }
-            }
-        }
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = cand[i];
+        const unsigned ray = (unsigned)(key >> 32);
+        if (ray == 0xffffffffu) continue;
+        const int tr = (int)(unsigned)(key & 0xffffffffu);
+        const f3 o = strict::mk(px.ro[ray], px.ro[n_px + ray], px.ro[2 * (size_t)n_px + ray]);
+        const f3 d = strict::mk(px.rd[ray], px.rd[n_px + ray], px.rd[2 * (size_t)n_px + ray]);
+        float t = px.rt[ray], v;
+        const float *q = tri_verts + 9 * (size_t)tr;
+        ++n_strict;
+        if (strict::intersect_triangle(o, d, strict::ld(q), strict::ld(q + 3), strict::ld(q + 6), t, v))
+            atomicMin(&px.best_occ[ray], ((unsigned long long)(unsigned)tr << 32) | __float_as_uint(t));
     }
     for (int o2 = 16; o2; o2 >>= 1) n_strict += __shfl_down_sync(0xffffffffu, n_strict, o2);
     if ((threadIdx.x & 31) == 0 && n_strict) atomicAdd(&counters->strict_evals, (unsigned long long)n_strict);
@@ -923,8 +929,9 @@ __global__ void __launch_bounds__(sweep::THREADS) shadow_boxes_kernel(const Shad
 
 struct BlockLists {
     const cull::BlockBoxes *boxes;
-    const unsigned long long *keys; // sorted block<<32|triangle survivors of phase A
+    const unsigned long long *keys; // sorted block<<tri_bits|triangle survivors of phase A
     unsigned long long n_keys;
+    int tri_bits;
 };
 
 // phase B.  Work item = a fixed-size segment of the sorted key array (so a ray block with a very long survivor
@@ -970,8 +977,8 @@ __device__ __forceinline__ void cull2_body(const Bundles &bd, const BlockLists b
         unsigned long long pos = item * CULL_SEG;
         const unsigned long long end = min(bl.n_keys, pos + CULL_SEG);
         while (pos < end) {
-            const int blk = (int)(bl.keys[pos] >> 32);
-            if (tid == 0) s_end = pos + cull::lower_bound_key(bl.keys + pos, end - pos, (unsigned long long)(unsigned)(blk + 1) << 32);
+            const int blk = (int)(bl.keys[pos] >> bl.tri_bits);
+            if (tid == 0) s_end = pos + cull::lower_bound_key(bl.keys + pos, end - pos, (unsigned long long)(unsigned)(blk + 1) << bl.tri_bits);
             __syncthreads();
             const unsigned long long run_end = s_end;
             float rp[R], rq[R];
@@ -979,7 +986,8 @@ __device__ __forceinline__ void cull2_body(const Bundles &bd, const BlockLists b
             unsigned valid;
             const float4 *tab = bd.template load<R>(blk, rp, rq, kp, valid);
             const cull::Box wb = bl.boxes[blk].warp[warp];
-            cull::walk_block_list<R>(lsm, bl.keys, pos, run_end, tab, rp, rq, valid, kp, wb, em, wc, d_l1);
+            cull::walk_block_list<R>(lsm, bl.keys, pos, run_end, (1u << bl.tri_bits) - 1u, tab, rp, rq, valid, kp, wb,
+                                     cull::lane_box_of<R>(rp, rq), em, wc, d_l1);
             pos = run_end;
             __syncthreads(); // s_end is rewritten by the next run
         }

@@ -119,6 +119,7 @@ struct __align__(128) Smem {
 struct Counters {
     unsigned long long tests_primary, tests_shadow, strict_evals, tests_shadow_ref, n_hits, filter_misses;
     unsigned long long cull_l0, cull_l1, cull_tiles_any, cull_tiles_fallback; // bundle-cull diagnostics
+    unsigned long long cull_overflow; // bundle-cull: a candidate buffer was too small (the frame is rejected)
 };
 
 // One 48-byte row triple per triangle: rb = (A,B,C,-) of s*u', rc of s*v', rd of s*w'.

@@ -565,19 +565,6 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         CK_CUDA(cudaGetLastError());
         s->rkey_npx = n_px;
     }
-    int ray_bits = 1;
-    while (((int64_t)1 << ray_bits) < n_px) ++ray_bits;
-    // candidates emitted by a culled sweep -> count (host), sorted ray-major / triangle-minor in cand_b
-    auto sort_candidates = [&](unsigned long long &n_cand) -> int {
-        CK_CUDA(cudaMemcpyAsync(&n_cand, s->cand_count, sizeof n_cand, cudaMemcpyDeviceToHost, st));
-        CK_CUDA(cudaStreamSynchronize(st));
-        if (n_cand > s->cand_cap)
-            return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow (" + std::to_string(n_cand) + " pairs); use the default mode");
-        if (n_cand)
-            CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n_cand, 0, 33 + ray_bits, st));
-        ++launches;
-        return 0;
-    };
     // two-phase bundle cull (cull.cuh "block lists"): phase A emits block<<32|triangle into cand_a; the sorted
     // keys land in cand_b, which phase B reads while it emits its ray<<32|triangle candidates into cand_a again.
     // Returns the number of keys, or -1 when the survivor lists would not fit (then the streaming kernels run).
@@ -591,9 +578,11 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         s->boxes_cap = n_blocks;
         return 0;
     };
+    int tri_bits = 1;
+    while (((int64_t)1 << tri_bits) < s->n_pad) ++tri_bits;
     auto block_lists = [&](cull::L0Params lp, int max_blocks, long long &n_keys) -> int {
         lp.boxes = s->boxes, lp.keys = s->cand_a, lp.count = s->cand_count, lp.cap = (unsigned long long)s->cand_cap;
-        lp.n_tris = s->n_tris, lp.diag = s->counters;
+        lp.n_tris = s->n_tris, lp.tri_bits = tri_bits, lp.diag = s->counters;
         CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
         const dim3 grid((unsigned)((s->n_tris + cull::L0_THREADS - 1) / cull::L0_THREADS), (unsigned)lp.n_groups);
         cull::cull_l0_kernel<<<grid, cull::L0_THREADS, 0, st>>>(lp);
@@ -610,7 +599,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         }
         int blk_bits = 1;
         while ((1 << blk_bits) < max_blocks) ++blk_bits;
-        if (n) CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n, 0, 32 + blk_bits, st));
+        if (n) CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n, 0, tri_bits + blk_bits, st));
         n_keys = (long long)n;
         return 0;
     };
@@ -642,7 +631,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             if (int rc = block_lists(lp, blocks, n_keys)) return rc;
         }
         if (n_keys >= 0) {
-            trk::primary_cull2_kernel<<<2 * g.n_sms, sweep::THREADS, 0, st>>>(p, trk::BlockLists{s->boxes, s->cand_b, (unsigned long long)n_keys});
+            trk::primary_cull2_kernel<<<2 * g.n_sms, sweep::THREADS, 0, st>>>(p, trk::BlockLists{s->boxes, s->cand_b, (unsigned long long)n_keys, tri_bits});
             CK_CUDA(cudaGetLastError());
             host_tests_primary += (int64_t)n_px * s->n_tris;
         } else {
@@ -652,13 +641,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, 2 * g.n_sms), sweep::THREADS, smem, st>>>(p);
             CK_CUDA(cudaGetLastError());
         }
-        unsigned long long n_cand = 0;
-        if (int rc = sort_candidates(n_cand)) return rc;
-        if (n_cand) {
-            trk::strict_primary_from_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(s->cand_b, n_cand, dc, bands, s->tri_verts,
-                                                                                                 s->best, s->counters);
-            CK_CUDA(cudaGetLastError());
-        }
+        trk::strict_primary_pairs<<<8 * g.n_sms, 256, 0, st>>>(s->cand_a, s->cand_count, (unsigned long long)s->cand_cap, dc, bands,
+                                                               s->tri_verts, s->best, s->counters);
+        CK_CUDA(cudaGetLastError());
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
                                                                         s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
         CK_CUDA(cudaGetLastError());
@@ -783,7 +768,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 if (int rc = block_lists(lp, max_blocks, n_keys)) return rc;
             }
             if (n_keys >= 0) {
-                trk::shadow_cull2_kernel<<<2 * g.n_sms, sweep::THREADS, 0, st>>>(sp, trk::BlockLists{s->boxes, s->cand_b, (unsigned long long)n_keys});
+                trk::shadow_cull2_kernel<<<2 * g.n_sms, sweep::THREADS, 0, st>>>(sp, trk::BlockLists{s->boxes, s->cand_b, (unsigned long long)n_keys, tri_bits});
                 CK_CUDA(cudaGetLastError());
                 for (int c : gcnt) host_tests_shadow += (int64_t)c * s->n_pad;
             } else {
@@ -793,13 +778,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 trk::shadow_cull_kernel<<<2 * g.n_sms, sweep::THREADS, smem, st>>>(sp);
                 CK_CUDA(cudaGetLastError());
             }
-            unsigned long long n_cand = 0;
-            if (int rc = sort_candidates(n_cand)) return rc;
-            if (n_cand) {
-                trk::strict_shadow_from_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(s->cand_b, n_cand, px, n_px,
-                                                                                                    s->tri_verts, s->counters);
-                CK_CUDA(cudaGetLastError());
-            }
+            trk::strict_shadow_pairs<<<8 * g.n_sms, 256, 0, st>>>(s->cand_a, s->cand_count, (unsigned long long)s->cand_cap, px, n_px,
+                                                                  s->tri_verts, s->counters);
+            CK_CUDA(cudaGetLastError());
             launches += 4;
             if (s->n_spheres > 0) {
                 const dim3 sgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
@@ -933,6 +914,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.strict_evals = (int64_t)hc.strict_evals;
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.kernel_launches = launches;
+    if (hc.cull_overflow)
+        return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow; use the default mode for this scene");
     if (getenv("TRACER_CULL_DIAG"))
         fprintf(stderr, "cull diag (shadow): l0 survivors %llu, tiles with any %llu, fallback tiles %llu, l1 warp-passes %llu, item-tiles %llu\n", hc.cull_l0,
                 hc.cull_tiles_any, hc.cull_tiles_fallback, hc.cull_l1, (unsigned long long)(hc.tests_shadow / 4096 / cull::CTILE));
