@@ -26,6 +26,7 @@ constexpr int CTA_WALK = 24; // CTA-box survivors per tile above which each warp
 
 struct Box {
     float pc, ph, qc, qh;
+    float lmax; // longest ray of the bundle (distance from the rays' common point O to the far end); FLT_MAX: unbounded
 };
 
 // sign word of the three edge-function maxima over the box: sign bit clear <=> all three >= 0
@@ -33,13 +34,16 @@ __device__ __forceinline__ unsigned box_sign(const float4 rb, const float4 rc, c
     const float x = fmaf(rb.x, b.pc, fmaf(fabsf(rb.x), b.ph, fmaf(rb.y, b.qc, fmaf(fabsf(rb.y), b.qh, rb.z))));
     const float y = fmaf(rc.x, b.pc, fmaf(fabsf(rc.x), b.ph, fmaf(rc.y, b.qc, fmaf(fabsf(rc.y), b.qh, rc.z))));
     const float z = fmaf(rd.x, b.pc, fmaf(fabsf(rd.x), b.ph, fmaf(rd.y, b.qc, fmaf(fabsf(rd.y), b.qh, rd.z))));
-    return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
+    // rb.w: lower bound of the distance from O to any point of the triangle (0 in tables without one): a triangle
+    // that lies wholly beyond the far end of every ray of the bundle cannot be hit by any of them
+    return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z) | (rb.w > b.lmax ? 0x80000000u : 0u);
 }
 
 // (min,max) ranges -> centre / half extent, slightly enlarged: the box evaluation rounds differently
 // from the per-ray evaluation, and must never be the stricter of the two
-__device__ __forceinline__ Box make_box(float pmin, float pmax, float qmin, float qmax) {
+__device__ __forceinline__ Box make_box(float pmin, float pmax, float qmin, float qmax, float lmax) {
     Box b;
+    b.lmax = lmax;
     b.pc = 0.5f * (pmin + pmax), b.qc = 0.5f * (qmin + qmax);
     b.ph = 0.5f * (pmax - pmin) * 1.0001f + 1e-6f * (fabsf(b.pc) + 1.f);
     b.qh = 0.5f * (qmax - qmin) * 1.0001f + 1e-6f * (fabsf(b.qc) + 1.f);
@@ -48,41 +52,46 @@ __device__ __forceinline__ Box make_box(float pmin, float pmax, float qmin, floa
 
 // box of the R rays held by one thread
 template <int R>
-__device__ __forceinline__ Box lane_box_of(const float (&rp)[R], const float (&rq)[R]) {
-    float pmin = rp[0], pmax = rp[0], qmin = rq[0], qmax = rq[0];
+__device__ __forceinline__ Box lane_box_of(const float (&rp)[R], const float (&rq)[R], const float (&rl)[R]) {
+    float pmin = rp[0], pmax = rp[0], qmin = rq[0], qmax = rq[0], lmax = rl[0];
 #pragma unroll
     for (int r = 1; r < R; ++r) {
         pmin = fminf(pmin, rp[r]), pmax = fmaxf(pmax, rp[r]);
         qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+        lmax = fmaxf(lmax, rl[r]);
     }
-    return make_box(pmin, pmax, qmin, qmax);
+    return make_box(pmin, pmax, qmin, qmax, lmax);
 }
 
-// warp box and CTA box of the rays held by this thread block (rp/rq of invalid rays must be duplicates
-// of valid ones).  scratch: 4 * THREADS/32 floats of shared memory.
+// warp box and CTA box of the rays held by this thread block (rp/rq/rl of invalid rays must be duplicates
+// of valid ones).  rl: far-end distance of each ray.  scratch: 5 * THREADS/32 floats of shared memory.
 template <int R>
-__device__ __forceinline__ void bundle_boxes(const float (&rp)[R], const float (&rq)[R], float *scratch, Box &warp_box,
-                                             Box &cta_box) {
-    float pmin = rp[0], pmax = rp[0], qmin = rq[0], qmax = rq[0];
+__device__ __forceinline__ void bundle_boxes(const float (&rp)[R], const float (&rq)[R], const float (&rl)[R], float *scratch,
+                                             Box &warp_box, Box &cta_box) {
+    float pmin = rp[0], pmax = rp[0], qmin = rq[0], qmax = rq[0], lmax = rl[0];
 #pragma unroll
     for (int r = 1; r < R; ++r) {
         pmin = fminf(pmin, rp[r]), pmax = fmaxf(pmax, rp[r]);
         qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+        lmax = fmaxf(lmax, rl[r]);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o)), pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
         qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o)), qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     }
-    warp_box = make_box(pmin, pmax, qmin, qmax);
+    warp_box = make_box(pmin, pmax, qmin, qmax, lmax);
     const int w = threadIdx.x >> 5, nw = sweep::THREADS / 32;
-    if ((threadIdx.x & 31) == 0) scratch[w] = pmin, scratch[nw + w] = pmax, scratch[2 * nw + w] = qmin, scratch[3 * nw + w] = qmax;
+    if ((threadIdx.x & 31) == 0)
+        scratch[w] = pmin, scratch[nw + w] = pmax, scratch[2 * nw + w] = qmin, scratch[3 * nw + w] = qmax, scratch[4 * nw + w] = lmax;
     __syncthreads();
     for (int i = 0; i < nw; ++i) {
         pmin = fminf(pmin, scratch[i]), pmax = fmaxf(pmax, scratch[nw + i]);
         qmin = fminf(qmin, scratch[2 * nw + i]), qmax = fmaxf(qmax, scratch[3 * nw + i]);
+        lmax = fmaxf(lmax, scratch[4 * nw + i]);
     }
-    cta_box = make_box(pmin, pmax, qmin, qmax);
+    cta_box = make_box(pmin, pmax, qmin, qmax, lmax);
     __syncthreads();
 }
 
@@ -100,7 +109,7 @@ struct __align__(128) EmitSmem {
     float4 tile[CSTAGES][CTILE * 3];
     uint64_t full_bar[CSTAGES];
     unsigned cmask[CTILE / 32];
-    float scratch[4 * sweep::THREADS / 32];
+    float scratch[5 * sweep::THREADS / 32];
     int blk, seg, slice;
 };
 
@@ -330,8 +339,9 @@ struct ListSmem {
 template <int R>
 __device__ __forceinline__ void walk_block_list(ListSmem &sm, const unsigned long long *__restrict__ keys, unsigned long long lo,
                                                 unsigned long long hi, unsigned tri_mask, const float4 *__restrict__ table, const float (&rp)[R],
-                                                const float (&rq)[R], unsigned valid, const int (&ray_id)[R], const Box warp_box,
-                                                const Box lane_box, const Emitter em, WarpChunk &wc, unsigned &d_l1) {
+                                                const float (&rq)[R], const float (&rl)[R], unsigned valid, const int (&ray_id)[R],
+                                                const Box warp_box, const Box lane_box, const Emitter em, WarpChunk &wc,
+                                                unsigned &d_l1) {
     using sweep::edge_sign;
     const int tid = threadIdx.x, lane = tid & 31;
     for (unsigned long long i0 = lo; i0 < hi; i0 += LTILE) {
@@ -359,7 +369,8 @@ __device__ __forceinline__ void walk_block_list(ListSmem &sm, const unsigned lon
                 ++d_l1;
                 if (!(box_sign(rb, rc, rd, lane_box) >> 31)) { // level 2: the box of this lane's own R rays
 #pragma unroll
-                    for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                    for (int r = 0; r < R; ++r)
+                        mask |= (((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) & (unsigned)(rb.w <= rl[r])) << r;
                     mask &= valid;
                 }
                 if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;

@@ -163,6 +163,10 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
             rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd);
             rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd);
         }
+        // rb.w (bundle-cull mode only): a lower bound of the distance from O to any point X of the triangle,
+        // |X - O| >= |V - O| - |X - V| >= max(la, lb, lc) - emax, less a slack far above the float noise of the
+        // reference's own t2.  A shadow ray that ends at O and is shorter than this cannot hit the triangle.
+        if (lmax > 0.0) rb.w = (float)fmax(0.0, (fmax(la, fmax(lb, lc)) - emax - 1e-4 * reach) * 0.999999);
     }
     table[3 * (size_t)i] = rb;
     table[3 * (size_t)i + 1] = rc;
@@ -694,8 +698,8 @@ struct PrimaryCullParams {
 
 // rays of block blk of the primary tiling: 128 x 32 pixels per block, 32 x 8 per warp, R = 8 rows per thread
 template <int R>
-__device__ __forceinline__ void load_primary_bundle(const PrimaryCullParams &p, int blk, float (&rp)[R], float (&rq)[R], int (&kp)[R],
-                                                    unsigned &valid) {
+__device__ __forceinline__ void load_primary_bundle(const PrimaryCullParams &p, int blk, float (&rp)[R], float (&rq)[R],
+                                                    float (&rl)[R], int (&kp)[R], unsigned &valid) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = p.bands.W;
     const int ty = blk / p.tiles_x, tx = blk - ty * p.tiles_x;
     const int x = tx * 128 + (warp & 3) * 32 + lane, y0 = ty * 32 + (warp >> 2) * 8;
@@ -709,6 +713,7 @@ __device__ __forceinline__ void load_primary_bundle(const PrimaryCullParams &p, 
         int w, h;
         p.bands.map(k, w, h);
         p.bands.pixel_st(w, h, rp[r], rq[r]);
+        rl[r] = FLT_MAX; // primary rays are unbounded (main.cpp:715)
     }
 }
 
@@ -735,12 +740,12 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
         const int slice = item / n_blocks, blk = item - slice * n_blocks;
         const int tile_lo = (int)((long long)p.n_tiles * slice / p.n_slices);
         const int tile_hi = (int)((long long)p.n_tiles * (slice + 1) / p.n_slices);
-        float rp[R], rq[R];
+        float rp[R], rq[R], rl[R];
         int kp[R];
         unsigned valid = 0;
-        load_primary_bundle<R>(p, blk, rp, rq, kp, valid);
+        load_primary_bundle<R>(p, blk, rp, rq, rl, kp, valid);
         cull::Box wb, cb;
-        cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
+        cull::bundle_boxes<R>(rp, rq, rl, sm.scratch, wb, cb);
         cull::sweep_cull_emit<R>(sm, p.table, tile_lo, tile_hi, rp, rq, valid, kp, gtile, cb, wb, p.em, wc, nullptr);
         const int t_lo = min(tile_lo * cull::CTILE, p.n_tris), t_hi = min(tile_hi * cull::CTILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
@@ -800,7 +805,7 @@ struct ShadowCullParams {
 // rays of block blk of group j: 512*R consecutive rays of the (group, Morton)-sorted list, 32*R consecutive per warp
 template <int R>
 __device__ __forceinline__ void load_shadow_bundle(const ShadowCullParams &p, int blk, int j, float (&rp)[R], float (&rq)[R],
-                                                   int (&kp)[R], unsigned &valid) {
+                                                   float (&rl)[R], int (&kp)[R], unsigned &valid) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n_px;
     const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
     const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane * R;
@@ -813,6 +818,9 @@ __device__ __forceinline__ void load_shadow_bundle(const ShadowCullParams &p, in
         const int k = p.list[e];
         kp[r] = k;
         rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
+        // the ray ends at the light vertex O and starts len = t + eps away from it (main.cpp:762-764): an accepted
+        // hit (eps <= t2 < t) lies within len of O
+        rl[r] = (p.px.rt[k] + 2.f * TRC_EPS) * 1.0001f;
     }
 }
 
@@ -849,12 +857,12 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const Sh
         const int blk = sm.blk, j = sm.seg, slice = sm.slice;
         if (blk < 0) break;
         const int lo = (int)((long long)p.n_tiles * slice / n_slices), hi = (int)((long long)p.n_tiles * (slice + 1) / n_slices);
-        float rp[R], rq[R];
+        float rp[R], rq[R], rl[R];
         int kp[R];
         unsigned valid = 0;
-        load_shadow_bundle<R>(p, blk, j, rp, rq, kp, valid);
+        load_shadow_bundle<R>(p, blk, j, rp, rq, rl, kp, valid);
         cull::Box wb, cb;
-        cull::bundle_boxes<R>(rp, rq, sm.scratch, wb, cb);
+        cull::bundle_boxes<R>(rp, rq, rl, sm.scratch, wb, cb);
         const int face = j % NFACE;
         const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
         cull::sweep_cull_emit<R>(sm, tab, lo, hi, rp, rq, valid, kp, gtile, cb, wb, p.em, wc, p.counters);
@@ -897,14 +905,14 @@ __global__ void strict_shadow_pairs(const unsigned long long *__restrict__ cand,
 __global__ void __launch_bounds__(sweep::THREADS) primary_boxes_kernel(const PrimaryCullParams p, cull::BlockBoxes *__restrict__ out,
                                                                        int *__restrict__ blk_off) {
     constexpr int R = 8;
-    __shared__ float scratch[4 * sweep::THREADS / 32];
+    __shared__ float scratch[5 * sweep::THREADS / 32];
     const int blk = blockIdx.x;
-    float rp[R], rq[R];
+    float rp[R], rq[R], rl[R];
     int kp[R];
     unsigned valid;
-    load_primary_bundle<R>(p, blk, rp, rq, kp, valid);
+    load_primary_bundle<R>(p, blk, rp, rq, rl, kp, valid);
     cull::Box wb, cb;
-    cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
+    cull::bundle_boxes<R>(rp, rq, rl, scratch, wb, cb);
     if ((threadIdx.x & 31) == 0) out[blk].warp[threadIdx.x >> 5] = wb;
     if (threadIdx.x == 0) out[blk].cta = cb;
     if (blk == 0 && threadIdx.x == 0) blk_off[0] = 0, blk_off[1] = p.tiles_x * p.tiles_y; // one group
@@ -912,17 +920,17 @@ __global__ void __launch_bounds__(sweep::THREADS) primary_boxes_kernel(const Pri
 
 __global__ void __launch_bounds__(sweep::THREADS) shadow_boxes_kernel(const ShadowCullParams p, cull::BlockBoxes *__restrict__ out) {
     constexpr int R = 8;
-    __shared__ float scratch[4 * sweep::THREADS / 32];
+    __shared__ float scratch[5 * sweep::THREADS / 32];
     const int blk = blockIdx.x;
     if (blk >= p.blk_off[p.n_groups]) return;
     int j = 0;
     while (blk >= p.blk_off[j + 1]) ++j;
-    float rp[R], rq[R];
+    float rp[R], rq[R], rl[R];
     int kp[R];
     unsigned valid;
-    load_shadow_bundle<R>(p, blk, j, rp, rq, kp, valid);
+    load_shadow_bundle<R>(p, blk, j, rp, rq, rl, kp, valid);
     cull::Box wb, cb;
-    cull::bundle_boxes<R>(rp, rq, scratch, wb, cb);
+    cull::bundle_boxes<R>(rp, rq, rl, scratch, wb, cb);
     if ((threadIdx.x & 31) == 0) out[blk].warp[threadIdx.x >> 5] = wb;
     if (threadIdx.x == 0) out[blk].cta = cb;
 }
@@ -942,18 +950,20 @@ constexpr unsigned long long CULL_SEG = 8192;
 struct PrimaryBundles {
     PrimaryCullParams p;
     template <int R>
-    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], int (&kp)[R], unsigned &valid) const {
-        load_primary_bundle<R>(p, blk, rp, rq, kp, valid);
+    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], float (&rl)[R], int (&kp)[R],
+                                                 unsigned &valid) const {
+        load_primary_bundle<R>(p, blk, rp, rq, rl, kp, valid);
         return p.table;
     }
 };
 struct ShadowBundles {
     ShadowCullParams p;
     template <int R>
-    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], int (&kp)[R], unsigned &valid) const {
+    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], float (&rl)[R], int (&kp)[R],
+                                                 unsigned &valid) const {
         int j = 0;
         while (blk >= p.blk_off[j + 1]) ++j;
-        load_shadow_bundle<R>(p, blk, j, rp, rq, kp, valid);
+        load_shadow_bundle<R>(p, blk, j, rp, rq, rl, kp, valid);
         return cull::group_table(p.tables, p.allcand, p.table_stride, NFACE, j);
     }
 };
@@ -981,13 +991,13 @@ __device__ __forceinline__ void cull2_body(const Bundles &bd, const BlockLists b
             if (tid == 0) s_end = pos + cull::lower_bound_key(bl.keys + pos, end - pos, (unsigned long long)(unsigned)(blk + 1) << bl.tri_bits);
             __syncthreads();
             const unsigned long long run_end = s_end;
-            float rp[R], rq[R];
+            float rp[R], rq[R], rl[R];
             int kp[R];
             unsigned valid;
-            const float4 *tab = bd.template load<R>(blk, rp, rq, kp, valid);
+            const float4 *tab = bd.template load<R>(blk, rp, rq, rl, kp, valid);
             const cull::Box wb = bl.boxes[blk].warp[warp];
-            cull::walk_block_list<R>(lsm, bl.keys, pos, run_end, (1u << bl.tri_bits) - 1u, tab, rp, rq, valid, kp, wb,
-                                     cull::lane_box_of<R>(rp, rq), em, wc, d_l1);
+            cull::walk_block_list<R>(lsm, bl.keys, pos, run_end, (1u << bl.tri_bits) - 1u, tab, rp, rq, rl, valid, kp, wb,
+                                     cull::lane_box_of<R>(rp, rq, rl), em, wc, d_l1);
             pos = run_end;
             __syncthreads(); // s_end is rewritten by the next run
         }
