@@ -242,7 +242,8 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
 // separates the levels into dense kernels:
 //   phase A  cull_l0_kernel: EVERY (ray block, triangle) pair — still no acceleration structure, no build
 //            step — with one triangle per thread held in registers and the block boxes broadcast from
-//            shared memory; survivors are appended as block<<tri_bits|triangle and radix-sorted;
+//            shared memory; survivors are tested against the block's 16 warp boxes at once and appended as
+//            (block*16+warp)<<tri_bits|triangle, then radix-sorted;
 //   phase B  walk_block_list: each warp of the ray block walks the block's (short) survivor list 32 triangles
 //            at a time against its own warp box, then per ray, and emits ray<<32|triangle candidates.
 // The candidates then take the same sort + strict path as before, so results stay bit-identical.
@@ -303,11 +304,28 @@ __global__ void __launch_bounds__(L0_THREADS) cull_l0_kernel(const L0Params p) {
 #pragma unroll 2
         for (int i = 0; i < nb; ++i) {
             const bool pass = live && !(box_sign(rb, rc, rd, sbox[i]) >> 31);
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                if (pass) st[fill + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)(b0 + i) << p.tri_bits) | (unsigned)tri;
-                fill += __popc(m);
-                if (fill > L0_STAGE - 32) flush();
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            while (m) { // (block, triangle) pairs that pass the block box: lanes 0..15 test the block's 16 warp boxes
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                float4 sb, sc, sd;
+                sb.x = __shfl_sync(0xffffffffu, rb.x, src), sb.y = __shfl_sync(0xffffffffu, rb.y, src);
+                sb.z = __shfl_sync(0xffffffffu, rb.z, src), sb.w = __shfl_sync(0xffffffffu, rb.w, src);
+                sc.x = __shfl_sync(0xffffffffu, rc.x, src), sc.y = __shfl_sync(0xffffffffu, rc.y, src);
+                sc.z = __shfl_sync(0xffffffffu, rc.z, src), sc.w = 0.f;
+                sd.x = __shfl_sync(0xffffffffu, rd.x, src), sd.y = __shfl_sync(0xffffffffu, rd.y, src);
+                sd.z = __shfl_sync(0xffffffffu, rd.z, src), sd.w = 0.f;
+                const unsigned stri = (unsigned)(tri - lane + src);
+                bool wp = false;
+                if (lane < sweep::THREADS / 32) wp = !(box_sign(sb, sc, sd, p.boxes[b0 + i].warp[lane]) >> 31);
+                const unsigned wm = __ballot_sync(0xffffffffu, wp);
+                if (wm) {
+                    if (wp)
+                        st[fill + __popc(wm & ((1u << lane) - 1u))] =
+                            ((unsigned long long)(unsigned)((b0 + i) * (sweep::THREADS / 32) + lane) << p.tri_bits) | stri;
+                    fill += __popc(wm);
+                    if (fill > L0_STAGE - 32) flush();
+                }
             }
         }
     }
@@ -327,57 +345,13 @@ __device__ __forceinline__ unsigned long long lower_bound_key(const unsigned lon
     return lo;
 }
 
-// phase B: the block's sorted survivor list keys[lo, hi) (low tri_bits = triangle).  The CTA stages LTILE rows at a
-// time in shared memory (each row gathered from the table ONCE per block); every warp then tests the staged rows
-// against its own box, one row per lane, and the rows that pass go through the per-ray filter (row broadcast
-// from shared memory); candidates are appended through the warp's chunk.
-constexpr int LTILE = sweep::THREADS;
-struct ListSmem {
-    float4 row[LTILE * 3];
-    unsigned tri[LTILE];
+// phase B works on the sorted keys one WARP at a time (kernels.cuh: cull2_body): 32 keys are staged per step
+// in a per-warp slice of shared memory (each lane gathers the row of one key), then walked in order with the
+// row broadcast from shared memory: lane box, per-ray filter, candidates appended through the warp's chunk.
+// No block-wide barrier: the survivors are spread very unevenly over the warps of a ray block.
+struct WarpListSmem {
+    float4 row[sweep::THREADS / 32][32 * 3];
+    unsigned long long key[sweep::THREADS / 32][32];
 };
-template <int R>
-__device__ __forceinline__ void walk_block_list(ListSmem &sm, const unsigned long long *__restrict__ keys, unsigned long long lo,
-                                                unsigned long long hi, unsigned tri_mask, const float4 *__restrict__ table, const float (&rp)[R],
-                                                const float (&rq)[R], const float (&rl)[R], unsigned valid, const int (&ray_id)[R],
-                                                const Box warp_box, const Box lane_box, const Emitter em, WarpChunk &wc,
-                                                unsigned &d_l1) {
-    using sweep::edge_sign;
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (unsigned long long i0 = lo; i0 < hi; i0 += LTILE) {
-        const int n = (int)((hi - i0) < (unsigned long long)LTILE ? (hi - i0) : (unsigned long long)LTILE);
-        __syncthreads(); // previous tile fully consumed
-        if (tid < n) {
-            const unsigned t = (unsigned)keys[i0 + tid] & tri_mask;
-            sm.tri[tid] = t;
-            sm.row[3 * tid] = __ldg(&table[3 * (size_t)t]);
-            sm.row[3 * tid + 1] = __ldg(&table[3 * (size_t)t + 1]);
-            sm.row[3 * tid + 2] = __ldg(&table[3 * (size_t)t + 2]);
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
-            bool pass = false;
-            if (k < n) pass = !(box_sign(sm.row[3 * k], sm.row[3 * k + 1], sm.row[3 * k + 2], warp_box) >> 31);
-            unsigned mm = __ballot_sync(0xffffffffu, pass);
-            while (mm) { // warp-box survivors in index order
-                const int e = k0 + __ffs(mm) - 1;
-                mm &= mm - 1;
-                const float4 rb = sm.row[3 * e], rc = sm.row[3 * e + 1], rd = sm.row[3 * e + 2];
-                unsigned mask = 0;
-                ++d_l1;
-                if (!(box_sign(rb, rc, rd, lane_box) >> 31)) { // level 2: the box of this lane's own R rays
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        mask |= (((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) & (unsigned)(rb.w <= rl[r])) << r;
-                    mask &= valid;
-                }
-                if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
-                emit_pairs<R>(em, wc, mask, ray_id, sm.tri[e]);
-            }
-        }
-    }
-}
 
 }  // namespace cull

@@ -698,9 +698,9 @@ struct PrimaryCullParams {
 
 // rays of block blk of the primary tiling: 128 x 32 pixels per block, 32 x 8 per warp, R = 8 rows per thread
 template <int R>
-__device__ __forceinline__ void load_primary_bundle(const PrimaryCullParams &p, int blk, float (&rp)[R], float (&rq)[R],
+__device__ __forceinline__ void load_primary_bundle(const PrimaryCullParams &p, int blk, int warp, float (&rp)[R], float (&rq)[R],
                                                     float (&rl)[R], int (&kp)[R], unsigned &valid) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = p.bands.W;
+    const int lane = threadIdx.x & 31, W = p.bands.W;
     const int ty = blk / p.tiles_x, tx = blk - ty * p.tiles_x;
     const int x = tx * 128 + (warp & 3) * 32 + lane, y0 = ty * 32 + (warp >> 2) * 8;
     valid = 0;
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull_kernel(const P
         float rp[R], rq[R], rl[R];
         int kp[R];
         unsigned valid = 0;
-        load_primary_bundle<R>(p, blk, rp, rq, rl, kp, valid);
+        load_primary_bundle<R>(p, blk, threadIdx.x >> 5, rp, rq, rl, kp, valid);
         cull::Box wb, cb;
         cull::bundle_boxes<R>(rp, rq, rl, sm.scratch, wb, cb);
         cull::sweep_cull_emit<R>(sm, p.table, tile_lo, tile_hi, rp, rq, valid, kp, gtile, cb, wb, p.em, wc, nullptr);
@@ -804,9 +804,9 @@ struct ShadowCullParams {
 
 // rays of block blk of group j: 512*R consecutive rays of the (group, Morton)-sorted list, 32*R consecutive per warp
 template <int R>
-__device__ __forceinline__ void load_shadow_bundle(const ShadowCullParams &p, int blk, int j, float (&rp)[R], float (&rq)[R],
+__device__ __forceinline__ void load_shadow_bundle(const ShadowCullParams &p, int blk, int warp, int j, float (&rp)[R], float (&rq)[R],
                                                    float (&rl)[R], int (&kp)[R], unsigned &valid) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n_px;
+    const int lane = threadIdx.x & 31, n = p.n_px;
     const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.seg_cnt[j];
     const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R) + warp * (32 * R) + lane * R;
     valid = 0;
@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 2) shadow_cull_kernel(const Sh
         float rp[R], rq[R], rl[R];
         int kp[R];
         unsigned valid = 0;
-        load_shadow_bundle<R>(p, blk, j, rp, rq, rl, kp, valid);
+        load_shadow_bundle<R>(p, blk, threadIdx.x >> 5, j, rp, rq, rl, kp, valid);
         cull::Box wb, cb;
         cull::bundle_boxes<R>(rp, rq, rl, sm.scratch, wb, cb);
         const int face = j % NFACE;
@@ -910,7 +910,7 @@ __global__ void __launch_bounds__(sweep::THREADS) primary_boxes_kernel(const Pri
     float rp[R], rq[R], rl[R];
     int kp[R];
     unsigned valid;
-    load_primary_bundle<R>(p, blk, rp, rq, rl, kp, valid);
+    load_primary_bundle<R>(p, blk, threadIdx.x >> 5, rp, rq, rl, kp, valid);
     cull::Box wb, cb;
     cull::bundle_boxes<R>(rp, rq, rl, scratch, wb, cb);
     if ((threadIdx.x & 31) == 0) out[blk].warp[threadIdx.x >> 5] = wb;
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(sweep::THREADS) shadow_boxes_kernel(const Shad
     float rp[R], rq[R], rl[R];
     int kp[R];
     unsigned valid;
-    load_shadow_bundle<R>(p, blk, j, rp, rq, rl, kp, valid);
+    load_shadow_bundle<R>(p, blk, threadIdx.x >> 5, j, rp, rq, rl, kp, valid);
     cull::Box wb, cb;
     cull::bundle_boxes<R>(rp, rq, rl, scratch, wb, cb);
     if ((threadIdx.x & 31) == 0) out[blk].warp[threadIdx.x >> 5] = wb;
@@ -937,73 +937,105 @@ __global__ void __launch_bounds__(sweep::THREADS) shadow_boxes_kernel(const Shad
 
 struct BlockLists {
     const cull::BlockBoxes *boxes;
-    const unsigned long long *keys; // sorted block<<tri_bits|triangle survivors of phase A
+    const unsigned long long *keys; // sorted (block*16+warp)<<tri_bits|triangle survivors of phase A
     unsigned long long n_keys;
     int tri_bits;
 };
 
-// phase B.  Work item = a fixed-size segment of the sorted key array (so a ray block with a very long survivor
-// list — e.g. a shadow-ray block that straddles a Morton-order jump and has a huge box — is spread over many
-// CTAs, and short lists share one); inside a segment every run of equal block ids is one walk_block_list call.
-constexpr unsigned long long CULL_SEG = 8192;
+// phase B.  Work item = a fixed-size segment of the sorted key array, taken by ONE warp (so a warp with a very
+// long survivor list — e.g. shadow rays that straddle a Morton-order jump and have a huge box — is spread over
+// many warps of the grid, and short lists share one); a key's high part names the (ray block, warp) whose rays
+// the executing warp loads when it changes.
+constexpr unsigned long long CULL_SEG = 2048;
 
 struct PrimaryBundles {
     PrimaryCullParams p;
+    __device__ __forceinline__ const float4 *table_of(int) const { return p.table; }
     template <int R>
-    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], float (&rl)[R], int (&kp)[R],
-                                                 unsigned &valid) const {
-        load_primary_bundle<R>(p, blk, rp, rq, rl, kp, valid);
-        return p.table;
+    __device__ __forceinline__ void load(int blk, int warp, float (&rp)[R], float (&rq)[R], float (&rl)[R], int (&kp)[R],
+                                         unsigned &valid) const {
+        load_primary_bundle<R>(p, blk, warp, rp, rq, rl, kp, valid);
     }
 };
 struct ShadowBundles {
     ShadowCullParams p;
-    template <int R>
-    __device__ __forceinline__ const float4 *load(int blk, float (&rp)[R], float (&rq)[R], float (&rl)[R], int (&kp)[R],
-                                                 unsigned &valid) const {
+    __device__ __forceinline__ int group_of(int blk) const {
         int j = 0;
         while (blk >= p.blk_off[j + 1]) ++j;
-        load_shadow_bundle<R>(p, blk, j, rp, rq, rl, kp, valid);
-        return cull::group_table(p.tables, p.allcand, p.table_stride, NFACE, j);
+        return j;
+    }
+    __device__ __forceinline__ const float4 *table_of(int blk) const {
+        return cull::group_table(p.tables, p.allcand, p.table_stride, NFACE, group_of(blk));
+    }
+    template <int R>
+    __device__ __forceinline__ void load(int blk, int warp, float (&rp)[R], float (&rq)[R], float (&rl)[R], int (&kp)[R],
+                                         unsigned &valid) const {
+        load_shadow_bundle<R>(p, blk, warp, group_of(blk), rp, rq, rl, kp, valid);
     }
 };
 
 template <class Bundles>
 __device__ __forceinline__ void cull2_body(const Bundles &bd, const BlockLists bl, int *work, const cull::Emitter em,
                                            sweep::Counters *counters) {
-    constexpr int R = 8;
-    __shared__ cull::ListSmem lsm;
-    __shared__ int s_item;
-    __shared__ unsigned long long s_end;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int R = 8, NW = sweep::THREADS / 32;
+    __shared__ cull::WarpListSmem lsm;
+    const int lane = threadIdx.x & 31, ws = threadIdx.x >> 5;
     const unsigned long long n_items = (bl.n_keys + CULL_SEG - 1) / CULL_SEG;
+    const unsigned tri_mask = (1u << bl.tri_bits) - 1u;
     unsigned d_l1 = 0;
     cull::WarpChunk wc{0, cull::CHUNK}; // no chunk yet
+    int cur = -1;                       // (block, warp) whose rays this warp holds
+    const float4 *tab = nullptr;
+    float rp[R], rq[R], rl[R];
+    int kp[R];
+    unsigned valid = 0;
+    cull::Box lane_box{};
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(work, 1);
-        __syncthreads();
-        const unsigned long long item = (unsigned long long)s_item;
+        int it = 0;
+        if (lane == 0) it = atomicAdd(work, 1);
+        const unsigned long long item = (unsigned long long)__shfl_sync(0xffffffffu, it, 0);
         if (item >= n_items) break;
-        unsigned long long pos = item * CULL_SEG;
-        const unsigned long long end = min(bl.n_keys, pos + CULL_SEG);
-        while (pos < end) {
-            const int blk = (int)(bl.keys[pos] >> bl.tri_bits);
-            if (tid == 0) s_end = pos + cull::lower_bound_key(bl.keys + pos, end - pos, (unsigned long long)(unsigned)(blk + 1) << bl.tri_bits);
-            __syncthreads();
-            const unsigned long long run_end = s_end;
-            float rp[R], rq[R], rl[R];
-            int kp[R];
-            unsigned valid;
-            const float4 *tab = bd.template load<R>(blk, rp, rq, rl, kp, valid);
-            const cull::Box wb = bl.boxes[blk].warp[warp];
-            cull::walk_block_list<R>(lsm, bl.keys, pos, run_end, (1u << bl.tri_bits) - 1u, tab, rp, rq, rl, valid, kp, wb,
-                                     cull::lane_box_of<R>(rp, rq, rl), em, wc, d_l1);
-            pos = run_end;
-            __syncthreads(); // s_end is rewritten by the next run
+        const unsigned long long pos = item * CULL_SEG, end = min(bl.n_keys, pos + CULL_SEG);
+        for (unsigned long long i0 = pos; i0 < end; i0 += 32) {
+            const int n = (int)min((unsigned long long)32, end - i0);
+            __syncwarp(); // the previous step's rows are consumed
+            if (lane < n) { // gather: one key and its row per lane
+                const unsigned long long key = bl.keys[i0 + lane];
+                const int kb = (int)(key >> bl.tri_bits);
+                const float4 *t = kb == cur ? tab : bd.table_of(kb / NW);
+                const unsigned tri = (unsigned)key & tri_mask;
+                lsm.key[ws][lane] = key;
+                lsm.row[ws][3 * lane] = __ldg(&t[3 * (size_t)tri]);
+                lsm.row[ws][3 * lane + 1] = __ldg(&t[3 * (size_t)tri + 1]);
+                lsm.row[ws][3 * lane + 2] = __ldg(&t[3 * (size_t)tri + 2]);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int e = 0; e < n; ++e) {
+                const unsigned long long key = lsm.key[ws][e];
+                const int kb = (int)(key >> bl.tri_bits);
+                if (kb != cur) { // warp-uniform
+                    cur = kb;
+                    tab = bd.table_of(kb / NW);
+                    bd.template load<R>(kb / NW, kb % NW, rp, rq, rl, kp, valid);
+                    lane_box = cull::lane_box_of<R>(rp, rq, rl);
+                }
+                const float4 rb = lsm.row[ws][3 * e], rc = lsm.row[ws][3 * e + 1], rd = lsm.row[ws][3 * e + 2];
+                unsigned mask = 0;
+                ++d_l1;
+                if (!(cull::box_sign(rb, rc, rd, lane_box) >> 31)) { // the box of this lane's own R rays
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        mask |= (((sweep::edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) & (unsigned)(rb.w <= rl[r])) << r;
+                    mask &= valid;
+                }
+                if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+                cull::emit_pairs<R>(em, wc, mask, kp, (unsigned)key & tri_mask);
+            }
         }
     }
     cull::chunk_close(em, wc);
-    if ((tid & 31) == 0) atomicAdd(&counters->cull_l1, (unsigned long long)d_l1);
+    if (lane == 0) atomicAdd(&counters->cull_l1, (unsigned long long)d_l1);
 }
 
 __global__ void __launch_bounds__(sweep::THREADS, 2) primary_cull2_kernel(const PrimaryCullParams p, const BlockLists bl) {

@@ -598,7 +598,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             return 0;
         }
         int blk_bits = 1;
-        while ((1 << blk_bits) < max_blocks) ++blk_bits;
+        while ((1 << blk_bits) < max_blocks * (sweep::THREADS / 32)) ++blk_bits; // keys name a (block, warp)
         if (n) CK_CUDA(cub::DeviceRadixSort::SortKeys(s->sort_tmp, s->sort_bytes, s->cand_a, s->cand_b, n, 0, tri_bits + blk_bits, st));
         n_keys = (long long)n;
         return 0;
