@@ -305,24 +305,28 @@ __global__ void __launch_bounds__(L0_THREADS) cull_l0_kernel(const L0Params p) {
         for (int i = 0; i < nb; ++i) {
             const bool pass = live && !(box_sign(rb, rc, rd, sbox[i]) >> 31);
             unsigned m = __ballot_sync(0xffffffffu, pass);
-            while (m) { // (block, triangle) pairs that pass the block box: lanes 0..15 test the block's 16 warp boxes
-                const int src = __ffs(m) - 1;
+            while (m) { // (block, triangle) pairs that pass the block box, two per step: each half-warp tests one
+                        // pair's row against the block's 16 warp boxes
+                const int s0 = __ffs(m) - 1;
                 m &= m - 1;
+                int s1 = -1;
+                if (m) s1 = __ffs(m) - 1, m &= m - 1;
+                const int wl = lane & 15, mysrc = (lane >> 4) ? s1 : s0, srcl = mysrc < 0 ? 0 : mysrc;
                 float4 sb, sc, sd;
-                sb.x = __shfl_sync(0xffffffffu, rb.x, src), sb.y = __shfl_sync(0xffffffffu, rb.y, src);
-                sb.z = __shfl_sync(0xffffffffu, rb.z, src), sb.w = __shfl_sync(0xffffffffu, rb.w, src);
-                sc.x = __shfl_sync(0xffffffffu, rc.x, src), sc.y = __shfl_sync(0xffffffffu, rc.y, src);
-                sc.z = __shfl_sync(0xffffffffu, rc.z, src), sc.w = 0.f;
-                sd.x = __shfl_sync(0xffffffffu, rd.x, src), sd.y = __shfl_sync(0xffffffffu, rd.y, src);
-                sd.z = __shfl_sync(0xffffffffu, rd.z, src), sd.w = 0.f;
-                const unsigned stri = (unsigned)(tri - lane + src);
+                sb.x = __shfl_sync(0xffffffffu, rb.x, srcl), sb.y = __shfl_sync(0xffffffffu, rb.y, srcl);
+                sb.z = __shfl_sync(0xffffffffu, rb.z, srcl), sb.w = __shfl_sync(0xffffffffu, rb.w, srcl);
+                sc.x = __shfl_sync(0xffffffffu, rc.x, srcl), sc.y = __shfl_sync(0xffffffffu, rc.y, srcl);
+                sc.z = __shfl_sync(0xffffffffu, rc.z, srcl), sc.w = 0.f;
+                sd.x = __shfl_sync(0xffffffffu, rd.x, srcl), sd.y = __shfl_sync(0xffffffffu, rd.y, srcl);
+                sd.z = __shfl_sync(0xffffffffu, rd.z, srcl), sd.w = 0.f;
+                static_assert(sweep::THREADS / 32 == 16, "one half-warp per ray block's warp boxes");
                 bool wp = false;
-                if (lane < sweep::THREADS / 32) wp = !(box_sign(sb, sc, sd, p.boxes[b0 + i].warp[lane]) >> 31);
+                if (mysrc >= 0) wp = !(box_sign(sb, sc, sd, p.boxes[b0 + i].warp[wl]) >> 31);
                 const unsigned wm = __ballot_sync(0xffffffffu, wp);
                 if (wm) {
                     if (wp)
                         st[fill + __popc(wm & ((1u << lane) - 1u))] =
-                            ((unsigned long long)(unsigned)((b0 + i) * (sweep::THREADS / 32) + lane) << p.tri_bits) | stri;
+                            ((unsigned long long)(unsigned)((b0 + i) * 16 + wl) << p.tri_bits) | (unsigned)(tri - lane + srcl);
                     fill += __popc(wm);
                     if (fill > L0_STAGE - 32) flush();
                 }

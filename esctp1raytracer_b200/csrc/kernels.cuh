@@ -888,6 +888,10 @@ __global__ void strict_shadow_pairs(const unsigned long long *__restrict__ cand,
         const unsigned ray = (unsigned)(key >> 32);
         if (ray == 0xffffffffu) continue;
         const int tr = (int)(unsigned)(key & 0xffffffffu);
+        // the answer is the LOWEST accepted index: once some lower-index occluder of this ray has been published,
+        // this pair cannot change it (best_occ only ever decreases, so a stale read is merely conservative).  The
+        // emitter walks each warp's triangles in ascending order, so this recovers most of occlusion()'s early exit.
+        if ((unsigned)(px.best_occ[ray] >> 32) < (unsigned)tr) continue;
         const f3 o = strict::mk(px.ro[ray], px.ro[n_px + ray], px.ro[2 * (size_t)n_px + ray]);
         const f3 d = strict::mk(px.rd[ray], px.rd[n_px + ray], px.rd[2 * (size_t)n_px + ray]);
         float t = px.rt[ray], v;
