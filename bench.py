@@ -283,8 +283,9 @@ def main():
             dist.all_reduce(cms, op=dist.ReduceOp.MAX)
         cull_extra = {"value": rays / (float(cms[0]) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(cms[0]) / args.steps,
                       "frame_identical_to_default_mode": same,
-                      "note": "opts.bundle_cull: bundle box -> warp box -> per-ray filter -> strict; every bundle still tests every "
-                              "triangle, results bit-identical; bound by the L2 stream of the 48-byte rows, not FP32 issue. "
+                      "note": "opts.bundle_cull (two-phase): every (ray block, triangle) pair against the block box, survivors against "
+                              "the 16 warp boxes -> sorted per-(block, warp) lists -> lane box -> per-ray filter -> strict pairs merged "
+                              "by atomicMin; no acceleration structure, results bit-identical.  "
                               "Reported beside the headline, which stays on the brute-force per-ray formulation of the north star."}
 
     # ---- e2e: the drop-in call with host buffers --------------------------------------------
@@ -361,7 +362,7 @@ def main():
                 "primary_ms_per_step": tot["ms_primary"] / world / args.steps, "shadow_ms_per_step": tot["ms_shadow"] / world / args.steps,
                 "primary_tflops": FLOP_PER_PAIR * tot["tests_primary"] / (tot["ms_primary"] * 1e-3) / 1e12 if tot["ms_primary"] else None,
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / world / sweep_s / 1e12,
-                "ceiling_note": "6 FFMA + 1.5 LOP3 (~2 issue slots) + 0.5 LDS/SHF per pair: FP32-pipe share of issue <= ~0.70; measured loop ceiling 0.58 of nominal (tools/sweep_mb.cu)",
+                "ceiling_note": "6 FFMA + 1.5 LOP3 + 0.5 LDS/SHF per pair = 8 instr at the measured issue ceiling IPC ~0.8 per scheduler: loop ceiling 0.58 of nominal (tools/sweep_mb.cu, DESIGN.md 4)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
                         "streams": "filter tables (48 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
             },
