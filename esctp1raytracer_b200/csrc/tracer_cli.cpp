@@ -24,7 +24,7 @@ int main(int argc, char *argv[]) {
         std::string model, output;
         float eye[3] = {0, 1, 3}, look[3] = {0, 1, 0}; // main.cpp:426
         int W = 1024, H = 768;                          // main.cpp:427
-        int device = 0, p6 = 0;
+        int device = 0, p6 = 0, bundle_cull = 0;
         bool have_seed = false;
         unsigned seed = 0;
         int rng = TRACER_RNG_MT19937; // the serial path's generator
@@ -49,6 +49,7 @@ int main(int argc, char *argv[]) {
                 rng = r == "hash" ? TRACER_RNG_HASH : TRACER_RNG_MT19937;
             } else if (f == "--device") device = std::atoi(need("--device"));
             else if (f == "--p6") p6 = 1;
+            else if (f == "--cull") bundle_cull = 1; // optional bundle-cull mode: same bytes out, much faster on big scenes
             else throw std::runtime_error("Unknown argument: " + f); // main.cpp:531-534
         }
         tracer_scene_host *scene = nullptr;
@@ -67,6 +68,7 @@ int main(int argc, char *argv[]) {
         tracer_render_opts o{};
         o.struct_size = sizeof o;
         o.rng_mode = rng;
+        o.bundle_cull = bundle_cull;
         o.seed = have_seed ? seed : std::random_device{}(); // main.cpp:587-588
         std::vector<uint8_t> rgb((size_t)W * H * 3);
         const auto t0 = std::chrono::high_resolution_clock::now(); // main.cpp:583

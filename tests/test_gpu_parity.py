@@ -270,6 +270,11 @@ def test_cli_host_flow_obj_to_ppm(renderer, restated, tmp_path):
     got = np.array(tok[4:], dtype=np.int64).reshape(H, W, 3)
     o = restated.render(to_flat(loaded), restated.camera((0, 1, 2.9), (0, 1, 0), W, H), W, H, seed=seed)
     assert np.array_equal(got, o.rgb8)
+    out2 = tmp_path / "out_cull.ppm"  # the optional bundle-cull mode writes the same file
+    r = subprocess.run([cli, "-m", str(obj), "-v", "0,1,2.9", "-l", "0,1,0", "-w", f"{W},{H}", "--seed", str(seed), "--cull", "-o",
+                        str(out2)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out2.read_bytes() == out.read_bytes()
 
 
 def test_multisample_jitter_extension(renderer, restated):
@@ -327,6 +332,8 @@ def test_bundle_cull_identical_to_default(renderer):
         b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=True)
         _same_frames(a, b)
         assert b.stats["tests_shadow_ref"] == a.stats["tests_shadow_ref"] and b.stats["n_shadow_rays"] == a.stats["n_shadow_rays"]
+        c = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=2)  # streaming form (fall-back)
+        _same_frames(a, c)
     # bands and multi-sample in cull mode
     s, W, H = cases[0][0], 100, 77
     cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
