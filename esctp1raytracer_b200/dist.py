@@ -45,6 +45,16 @@ def gather_bands(local, rank: int, world: int, dst: int = 0, group=None):
     return stacked if rank == dst else None
 
 
+def torch_stream_handle():
+    """cudaStream_t of torch's current stream, as the C ABI wants it.  torch reports the legacy default stream as
+    handle 0, which the ABI reads as "use the library's own (non-blocking) stream": the render would then not be
+    ordered with torch's allocations, the NCCL gather and the assemble kernel.  cudaStreamLegacy (0x1) names the
+    same stream explicitly."""
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream or 1
+
+
 def render_frame(renderer, resident_scene, camera, width, height, *, rank=0, world=1, band_rows=DEFAULT_BAND_ROWS,
                  rng_mode=0, seed=1, group=None, bundle_cull=False, samples_per_pixel=0):
     """Render this rank's bands into HBM, gather to rank 0, assemble.  Returns
@@ -53,7 +63,7 @@ def render_frame(renderer, resident_scene, camera, width, height, *, rank=0, wor
 
     rows_pad = padded_rows(height, band_rows, world) if world > 1 else height
     local = torch.zeros((rows_pad, width, 3), dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch_stream_handle()
     bands = (band_rows, rank, world) if world > 1 else None
     fr = renderer.trace(resident_scene, camera, width, height, rng_mode=rng_mode, seed=seed, bands=bands,
                         out_device_ptr=local.data_ptr(), stream=stream, bundle_cull=bundle_cull,

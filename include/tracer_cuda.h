@@ -105,7 +105,8 @@ typedef struct tracer_render_opts {
     int32_t band_count;
 
     int32_t rgb_out_is_device; /* rgb_out is a device pointer (stays in HBM, e.g. for an NCCL gather) */
-    void *cuda_stream;         /* cudaStream_t to launch on; NULL = the library's own stream */
+    void *cuda_stream;         /* cudaStream_t to launch on; NULL = the library's own (non-blocking) stream.  To order the
+                                  render with work on the legacy default stream pass cudaStreamLegacy (0x1), not 0 */
 
     int32_t exhaustive_strict; /* debug: bypass the conservative filter, strict-test every pair */
     int32_t samples_per_pixel; /* extension (parity unpinned): 0/1 = reference; n*n stratified jitter */

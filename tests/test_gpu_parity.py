@@ -376,3 +376,26 @@ def test_full_size_c4_frame(renderer, restated):
     assert np.array_equal(a.occ_tri[k], o.occ_tri)
     assert np.array_equal(bits(a.rgb[k]), bits(o.rgb))
     assert np.array_equal(a.rgb8.reshape(-1, 3)[k], o.rgb8)
+
+
+def test_render_frame_is_ordered_on_torchs_stream(renderer):
+    """dist.render_frame hands the library torch's current stream; the legacy default stream must go in as
+    cudaStreamLegacy (0x1), never as 0 (= the library's own stream, unordered with torch's allocations and NCCL)."""
+    import torch
+
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+    from esctp1raytracer_b200 import dist as tdist
+
+    assert tdist.torch_stream_handle() != 0
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        assert tdist.torch_stream_handle() == side.cuda_stream
+    s = scenes.soup_scene(3000, 10, 2, seed=2)
+    W, H = 96, 64
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    want = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=5).rgb8
+    for _ in range(3):  # back to back, no synchronize in between
+        a, _ = tdist.render_frame(renderer, rs, cam, W, H, seed=5)
+        b, _ = tdist.render_frame(renderer, rs, cam, W, H, seed=5, bundle_cull=True)
+    assert np.array_equal(a.cpu().numpy(), want) and np.array_equal(b.cpu().numpy(), want)
