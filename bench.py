@@ -12,10 +12,10 @@ synthetic 1M-triangle + 1k-sphere scene at 3840x2160, 4 lights ("c4").  Other wo
 `value`  : scene resident in HBM, frame left in HBM on rank 0 (CUDA events, max over ranks).
 `e2e`    : the drop-in C-ABI call with HOST buffers each step — scene upload (pinned host ->
            HBM), render, gather, device -> host read of the packed frame.
-`roofline`: FP32-FMA bound (no tensor cores on this path).  achieved = 12 flop (6 FFMA per
-           ray-triangle pair, the filter formulation the kernels execute) x ALGORITHMIC pairs
-           (P*N primary + the reference's own in-order count for shadow rays) / sweep-kernel
-           time; peak = our own FFMA microbenchmark measured in the same process
+`roofline`: FP32-FMA bound (no tensor cores on this path).  achieved = the flops the sweeps
+           EXECUTE per ray-triangle pair (shadow 12 = 6 FFMA; primary 6.75: the q-term of each
+           edge row is shared by the 8 rays of a thread) x ALGORITHMIC pairs (P*N primary + the
+           reference's own in-order count for shadow rays) / sweep-kernel time; peak = our own FFMA microbenchmark measured in the same process
            (MEASURED_PEAKS.json has no FP32 number); nominal peak printed beside it.
 `cpu_baseline`: oracle/_ref (the unmodified reference compiled from /root/reference; kind
            "reference") or the plain-C port, on a bounded pixel sample of the same workload.
@@ -33,7 +33,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_PAIR = 12.0      # 6 FFMA (2-D affine edge rows): what the sweep executes per (ray, triangle) pair
+FLOP_PER_PAIR = 12.0      # 6 FFMA (2-D affine edge rows) per (ray, triangle) pair: shadow sweeps, and primary sweeps with jitter.
+                          # Primary sweeps without jitter share the inner term of each row among the 8 rays of a thread:
+                          # 2*(3+3*8)/8 = 6.75 flop per pair (the library reports the figure it ran: stats flop_primary)
 FLOP_PER_PAIR_REF = 46.0  # Moller-Trumbore with precomputed edges, reported beside it
 EYE, LOOK = (0.0, 1.0, 3.0), (0.0, 1.0, 0.0)
 
@@ -248,6 +250,8 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    flop_primary = float(st.get("flop_primary") or FLOP_PER_PAIR)  # executed flops per primary pair (same on every rank)
+    flop_shadow = float(st.get("flop_shadow") or FLOP_PER_PAIR)
     keys = ["n_primary_rays", "n_shadow_rays", "tests_primary", "tests_shadow", "tests_shadow_ref", "strict_evals",
             "kernel_launches", "ms_primary", "ms_shadow", "ms_total"]
     t = torch.tensor([ms] + [float(acc.get(k, 0)) for k in keys], dtype=torch.float64, device="cuda")
@@ -326,7 +330,9 @@ def main():
         alg_pairs = tot["tests_primary"] + tot["tests_shadow_ref"]
         swept_pairs = tot["tests_primary"] + tot["tests_shadow"]
         sweep_s = sweep_ms_max * 1e-3
-        achieved = FLOP_PER_PAIR * alg_pairs / world / sweep_s / 1e12  # per GPU
+        alg_flop = flop_primary * tot["tests_primary"] + flop_shadow * tot["tests_shadow_ref"]
+        swept_flop = flop_primary * tot["tests_primary"] + flop_shadow * tot["tests_shadow"]
+        achieved = alg_flop / world / sweep_s / 1e12  # per GPU
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -356,13 +362,21 @@ def main():
                 "traffic": traffic,
                 "peak_source": "own FFMA/FFMA2 microbenchmark in this process (tracer_cuda_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "peak_variants_tflops": peaks,
-                "flop_per_pair": FLOP_PER_PAIR, "algorithmic_pairs_per_step": alg_pairs / args.steps,
+                "flop_per_pair": {"primary": flop_primary, "shadow": flop_shadow,
+                                  "note": "flops the sweeps execute per (ray, triangle) pair: 6 FFMA = 12 (three 2-D affine edge rows); the "
+                                          "closest-hit sweep computes the q-term of each row once per thread (8 rays of one image row): "
+                                          "(3 + 3*8) FFMA / 8 pairs = 6.75"},
+                "algorithmic_pairs_per_step": alg_pairs / args.steps,
                 "swept_pairs_per_step": swept_pairs / args.steps, "sweep_ms_per_step": sweep_ms_max / args.steps,
-                "executed_tflops": FLOP_PER_PAIR * swept_pairs / world / sweep_s / 1e12,
+                "executed_tflops": swept_flop / world / sweep_s / 1e12,
                 "primary_ms_per_step": tot["ms_primary"] / world / args.steps, "shadow_ms_per_step": tot["ms_shadow"] / world / args.steps,
-                "primary_tflops": FLOP_PER_PAIR * tot["tests_primary"] / (tot["ms_primary"] * 1e-3) / 1e12 if tot["ms_primary"] else None,
+                "primary_tflops": flop_primary * tot["tests_primary"] / (tot["ms_primary"] * 1e-3) / 1e12 if tot["ms_primary"] else None,
+                "shadow_tflops": flop_shadow * tot["tests_shadow"] / (tot["ms_shadow"] * 1e-3) / 1e12 if tot["ms_shadow"] else None,
+                "pair_rate_tpairs_s": swept_pairs / world / sweep_s / 1e12,
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / world / sweep_s / 1e12,
-                "ceiling_note": "6 FFMA + 1.5 LOP3 + 0.5 LDS/SHF per pair = 8 instr at the measured issue ceiling IPC ~0.8 per scheduler: loop ceiling 0.58 of nominal (tools/sweep_mb.cu, DESIGN.md 4)",
+                "ceiling_note": "shadow sweeps: 6 FFMA + 1.5 LOP3 + 0.5 LDS/SHF per pair = 8 instr at the measured issue ceiling IPC ~0.8: 0.58 of nominal; "
+                                "closest-hit sweep with shared q: 3.4 FFMA + 1.1 LOP3 + 0.5 per pair = 5 instr, 1.4x faster per pair but only 68% of its "
+                                "instructions are FFMA, so its FMA fraction is lower (tools/sweep_mb.cu, DESIGN.md 4)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
                         "streams": "filter tables (48 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
             },

@@ -60,7 +60,7 @@ class FrameStats(C.Structure):
         ("n_pixels", C.c_int64), ("n_primary_rays", C.c_int64), ("n_shadow_rays", C.c_int64),
         ("tests_primary", C.c_int64), ("tests_shadow", C.c_int64), ("tests_shadow_ref", C.c_int64),
         ("strict_evals", C.c_int64), ("filter_misses", C.c_int64), ("kernel_launches", C.c_int32),
-        ("n_sms", C.c_int32),
+        ("n_sms", C.c_int32), ("flop_primary", C.c_double), ("flop_shadow", C.c_double),
     ]
 
     def asdict(self):

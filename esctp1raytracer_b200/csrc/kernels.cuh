@@ -202,9 +202,14 @@ struct PrimaryParams {
     sweep::Counters *counters;
     int *work;
     int n_blocks, n_slices;
+    int tiles_x, n_rows; // ray blocks are screen tiles of (16*R) x 32 pixels: n_blocks = tiles_x * tiles_y
 };
 
-template <int R, bool EXHAUSTIVE>
+// Ray block = screen tile, each thread holding R horizontally consecutive pixels of ONE image row.  Without
+// jitter those R rays share the filter parameter q (SHAREDQ), so the inner term B*q + C of every edge function is
+// computed once per thread and triangle instead of once per ray: 3 + 3R FFMA per triangle instead of 6R (the
+// values — and therefore the filter's decisions — are bit-identical, the compiler merely sees one q).
+template <int R, bool EXHAUSTIVE, bool SHAREDQ>
 __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const PrimaryParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
@@ -226,14 +231,17 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         const int slice = item / p.n_blocks, blk = item - slice * p.n_blocks;
         const int tile_lo = (int)((long long)p.n_tiles * slice / p.n_slices);
         const int tile_hi = (int)((long long)p.n_tiles * (slice + 1) / p.n_slices);
-        const int base = blk * (sweep::THREADS * R);
+        const int W = p.bands.W;
+        const int tile_y = blk / p.tiles_x, tile_x = blk - tile_y * p.tiles_x;
+        const int x0 = (tile_x * 16 + (tid & 15)) * R, ly = tile_y * 32 + (tid >> 4);
         float rp[R], rq[R];
+        int kp[R];
         unsigned valid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int k = base + r * sweep::THREADS + tid;
-            if (k < p.bands.n_px) valid |= 1u << r;
-            k = min(k, p.bands.n_px - 1);
+            if (x0 + r < W && ly < p.n_rows) valid |= 1u << r;
+            const int k = min(ly, p.n_rows - 1) * W + min(x0 + r, W - 1);
+            kp[r] = k;
             int w, h;
             p.bands.map(k, w, h);
             const f3 d = primary_dir(p.cam, p.bands, w, h);
@@ -245,6 +253,11 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             sm.v[r][tid] = 0.f;
             sm.tri[r][tid] = -1;
         }
+        if (SHAREDQ) { // same image row, no jitter: every rq[r] holds the same bits; say so to the compiler
+            const float q0 = rq[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) rq[r] = q0;
+        }
         unsigned done = 0;
         sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, rp, rq, valid, done,
                                                  gtile, n_strict, n_swept, n_miss);
@@ -255,9 +268,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             if (!((valid >> r) & 1u)) continue;
             const float t = sm.t[r][tid];
             const int tri = sm.tri[r][tid];
-            if (tri >= 0)
-                atomicMin(&p.best[base + r * sweep::THREADS + tid],
-                          ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri);
+            if (tri >= 0) atomicMin(&p.best[kp[r]], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri);
         }
         __syncthreads(); // slots are rewritten by the next item
     }

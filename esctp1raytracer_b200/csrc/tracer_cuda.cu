@@ -184,13 +184,18 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
     return 0;
 }
 
-template <int R, bool EX>
-int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+template <int R, bool EX, bool SQ>
+int launch_primary_q(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem<R>);
-    CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trk::primary_kernel<R, EX><<<grid, sweep::THREADS, smem, st>>>(p);
+    CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trk::primary_kernel<R, EX, SQ><<<grid, sweep::THREADS, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
+}
+template <int R, bool EX>
+int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+    // rays of one thread share q unless the sample positions are jittered (extension)
+    return p.bands.spp_n > 1 ? launch_primary_q<R, EX, false>(p, grid, st) : launch_primary_q<R, EX, true>(p, grid, st);
 }
 template <int R, bool EX>
 int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st) {
@@ -568,6 +573,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // two-phase bundle cull (cull.cuh "block lists"): phase A emits block<<32|triangle into cand_a; the sorted
     // keys land in cand_b, which phase B reads while it emits its ray<<32|triangle candidates into cand_a again.
     // Returns the number of keys, or -1 when the survivor lists would not fit (then the streaming kernels run).
+    double flop_primary = 0.0; // executed FP32 flops per swept pair of the closest-hit sweep (default mode)
     const bool two_phase = cull && o.bundle_cull != 2;
     int64_t host_tests_primary = 0, host_tests_shadow = 0; // pairs considered by two-phase sweeps (every block x every triangle)
     auto ensure_boxes = [&](size_t n_blocks) -> int {
@@ -654,8 +660,12 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
         p.tri_verts = s->tri_verts;
         p.best = s->best, p.counters = s->counters, p.work = s->work;
-        p.n_blocks = (n_px + sweep::THREADS * d.R - 1) / (sweep::THREADS * d.R), p.n_slices = d.n_slices;
+        p.tiles_x = (W + 16 * d.R - 1) / (16 * d.R), p.n_rows = n_rows; // ray blocks = screen tiles of (16 R) x 32 pixels
+        p.n_blocks = p.tiles_x * ((n_rows + 31) / 32), p.n_slices = d.n_slices;
+        if (p.n_blocks < items_per_sm(true) * g.n_sms) // same sizing rule as pick_decomp, on the real block count
+            p.n_slices = std::max(1, std::min((items_per_sm(true) * g.n_sms + p.n_blocks - 1) / p.n_blocks, std::max(1, n_tiles / 4)));
         const int grid = std::min(p.n_blocks * p.n_slices, g.n_sms);
+        flop_primary = bands.spp_n > 1 ? 12.0 : 2.0 * (3 + 3 * d.R) / d.R;
         if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, p, grid, st)) return rc;
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
                                                                         s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
@@ -914,6 +924,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.strict_evals = (int64_t)hc.strict_evals;
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.kernel_launches = launches;
+    s->stats.flop_primary = flop_primary, s->stats.flop_shadow = cull ? 0.0 : 12.0;
     if (hc.cull_overflow)
         return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow; use the default mode for this scene");
     if (getenv("TRACER_CULL_DIAG"))

@@ -140,6 +140,9 @@ typedef struct tracer_frame_stats {
     int64_t filter_misses;  /* exhaustive_strict only: strict accepts the filter would have lost (must be 0) */
     int32_t kernel_launches;
     int32_t n_sms;
+    double flop_primary;    /* FP32 flops the closest-hit sweep executes per swept pair: 2*(3+3R)/R when the R rays of a
+                               thread share q (no jitter), else 12; 0 in bundle-cull mode                       */
+    double flop_shadow;     /* same for the any-hit sweeps: 12 (6 FFMA)                                         */
 } tracer_frame_stats;
 
 typedef struct tracer_device_info {

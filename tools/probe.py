@@ -33,7 +33,7 @@ for n, W, H, L in cases:
         wall = time.time() - t0
     st = out.stats
     ffma = 6.0
-    prim = st["tests_primary"] * ffma * 2 / (st["ms_primary"] * 1e-3) / 1e12
+    prim = st["tests_primary"] * (st.get("flop_primary") or ffma * 2) / (st["ms_primary"] * 1e-3) / 1e12  # executed flops
     shad = st["tests_shadow"] * ffma * 2 / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
     shad_ref = st["tests_shadow_ref"] * ffma * 2 / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
     rays = st["n_primary_rays"] + st["n_shadow_rays"]

@@ -291,6 +291,94 @@ __global__ void __launch_bounds__(512, 1) k_sat(const float4 *tile_g, int reps, 
     if (hits == 123456789) out[0] = hits;
 }
 
+// V6q: as V6 but the R rays of a thread share q (py), sign test via LOP3 (SIGN=1) or FMNMX3 (SIGN=0); 3-D rows when DIM3
+template <int R, int SIGN, int DIM3, int BATCH, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_2d_sq(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE * 3];
+    for (int i = threadIdx.x; i < TILE * 3; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float px[R], py[R], pz[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) px[r] = seed * (threadIdx.x + 1) * (r + 1), py[r] = seed * (threadIdx.x + 7) * 3, pz[r] = -1.f - seed * r;
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TILE; b += BATCH) {
+            unsigned neg = 0xffffffffu;
+#pragma unroll UNROLL
+            for (int k = 0; k < BATCH; ++k) {
+                const float4 rb = tile[3 * (b + k)], rc = tile[3 * (b + k) + 1], rd = tile[3 * (b + k) + 2];
+                float M = -1.f;
+                unsigned A = 0xffffffffu;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float x, y, z;
+                    if (DIM3) {
+                        x = fmaf(px[r], rb.x, fmaf(py[r], rb.y, fmaf(pz[r], rb.z, rb.w)));
+                        y = fmaf(px[r], rc.x, fmaf(py[r], rc.y, fmaf(pz[r], rc.z, rc.w)));
+                        z = fmaf(px[r], rd.x, fmaf(py[r], rd.y, fmaf(pz[r], rd.z, rd.w)));
+                    } else {
+                        x = fmaf(px[r], rb.x, fmaf(py[r], rb.y, rb.z));
+                        y = fmaf(px[r], rc.x, fmaf(py[r], rc.y, rc.z));
+                        z = fmaf(px[r], rd.x, fmaf(py[r], rd.y, rd.z));
+                    }
+                    if (SIGN)
+                        A &= __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
+                    else
+                        M = fmaxf(M, fminf(fminf(x, y), z));
+                }
+                neg = __funnelshift_l(SIGN ? A : __float_as_uint(M), neg, 1);
+            }
+            if (~neg & ((BATCH >= 32) ? 0xffffffffu : ((1u << BATCH) - 1u))) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+
+
+// V7q: as V7 with shared q: everything in the FMA pipe (no LOP3).
+// rows are pre-scaled so that a true candidate saturates to exactly 1: ind = x'*y'*z', acc += ind over the batch
+template <int R, int NACC, int BATCH, int UNROLL>
+__global__ void __launch_bounds__(512, 1) k_sat_sq(const float4 *tile_g, int reps, float *out, float seed) {
+    __shared__ __align__(16) float4 tile[TILE * 3];
+    for (int i = threadIdx.x; i < TILE * 3; i += blockDim.x) tile[i] = tile_g[i];
+    __syncthreads();
+    float px[R], py[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) px[r] = seed * (threadIdx.x + 1) * (r + 1), py[r] = seed * (threadIdx.x + 7) * 3;
+    int hits = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TILE; b += BATCH) {
+            float acc[NACC];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+#pragma unroll UNROLL
+            for (int k = 0; k < BATCH; ++k) {
+                const float4 rb = tile[3 * (b + k)], rc = tile[3 * (b + k) + 1], rd = tile[3 * (b + k) + 2];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float x = __saturatef(fmaf(px[r], rb.x, fmaf(py[r], rb.y, rb.z)));
+                    const float y = __saturatef(fmaf(px[r], rc.x, fmaf(py[r], rc.y, rc.z)));
+                    const float z = __saturatef(fmaf(px[r], rd.x, fmaf(py[r], rd.y, rd.z)));
+                    acc[r % NACC] = fmaf(x * y, z, acc[r % NACC]);
+                }
+            }
+            float s = acc[0];
+#pragma unroll
+            for (int a = 1; a < NACC; ++a) s += acc[a];
+            if (s >= 1.f) {
+                hits += 1;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+    if (hits == 123456789) out[0] = hits;
+}
+
+
 // VP: the production data path (TMA tile stream + mbarrier + per-tile barrier) without the strict path
 template <int R>
 __global__ void __launch_bounds__(sweep::THREADS, 1) k_prod(const float4 *table, int n_tiles, int n_blocks, int *work, float *out, float seed) {
@@ -400,6 +488,17 @@ int main() {
     ST(8, 1, 16, 4) ST(8, 2, 16, 4) ST(8, 4, 16, 4) ST(8, 8, 16, 4) ST(8, 2, 16, 2) ST(8, 2, 32, 4) ST(8, 2, 16, 8) ST(10, 2, 16, 4) ST(12, 2, 16, 2) ST(6, 2, 16, 4) ST(4, 2, 16, 4)
     run("SAT R=8 acc2 b16 u4 256thr", [&] { k_sat<8, 2, 16, 4><<<sms, 256>>>(tile_g, reps, out, seed); }, PAIRS(256, 8));
     run("SAT R=8 acc2 b16 u4 384thr", [&] { k_sat<8, 2, 16, 4><<<sms, 384>>>(tile_g, reps, out, seed); }, PAIRS(384, 8));
+    printf("-- shared-q variants (rays of a thread share q): same 18-flop-equiv column, i.e. a pair-rate scale\n");
+    run("SQ 2D LOP3 R=8 b16 u4", [&] { k_2d_sq<8, 1, 0, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("SQ 2D LOP3 R=8 b16 u2", [&] { k_2d_sq<8, 1, 0, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("SQ 2D LOP3 R=12 b16 u2", [&] { k_2d_sq<12, 1, 0, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 12));
+    run("SQ 2D LOP3 R=16 b16 u2", [&] { k_2d_sq<16, 1, 0, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 16));
+    run("SQ 2D FMNMX3 R=8 b16 u4", [&] { k_2d_sq<8, 0, 0, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("SQ SAT R=8 acc2 b16 u4", [&] { k_sat_sq<8, 2, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("SQ SAT R=8 acc4 b16 u4", [&] { k_sat_sq<8, 4, 16, 4><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("SQ SAT R=8 acc4 b16 u2", [&] { k_sat_sq<8, 4, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 8));
+    run("SQ SAT R=16 acc4 b16 u2", [&] { k_sat_sq<16, 4, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 16));
+    run("SQ SAT R=12 acc4 b16 u2", [&] { k_sat_sq<12, 4, 16, 2><<<sms, 512>>>(tile_g, reps, out, seed); }, PAIRS(512, 12));
     {   // production data path
         const int n_tiles = 400;
         std::vector<float> ht((size_t)n_tiles * TILE * 12, 0.f);
