@@ -202,7 +202,8 @@ struct PrimaryParams {
     sweep::Counters *counters;
     int *work;
     int n_blocks, n_slices;
-    int tiles_x, n_rows; // ray blocks are screen tiles of (16*R) x 32 pixels: n_blocks = tiles_x * tiles_y
+    int tiles_x, n_rows; // ray blocks are screen tiles of (TX*R) x (512/TX) pixels, TX = 1 << tx_log2: n_blocks = tiles_x * tiles_y
+    int tx_log2;         // threads across a tile (the host picks the shape that wastes the fewest pixels at the frame's edges)
 };
 
 // Ray block = screen tile, each thread holding R horizontally consecutive pixels of ONE image row.  Without
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         const int tile_hi = (int)((long long)p.n_tiles * (slice + 1) / p.n_slices);
         const int W = p.bands.W;
         const int tile_y = blk / p.tiles_x, tile_x = blk - tile_y * p.tiles_x;
-        const int x0 = (tile_x * 16 + (tid & 15)) * R, ly = tile_y * 32 + (tid >> 4);
+        const int txn = 1 << p.tx_log2;
+        const int x0 = (tile_x * txn + (tid & (txn - 1))) * R, ly = tile_y * (sweep::THREADS >> p.tx_log2) + (tid >> p.tx_log2);
         float rp[R], rq[R];
         int kp[R];
         unsigned valid = 0;
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             for (int r = 1; r < R; ++r) rq[r] = q0;
         }
         unsigned done = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, rp, rq, valid, done,
-                                                 gtile, n_strict, n_swept, n_miss);
+        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, sweep::RaySrc{}, rp, rq,
+                                                 valid, done, gtile, n_strict, n_swept, n_miss);
         const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
 #pragma unroll
@@ -573,6 +575,43 @@ struct ShadowParams {
     int *work;
 };
 
+// one (ray block, triangle slice) work item with RR rays per thread; the slot arrays are laid out for RS >= RR
+template <int RR, int RS, bool EXHAUSTIVE>
+__device__ __forceinline__ void shadow_item(sweep::Smem<RS> &sm, const ShadowParams &p, int base, int seg_end, int lo, int hi,
+                                            const float4 *__restrict__ tab, unsigned &gtile, unsigned &n_strict, unsigned &n_miss,
+                                            unsigned long long &tests) {
+    static_assert(RR <= RS, "slot layout too small");
+    const int tid = threadIdx.x, n = p.n_px;
+    float rp[RR], rq[RR];
+    int kp[RR];
+    unsigned valid = 0, done = 0;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        int e = base + r * sweep::THREADS + tid;
+        if (e < seg_end) valid |= 1u << r;
+        e = min(e, seg_end - 1);
+        const int k = p.list_in[e];
+        kp[r] = k;
+        rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
+        // origin, direction and length stay in the pixel state: the strict path fetches them on demand
+        // through the pixel index parked in the tri slot (sweep::RaySrc)
+        sm.tri[r][tid] = -2 - k;
+        // an earlier slice may already have published an occluder below this slice: nothing to do
+        const unsigned long long seen = p.px.best_occ[k];
+        if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
+    }
+    unsigned swept = 0;
+    sweep::sweep_table<RR, true, EXHAUSTIVE>(sm, tab, lo, hi, p.n_tris, p.tri_verts, sweep::RaySrc{p.px.ro, p.px.rd, p.px.rt, n}, rp,
+                                             rq, valid, done, gtile, n_strict, swept, n_miss);
+    tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        const int tri = sm.tri[r][tid];
+        if (((valid >> r) & 1u) && tri >= 0) // occlusion() leaves t = t2 behind (main.cpp:320-324): the multi-light carry
+            atomicMin(&p.px.best_occ[kp[r]], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(sm.t[r][tid]));
+    }
+}
+
 template <int R, bool EXHAUSTIVE>
 __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -583,7 +622,6 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         sweep::fence_barrier_init();
     }
     __syncthreads();
-    const int n = p.n_px;
     const int total_blocks = p.blk_off[p.F];
     const int n_slices = *p.n_slices;
     const int n_items = total_blocks * n_slices;
@@ -609,38 +647,26 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         const int hi = p.tile_lo + (int)((long long)n_tiles * (slice + 1) / n_slices);
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
         const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
-        float rp[R], rq[R];
-        int kp[R];
-        unsigned valid = 0, done = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int e = base + r * sweep::THREADS + tid;
-            if (e < seg_end) valid |= 1u << r;
-            e = min(e, seg_end - 1);
-            const int k = p.list_in[e];
-            kp[r] = k;
-            rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
-            sm.ox[r][tid] = p.px.ro[k], sm.oy[r][tid] = p.px.ro[n + k], sm.oz[r][tid] = p.px.ro[2 * n + k];
-            sm.dx[r][tid] = p.px.rd[k], sm.dy[r][tid] = p.px.rd[n + k], sm.dz[r][tid] = p.px.rd[2 * n + k];
-            sm.t[r][tid] = p.px.rt[k];
-            sm.v[r][tid] = 0.f;
-            sm.tri[r][tid] = -1;
-            // an earlier slice may already have published an occluder below this slice: nothing to do
-            const unsigned long long seen = p.px.best_occ[k];
-            if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
-        }
-        unsigned swept = 0;
         const int face = j % NFACE;
         const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-        sweep::sweep_table<R, true, EXHAUSTIVE>(sm, tab, lo, hi, p.n_tris, p.tri_verts, rp, rq, valid, done, gtile, n_strict,
-                                                swept, n_miss);
-        tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int tri = sm.tri[r][tid];
-            if (((valid >> r) & 1u) && tri >= 0) // occlusion() leaves t = t2 behind (main.cpp:320-324): the multi-light carry
-                atomicMin(&p.px.best_occ[kp[r]], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(sm.t[r][tid]));
+        // The last block of a ray group is rarely full.  Rays sit at base + r*THREADS + tid, so a block with at most
+        // THREADS*RR rays only has rays r < RR: sweep it with RR rays per thread instead of dragging empty lanes
+        // through every triangle (late chunks have few rays in many groups: this padding is a fixed cost per frame).
+        const int cnt = seg_end - base;
+        bool swept_it = false;
+        if constexpr (R >= 8) {
+            if (cnt > 4 * sweep::THREADS) {
+                shadow_item<8, R, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                swept_it = true;
+            }
         }
+        if constexpr (R >= 4) {
+            if (!swept_it && cnt > 2 * sweep::THREADS) {
+                shadow_item<4, R, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                swept_it = true;
+            }
+        }
+        if (!swept_it) shadow_item<2, R, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
         __syncthreads();
     }
     atomicAdd(&p.counters->tests_shadow, tests);

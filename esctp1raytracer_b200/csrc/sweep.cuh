@@ -116,6 +116,16 @@ struct __align__(128) Smem {
     int consumed[STAGES]; // closest-hit sweeps: warps that have finished the tile in this stage
 };
 
+// Where the strict path finds a ray.  Closest-hit sweeps compute their rays in the item prologue and keep them
+// in the shared-memory slots (src.ro == nullptr).  Any-hit sweeps would have to GATHER origin, direction and
+// length of 512*R rays per work item although only a few rays per item ever reach the strict path, so they
+// leave them in the pixel state and the strict path fetches them on demand through the pixel index, which is
+// parked in the (otherwise unused) tri slot as -2 - k until the ray finds its occluder.
+struct RaySrc {
+    const float *ro, *rd, *rt; // [3][n], [3][n], [n]
+    int n;
+};
+
 struct Counters {
     unsigned long long tests_primary, tests_shadow, strict_evals, tests_shadow_ref, n_hits, filter_misses;
     unsigned long long cull_l0, cull_l1, cull_tiles_any, cull_tiles_fallback; // bundle-cull diagnostics
@@ -136,9 +146,9 @@ __device__ __forceinline__ unsigned edge_sign(const float4 rb, const float4 rc, 
 // CLOSEST: cpp_intersect semantics (main.cpp:176-192) — keep going, lower index wins ties.
 // ANYHIT : occlusion() semantics (main.cpp:314-329) — the first accepted face in order ends
 //          the ray; it leaves t = t2 behind (the multi-light carry).  Returns newly-done rays.
-template <int R, bool ANYHIT>
-__device__ __noinline__ unsigned strict_tri(Smem<R> &sm, int tid, unsigned mask, int tri,
-                                            const float *__restrict__ tri_verts, unsigned &n_strict) {
+template <int R, bool ANYHIT, int RS> // RS: rays per thread the slot arrays are laid out for (>= R)
+__device__ __noinline__ unsigned strict_tri(Smem<RS> &sm, int tid, unsigned mask, int tri,
+                                            const float *__restrict__ tri_verts, const RaySrc src, unsigned &n_strict) {
     unsigned newly = 0;
     const float *p = tri_verts + 9 * (size_t)tri;
     const strict::f3 v0 = strict::mk(__ldg(p), __ldg(p + 1), __ldg(p + 2));
@@ -147,9 +157,18 @@ __device__ __noinline__ unsigned strict_tri(Smem<R> &sm, int tid, unsigned mask,
     while (mask) {
         const int r = __ffs(mask) - 1;
         mask &= mask - 1;
-        const strict::f3 o = strict::mk(sm.ox[r][tid], sm.oy[r][tid], sm.oz[r][tid]);
-        const strict::f3 d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
-        float t = sm.t[r][tid], v = sm.v[r][tid];
+        strict::f3 o, d;
+        float t, v;
+        if (ANYHIT && src.ro) { // on demand from the pixel state; the ray has no occluder yet, so t is its initial length
+            const int k = -2 - sm.tri[r][tid];
+            o = strict::mk(src.ro[k], src.ro[src.n + k], src.ro[2 * (size_t)src.n + k]);
+            d = strict::mk(src.rd[k], src.rd[src.n + k], src.rd[2 * (size_t)src.n + k]);
+            t = src.rt[k], v = 0.f;
+        } else {
+            o = strict::mk(sm.ox[r][tid], sm.oy[r][tid], sm.oz[r][tid]);
+            d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
+            t = sm.t[r][tid], v = sm.v[r][tid];
+        }
         ++n_strict;
         if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
             sm.t[r][tid] = t;
@@ -165,9 +184,9 @@ __device__ __noinline__ unsigned strict_tri(Smem<R> &sm, int tid, unsigned mask,
 // rp/rq: the rays' parameters in the table's direction parametrisation
 // valid: bit r set = ray r exists; done: bit r set = ray r needs no more tests
 // gtile: running tile counter of this CTA (mbarrier phase bookkeeping across ray blocks)
-template <int R, bool ANYHIT, bool EXHAUSTIVE>
-__device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
-                                            int n_tris, const float *__restrict__ tri_verts, const float (&rp)[R],
+template <int R, bool ANYHIT, bool EXHAUSTIVE, int RS>
+__device__ __forceinline__ void sweep_table(Smem<RS> &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
+                                            int n_tris, const float *__restrict__ tri_verts, const RaySrc rsrc, const float (&rp)[R],
                                             const float (&rq)[R], unsigned valid, unsigned &done, unsigned &gtile,
                                             unsigned &n_strict, unsigned &n_tiles_swept, unsigned &n_miss) {
     const int tid = threadIdx.x;
@@ -227,7 +246,7 @@ __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restric
                             int before[R];
 #pragma unroll
                             for (int r = 0; r < R; ++r) before[r] = sm.tri[r][tid];
-                            const unsigned nw = strict_tri<R, ANYHIT>(sm, tid, live, tri, tri_verts, n_strict);
+                            const unsigned nw = strict_tri<R, ANYHIT, RS>(sm, tid, live, tri, tri_verts, rsrc, n_strict);
                             if (ANYHIT) done |= nw;
 #pragma unroll
                             for (int r = 0; r < R; ++r)
@@ -236,7 +255,7 @@ __device__ __forceinline__ void sweep_table(Smem<R> &sm, const float4 *__restric
                     } else {
                         mask &= live;
                         if (mask) {
-                            const unsigned nw = strict_tri<R, ANYHIT>(sm, tid, mask, tri, tri_verts, n_strict);
+                            const unsigned nw = strict_tri<R, ANYHIT, RS>(sm, tid, mask, tri, tri_verts, rsrc, n_strict);
                             if (ANYHIT) done |= nw;
                         }
                     }

@@ -660,8 +660,13 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
         p.tri_verts = s->tri_verts;
         p.best = s->best, p.counters = s->counters, p.work = s->work;
-        p.tiles_x = (W + 16 * d.R - 1) / (16 * d.R), p.n_rows = n_rows; // ray blocks = screen tiles of (16 R) x 32 pixels
-        p.n_blocks = p.tiles_x * ((n_rows + 31) / 32), p.n_slices = d.n_slices;
+        p.n_rows = n_rows, p.n_blocks = 0; // ray blocks = screen tiles of (TX R) x (512 / TX) pixels: least edge waste wins
+        for (int lg = 3; lg <= 6; ++lg) {
+            const int tw = (1 << lg) * d.R, th = sweep::THREADS >> lg;
+            const int tx = (W + tw - 1) / tw, nb = tx * ((n_rows + th - 1) / th);
+            if (!p.n_blocks || nb < p.n_blocks) p.n_blocks = nb, p.tiles_x = tx, p.tx_log2 = lg;
+        }
+        p.n_slices = d.n_slices;
         if (p.n_blocks < items_per_sm(true) * g.n_sms) // same sizing rule as pick_decomp, on the real block count
             p.n_slices = std::max(1, std::min((items_per_sm(true) * g.n_sms + p.n_blocks - 1) / p.n_blocks, std::max(1, n_tiles / 4)));
         const int grid = std::min(p.n_blocks * p.n_slices, g.n_sms);
@@ -810,31 +815,48 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
         // triangle chunks: after each one the still-unoccluded rays are compacted (early exit, main.cpp:324)
-        int n_chunks = o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(64, n_tiles / 8));
-        n_chunks = std::min(n_chunks, n_tiles);
-        int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
+        // Chunk boundaries (in tiles).  Equal chunks keep the pairs swept past a ray's occluder lowest (x1.12 at 32
+        // chunks) and win when a light has many shadow rays; with few rays (small frames, one band share of a
+        // multi-GPU frame) the per-launch tails weigh more and boundaries that start fine (1/64 of the triangles: most
+        // occluded rays find their occluder early) and coarsen geometrically win (12 launches, x1.19).
+        // opts.shadow_chunks asks for that many equal chunks.
         std::vector<int> h_cnt((size_t)F);
+        CK_CUDA(cudaMemcpyAsync(h_cnt.data(), s->cursor, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(cudaStreamSynchronize(st));
+        int64_t n_live0 = 0;
+        for (int j = 0; j < F; ++j) n_live0 += h_cnt[j];
+        std::vector<int> bounds{0};
+        if (o.shadow_chunks > 0 || n_tiles < 64 || n_live0 >= ((int64_t)1 << 20)) {
+            const int nc = std::min(n_tiles, o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(32, n_tiles / 8)));
+            for (int c = 1; c <= nc; ++c) bounds.push_back((int)((int64_t)n_tiles * c / nc));
+        } else {
+            for (int f : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64}) bounds.push_back((int)((int64_t)n_tiles * f / 64));
+        }
+        const int n_chunks = (int)bounds.size() - 1;
+        int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
         const dim3 cgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
         bool live = true;
         int Rk = 8;
         for (int c = 0; c < n_chunks; ++c) {
             // The host looks at the live-ray counts only at the first chunk (which face tables to build, ray
-            // block size) and every 16th chunk (stop early); everything else is sized on the device, so
+            // block size) and every 8th chunk (stop early); everything else is sized on the device, so
             // the chunk launches queue back to back.
-            if (c % 16 == 0) {
-                CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
-                CK_CUDA(cudaStreamSynchronize(st));
+            if (c % 8 == 0) {
+                if (c) {
+                    CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+                    CK_CUDA(cudaStreamSynchronize(st));
+                }
                 int64_t n_live = 0;
                 for (int j = 0; j < F; ++j) n_live += h_cnt[j];
                 if (n_live == 0) { // every shadow ray of this light already has its occluder
                     live = false;
                     break;
                 }
-                Rk = pick_decomp(n_live, n_tiles / n_chunks, g.n_sms, o.rays_per_thread, F).R;
+                Rk = pick_decomp(n_live, bounds[c + 1] - bounds[c], g.n_sms, o.rays_per_thread, F).R;
             }
             if (c == 0)
                 if (int rc = build_face_tables(k, h_cnt)) return rc;
-            const int tile_lo = (int)((int64_t)n_tiles * c / n_chunks), tile_hi = (int)((int64_t)n_tiles * (c + 1) / n_chunks);
+            const int tile_lo = bounds[c], tile_hi = bounds[c + 1];
             trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::THREADS * Rk, tile_hi - tile_lo, g.n_sms, s->blk_off, cnt_out,
                                                        s->work, s->n_slices, items_per_sm(false), 4);
             CK_CUDA(cudaGetLastError());
