@@ -374,6 +374,11 @@ def main():
                 "shadow_tflops": flop_shadow * tot["tests_shadow"] / (tot["ms_shadow"] * 1e-3) / 1e12 if tot["ms_shadow"] else None,
                 "pair_rate_tpairs_s": swept_pairs / world / sweep_s / 1e12,
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / world / sweep_s / 1e12,
+                "pair_formulation_view": {
+                    "flop_per_pair": FLOP_PER_PAIR, "tflops": FLOP_PER_PAIR * alg_pairs / world / sweep_s / 1e12,
+                    "frac_of_measured_peak": FLOP_PER_PAIR * alg_pairs / world / sweep_s / 1e12 / peak_tflops,
+                    "note": "NOT roofline.frac: what the rate would be called if every pair were charged the 12 flop of an "
+                            "independent evaluation of its three edge rows; the closest-hit sweep avoids 5.25 of them per pair"},
                 "ceiling_note": "shadow sweeps: 6 FFMA + 1.5 LOP3 + 0.5 LDS/SHF per pair = 8 instr at the measured issue ceiling IPC ~0.8: 0.58 of nominal; "
                                 "closest-hit sweep with shared q: 3.4 FFMA + 1.1 LOP3 + 0.5 per pair = 5 instr, 1.4x faster per pair but only 68% of its "
                                 "instructions are FFMA, so its FMA fraction is lower (tools/sweep_mb.cu, DESIGN.md 4)",
