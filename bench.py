@@ -131,7 +131,24 @@ def cpu_sample(scene, W, H, n_pixels, threads, seed=42):
         o = rst.render_pixels(fs, Camera.for_frame(EYE, LOOK, W, H).as_array(), W, H, pw, ph, fid, n_threads=threads)
         secs, hits, kind = time.time() - t0, int((o.tri >= 0).sum()), "port"
     rays = n_pixels + hits * L
-    return dict(value=rays / secs / 1e6, unit="Mrays/s", cores=threads, kind=kind, seconds=secs,
+    # the same algorithm as a SIMD CPU comparator (oracle/restated.c, 8 triangles per AVX2 step, pinned
+    # bit-identical to the scalar restatement), timed on the same pixels: what a vectorised CPU build would reach
+    simd = None
+    try:
+        from esctp1raytracer_b200 import Camera
+
+        rst = Restated()
+        if rst.set_simd(True):
+            cam12 = Camera.for_frame(EYE, LOOK, W, H).as_array()
+            t0 = time.time()
+            o = rst.render_pixels(fs, cam12, W, H, pw, ph, fid, n_threads=threads)
+            dt = time.time() - t0
+            simd = dict(value=(n_pixels + int((o.tri >= 0).sum()) * L) / dt / 1e6, unit="Mrays/s", cores=threads, kind="port",
+                        seconds=dt, simd="AVX2, 8 triangles per step", sample="same pixels as cpu_baseline")
+        rst.set_simd(False)
+    except Exception as e:  # the comparator is optional
+        simd = {"unavailable": str(e)[:200]}
+    return dict(value=rays / secs / 1e6, unit="Mrays/s", cores=threads, kind=kind, seconds=secs, simd_comparator=simd,
                 sample=f"{n_pixels} random pixels of the {W}x{H} frame (all {scene.n_tris} triangles, {L} lights; spheres omitted: "
                        f"the reference has none), {'reference intersect()/occlusion() via oracle/_ref' if kind == 'reference' else 'oracle/restated.c'}, "
                        f"{threads} threads")

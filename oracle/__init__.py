@@ -166,6 +166,12 @@ class Restated:
         L.rst_dot.argtypes = [_f32p, _f32p]
         L.rst_cross.argtypes = [_f32p, _f32p, _f32p]
 
+    def set_simd(self, on: bool) -> bool:
+        """SURVEY 8f-4 CPU comparator: 8 triangles per step (AVX2), bit-identical to the scalar loops.
+        Process-wide; returns the mode in force (False when the CPU has no AVX2)."""
+        self.lib.rst_set_simd.restype = C.c_int
+        return bool(self.lib.rst_set_simd(int(bool(on))))
+
     def camera(self, eye, look, W, H, vup=(0, 1, 0), vfov=60.0):
         out = np.zeros(12, np.float32)
         aspect = np.float32(W) / np.float32(H)

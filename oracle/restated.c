@@ -116,7 +116,7 @@ static inline int sphere_test(v3 orig, v3 dir, const float *cr, float *t) {
 static inline int n_tris_of(const rst_scene *sc) { return sc->geom_tri_offset[sc->n_geoms]; }
 
 /* ---- closest hit: cpp_intersect, main.cpp:176-192, called as (t, v, v) ---- */
-static int closest_hit(const rst_scene *sc, v3 o, v3 d, float *t, float *v, int64_t *tests) {
+static int closest_hit_scalar(const rst_scene *sc, v3 o, v3 d, float *t, float *v, int64_t *tests) {
     int best = -1;
     const int n = n_tris_of(sc);
     float alias_uv = *v; /* u and v alias the caller's v (main.cpp:307/310) */
@@ -132,7 +132,7 @@ static int closest_hit(const rst_scene *sc, v3 o, v3 d, float *t, float *v, int6
 }
 
 /* ---- any hit: occlusion, main.cpp:314-329 (first accepted face in order) -- */
-static int first_occluder(const rst_scene *sc, v3 o, v3 d, float *t, int64_t *tests) {
+static int first_occluder_scalar(const rst_scene *sc, v3 o, v3 d, float *t, int64_t *tests) {
     const int n = n_tris_of(sc);
     float u, v;
     for (int i = 0; i < n; ++i) {
@@ -146,6 +146,143 @@ static int first_occluder(const rst_scene *sc, v3 o, v3 d, float *t, int64_t *te
     for (int s = 0; s < sc->n_spheres; ++s)
         if (sphere_test(o, d, sc->sphere_cr + 4 * s, t)) return n + s;
     return -1;
+}
+
+
+/* ---- the same tests 8 triangles at a time (AVX2) -------------------------
+ * A CPU comparator for boxes without ispc: the reference's per-lane arithmetic, in the same
+ * order and precision (float products and sums, double det / inv_det / scaling, ordered
+ * compares so NaNs take the same branches), applied to 8 consecutive triangles per step;
+ * lanes that pass are then resolved one by one in index order, so closest-hit ties and the
+ * first-occluder rule come out exactly as in the scalar loops above.  Pinned bit-for-bit
+ * against them (tests/test_oracle_pin.py).  Enabled per process with rst_set_simd(1). */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define RST_AVX2 __attribute__((target("avx2")))
+typedef struct {
+    int n, n_pad;
+    float *a[9]; /* v0.xyz, e1.xyz, e2.xyz, each n_pad floats */
+} soa_tris;
+static int g_simd = 0;
+static soa_tris g_soa; /* of the scene being rendered (one render at a time when SIMD is on) */
+
+int rst_set_simd(int on) {
+    g_simd = on && __builtin_cpu_supports("avx2");
+    return g_simd;
+}
+
+static void soa_build(const rst_scene *sc) {
+    const int n = n_tris_of(sc), n_pad = (n + 7) & ~7;
+    g_soa.n = n, g_soa.n_pad = n_pad;
+    for (int c = 0; c < 9; ++c) g_soa.a[c] = (float *)aligned_alloc(32, sizeof(float) * (size_t)(n_pad ? n_pad : 8));
+    for (int i = 0; i < n_pad; ++i) {
+        v3 v0 = V(0, 0, 0), e1 = V(0, 0, 0), e2 = V(0, 0, 0); /* padding: det == 0, rejected */
+        if (i < n) {
+            const float *p = sc->tri_verts + 9 * (size_t)i;
+            v0 = ld3(p), e1 = sub3(ld3(p + 3), v0), e2 = sub3(ld3(p + 6), v0);
+        }
+        g_soa.a[0][i] = v0.x, g_soa.a[1][i] = v0.y, g_soa.a[2][i] = v0.z;
+        g_soa.a[3][i] = e1.x, g_soa.a[4][i] = e1.y, g_soa.a[5][i] = e1.z;
+        g_soa.a[6][i] = e2.x, g_soa.a[7][i] = e2.y, g_soa.a[8][i] = e2.z;
+    }
+}
+static void soa_free(void) {
+    for (int c = 0; c < 9; ++c) free(g_soa.a[c]), g_soa.a[c] = NULL;
+}
+
+/* (float)((double)x * inv) for 8 lanes, inv given as two 4-lane halves */
+RST_AVX2 static inline __m256 scale8(__m256 x, __m256d inv_lo, __m256d inv_hi) {
+    const __m256d lo = _mm256_mul_pd(_mm256_cvtps_pd(_mm256_castps256_ps128(x)), inv_lo);
+    const __m256d hi = _mm256_mul_pd(_mm256_cvtps_pd(_mm256_extractf128_ps(x, 1)), inv_hi);
+    return _mm256_set_m128(_mm256_cvtpd_ps(hi), _mm256_cvtpd_ps(lo));
+}
+RST_AVX2 static inline __m256 dot8(__m256 ax, __m256 ay, __m256 az, __m256 bx, __m256 by, __m256 bz) {
+    /* vec.h:95-101: ((0 + ax*bx) + ay*by) + az*bz; 0 + x is exact except for x = -0, which it turns into +0 */
+    __m256 r = _mm256_add_ps(_mm256_setzero_ps(), _mm256_mul_ps(ax, bx));
+    r = _mm256_add_ps(r, _mm256_mul_ps(ay, by));
+    return _mm256_add_ps(r, _mm256_mul_ps(az, bz));
+}
+/* tests triangles i..i+7 against t_now; returns the lane mask of accepts and their t2 / v2 */
+RST_AVX2 static inline int tri_test8(v3 o, v3 d, int i, float t_now, float t2_out[8], float v2_out[8]) {
+    const __m256 v0x = _mm256_load_ps(g_soa.a[0] + i), v0y = _mm256_load_ps(g_soa.a[1] + i), v0z = _mm256_load_ps(g_soa.a[2] + i);
+    const __m256 e1x = _mm256_load_ps(g_soa.a[3] + i), e1y = _mm256_load_ps(g_soa.a[4] + i), e1z = _mm256_load_ps(g_soa.a[5] + i);
+    const __m256 e2x = _mm256_load_ps(g_soa.a[6] + i), e2y = _mm256_load_ps(g_soa.a[7] + i), e2z = _mm256_load_ps(g_soa.a[8] + i);
+    const __m256 dx = _mm256_set1_ps(d.x), dy = _mm256_set1_ps(d.y), dz = _mm256_set1_ps(d.z);
+    const __m256 eps = _mm256_set1_ps(EPS), one = _mm256_set1_ps(1.0f);
+    /* pvec = cross(dir, edge2) */
+    const __m256 px = _mm256_sub_ps(_mm256_mul_ps(dy, e2z), _mm256_mul_ps(dz, e2y));
+    const __m256 py = _mm256_sub_ps(_mm256_mul_ps(dz, e2x), _mm256_mul_ps(dx, e2z));
+    const __m256 pz = _mm256_sub_ps(_mm256_mul_ps(dx, e2y), _mm256_mul_ps(dy, e2x));
+    const __m256 detf = dot8(e1x, e1y, e1z, px, py, pz);
+    /* det > -EPS && det < EPS (as doubles of floats: same truth values as the float compares) */
+    __m256 rej = _mm256_and_ps(_mm256_cmp_ps(detf, _mm256_sub_ps(_mm256_setzero_ps(), eps), _CMP_GT_OQ), _mm256_cmp_ps(detf, eps, _CMP_LT_OQ));
+    const __m256d inv_lo = _mm256_div_pd(_mm256_set1_pd(1.0), _mm256_cvtps_pd(_mm256_castps256_ps128(detf)));
+    const __m256d inv_hi = _mm256_div_pd(_mm256_set1_pd(1.0), _mm256_cvtps_pd(_mm256_extractf128_ps(detf, 1)));
+    const __m256 tx = _mm256_sub_ps(_mm256_set1_ps(o.x), v0x), ty = _mm256_sub_ps(_mm256_set1_ps(o.y), v0y), tz = _mm256_sub_ps(_mm256_set1_ps(o.z), v0z);
+    const __m256 u2 = scale8(dot8(tx, ty, tz, px, py, pz), inv_lo, inv_hi);
+    rej = _mm256_or_ps(rej, _mm256_or_ps(_mm256_cmp_ps(u2, eps, _CMP_LT_OQ), _mm256_cmp_ps(u2, one, _CMP_GT_OQ)));
+    /* qvec = cross(tvec, edge1) */
+    const __m256 qx = _mm256_sub_ps(_mm256_mul_ps(ty, e1z), _mm256_mul_ps(tz, e1y));
+    const __m256 qy = _mm256_sub_ps(_mm256_mul_ps(tz, e1x), _mm256_mul_ps(tx, e1z));
+    const __m256 qz = _mm256_sub_ps(_mm256_mul_ps(tx, e1y), _mm256_mul_ps(ty, e1x));
+    const __m256 v2 = scale8(dot8(dx, dy, dz, qx, qy, qz), inv_lo, inv_hi);
+    rej = _mm256_or_ps(rej, _mm256_or_ps(_mm256_cmp_ps(v2, eps, _CMP_LT_OQ), _mm256_cmp_ps(_mm256_add_ps(u2, v2), one, _CMP_GT_OQ)));
+    const __m256 t2 = scale8(dot8(e2x, e2y, e2z, qx, qy, qz), inv_lo, inv_hi);
+    rej = _mm256_or_ps(rej, _mm256_or_ps(_mm256_cmp_ps(t2, eps, _CMP_LT_OQ), _mm256_cmp_ps(t2, _mm256_set1_ps(t_now), _CMP_GE_OQ)));
+    _mm256_storeu_ps(t2_out, t2);
+    _mm256_storeu_ps(v2_out, v2);
+    return ~_mm256_movemask_ps(rej) & 0xff;
+}
+
+RST_AVX2 static int closest_hit_simd(const rst_scene *sc, v3 o, v3 d, float *t, float *v, int64_t *tests) {
+    int best = -1;
+    float alias_uv = *v, t2[8], v2[8];
+    for (int i = 0; i < g_soa.n_pad; i += 8) {
+        int m = tri_test8(o, d, i, *t, t2, v2);
+        while (m) { /* in index order, against the running t (ray_triangle.h:49) */
+            const int l = __builtin_ctz(m);
+            m &= m - 1;
+            if (t2[l] >= *t) continue;
+            *t = t2[l], alias_uv = v2[l], best = i + l;
+        }
+    }
+    *v = alias_uv;
+    *tests += g_soa.n;
+    for (int s = 0; s < sc->n_spheres; ++s)
+        if (sphere_test(o, d, sc->sphere_cr + 4 * s, t)) best = g_soa.n + s;
+    return best;
+}
+
+RST_AVX2 static int first_occluder_simd(const rst_scene *sc, v3 o, v3 d, float *t, int64_t *tests) {
+    float t2[8], v2[8];
+    for (int i = 0; i < g_soa.n_pad; i += 8) {
+        const int m = tri_test8(o, d, i, *t, t2, v2);
+        if (m) {
+            const int l = __builtin_ctz(m);
+            *t = t2[l];
+            *tests += i + l + 1;
+            return i + l;
+        }
+    }
+    *tests += g_soa.n;
+    for (int s = 0; s < sc->n_spheres; ++s)
+        if (sphere_test(o, d, sc->sphere_cr + 4 * s, t)) return g_soa.n + s;
+    return -1;
+}
+#else
+static int g_simd = 0;
+int rst_set_simd(int on) { (void)on; return 0; }
+static void soa_build(const rst_scene *sc) { (void)sc; }
+static void soa_free(void) {}
+#define closest_hit_simd closest_hit_scalar
+#define first_occluder_simd first_occluder_scalar
+#endif
+
+static int closest_hit(const rst_scene *sc, v3 o, v3 d, float *t, float *v, int64_t *tests) {
+    return g_simd ? closest_hit_simd(sc, o, d, t, v, tests) : closest_hit_scalar(sc, o, d, t, v, tests);
+}
+static int first_occluder(const rst_scene *sc, v3 o, v3 d, float *t, int64_t *tests) {
+    return g_simd ? first_occluder_simd(sc, o, d, t, tests) : first_occluder_scalar(sc, o, d, t, tests);
 }
 
 static int geom_of_tri(const rst_scene *sc, int tri) {
@@ -407,6 +544,7 @@ int rst_render_spp(const rst_scene *sc, const float cam[12], int W, int H, uint3
                    uint8_t *rgb8) {
     if (sc->n_lights > 64 || spp_n < 1) return -1;
     if (n_threads < 1) n_threads = 1;
+    if (g_simd) soa_build(sc);
     spp_job *js = (spp_job *)malloc(sizeof(spp_job) * n_threads);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
     for (int k = 0; k < n_threads; ++k) {
@@ -417,6 +555,7 @@ int rst_render_spp(const rst_scene *sc, const float cam[12], int W, int H, uint3
     for (int k = 0; k < n_threads; ++k) pthread_join(th[k], NULL);
     free(js);
     free(th);
+    if (g_simd) soa_free();
     return 0;
 }
 
@@ -493,6 +632,7 @@ int rst_render(const rst_scene *sc, const float cam[12], int W, int H, uint32_t 
     j.sc = sc, j.cam = cam, j.W = W, j.H = H, j.hits = hits, j.out = out;
     j.h_lo = 0, j.h_hi = H;
     j.phase = 0;
+    if (g_simd) soa_build(sc);
     run_jobs(&j, n_threads, frame_worker, tests);
     int32_t *faceid = NULL;
     if (!faceid_in) {
@@ -512,6 +652,7 @@ int rst_render(const rst_scene *sc, const float cam[12], int W, int H, uint32_t 
     j.phase = 1;
     j.faceid = faceid_in;
     run_jobs(&j, n_threads, frame_worker, tests);
+    if (g_simd) soa_free();
     if (out->n_tests) out->n_tests[0] = tests[0], out->n_tests[1] = tests[1];
     free(hits);
     free(faceid);
@@ -548,7 +689,9 @@ int rst_render_pixels(const rst_scene *sc, const float cam[12], int W, int H, in
     memset(&j, 0, sizeof j);
     j.sc = sc, j.cam = cam, j.W = W, j.H = H, j.out = out;
     j.n = n, j.pw = pw, j.ph = ph, j.faceid = faceids;
+    if (g_simd) soa_build(sc);
     run_jobs(&j, n_threads, pixel_worker, tests);
+    if (g_simd) soa_free();
     if (out->n_tests) out->n_tests[0] = tests[0], out->n_tests[1] = tests[1];
     return 0;
 }

@@ -70,6 +70,11 @@ int rst_render_pixels(const rst_scene *sc, const float cam[12], int W, int H, in
 int rst_render_spp(const rst_scene *sc, const float cam[12], int W, int H, uint32_t seed, int spp_n, int n_threads, float *rgb,
                    uint8_t *rgb8);
 
+/* SURVEY 8f-4 CPU comparator: run the triangle loops 8 triangles at a time (AVX2), bit-identical to the scalar
+ * loops by construction and pinned against them.  Process-wide switch; returns the mode in force (0 when the CPU
+ * has no AVX2).  One render at a time while it is on. */
+int rst_set_simd(int on);
+
 /* single-call known-answer entry: Moller-Trumbore exactly as ray_triangle.h:7-57 */
 int rst_intersect_triangle(const float orig[3], const float dir[3], const float v0[3], const float v1[3],
                            const float v2[3], float *t, float *u, float *v);

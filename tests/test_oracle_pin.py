@@ -142,3 +142,32 @@ def test_spp_extension_reduces_to_single_sample(restated):
     assert np.array_equal(bits(rgb), bits(o.rgb)) and np.array_equal(rgb8, o.rgb8)
     rgb4, _ = restated.render_spp(to_flat(s), cam, W, H, seed, 2)
     assert not np.array_equal(rgb4, rgb) and abs(float(rgb4.mean()) - float(rgb.mean())) < 0.05
+
+
+def test_simd_comparator_is_bit_identical_to_the_scalar_restatement(restated):
+    """the 8-triangles-per-step AVX2 form of the restatement (the CPU comparator for boxes without ispc)
+    must reproduce the scalar loops bit for bit: ids, t, v, occluders, float accumulator, u8 — on the reference's
+    golden models (index-order ties, self-shadow chaos) and on a multi-light soup with normals, specular and spheres."""
+    from esctp1raytracer_b200 import Camera, hash_faceids, scenes
+
+    if not restated.set_simd(True):
+        restated.set_simd(False)
+        pytest.skip("no AVX2 on this CPU")
+    try:
+        cases = []
+        for name in golden_names():
+            fs, fr = load_golden(name)
+            cases.append((fs, fr["cam"], fr["W"], fr["H"], fr["faceid"]))
+        s = scenes.soup_scene(5003, 17, 3, seed=11, with_normals=True, specular=True, n_spheres=7)
+        W, H = 40, 30
+        cases.append((to_flat(s), Camera.for_frame((0, 1, 3), (0, 1, 0), W, H).as_array(), W, H, hash_faceids(9, W, H, s.faces_per_light)))
+        for fs, cam, W, H, fid in cases:
+            restated.set_simd(True)
+            a = restated.render(fs, cam, W, H, faceid=fid)
+            restated.set_simd(False)
+            b = restated.render(fs, cam, W, H, faceid=fid)
+            assert np.array_equal(a.tri, b.tri) and np.array_equal(bits(a.t), bits(b.t)) and np.array_equal(bits(a.v), bits(b.v))
+            assert np.array_equal(a.occ_tri, b.occ_tri) and np.array_equal(bits(a.rgb), bits(b.rgb)) and np.array_equal(a.rgb8, b.rgb8)
+            assert np.array_equal(a.n_tests, b.n_tests)
+    finally:
+        restated.set_simd(False)
