@@ -49,7 +49,7 @@ int main(int argc, char *argv[]) {
                 rng = r == "hash" ? TRACER_RNG_HASH : TRACER_RNG_MT19937;
             } else if (f == "--device") device = std::atoi(need("--device"));
             else if (f == "--p6") p6 = 1;
-            else if (f == "--cull") bundle_cull = 1; // optional bundle-cull mode: same bytes out, much faster on big scenes
+            else if (f == "--cull") bundle_cull = 3; // optional bundle-cull mode: same bytes out, much faster on big scenes
             else throw std::runtime_error("Unknown argument: " + f); // main.cpp:531-534
         }
         tracer_scene_host *scene = nullptr;

@@ -546,7 +546,10 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int), st));
 
     const int n_tiles = s->n_pad / sweep::TILE;
-    const bool cull = o.bundle_cull != 0;
+    // bundle_cull: 1 two-phase, 2 streaming, 3 auto = two-phase unless the default sweeps are estimated to be the
+    // faster of the two (tiny scenes: the mode has a fixed cost of a few ms in sorts and count read-backs)
+    const double est_default_ms = (double)n_px * (double)s->n_tris * (1.0 + 0.25 * L) / 4.0e9;
+    const bool cull = o.bundle_cull == 3 ? est_default_ms > 6.0 : o.bundle_cull != 0;
     if (cull) { // candidate buffers: 24 per ray + slack (a few per ray are typical), sorted with a radix sort
         const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
         if (cap > s->cand_cap) {
@@ -599,7 +602,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
         launches += 2;
         if (getenv("TRACER_CULL_DIAG")) fprintf(stderr, "cull diag: phase A kept %llu (block, triangle) pairs over %d groups, <= %d blocks\n", n, lp.n_groups, max_blocks);
-        if (n > s->cand_cap) {
+        const char *cap_env = getenv("TRACER_L0_CAP"); // development/test knob: pretend the key buffer is this small
+        if (n > s->cand_cap || (cap_env && n > (unsigned long long)std::atoll(cap_env))) {
             n_keys = -1;
             return 0;
         }

@@ -114,7 +114,8 @@ typedef struct tracer_render_opts {
     int32_t shadow_chunks;     /* tuning: 0 = auto; triangle chunks between shadow-ray compactions */
     int32_t bundle_cull;       /* OPTIONAL mode: hierarchical (bundle box -> warp box -> ray) evaluation of the same
                                   conservative filter; identical results.  1 = two-phase (dense block-box pass, then
-                                  per-block survivor lists), 2 = single streaming sweep (also the fall-back of 1) */
+                                  per-block survivor lists), 2 = single streaming sweep (also the fall-back of 1),
+                                  3 = auto: two-phase unless the scene is so small that the default sweeps are faster */
 
     /* optional debug outputs, HOST pointers, indexed like the output rows
      * (local pixel k = local_row*W + w), any may be NULL */

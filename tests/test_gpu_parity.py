@@ -334,6 +334,8 @@ def test_bundle_cull_identical_to_default(renderer):
         assert b.stats["tests_shadow_ref"] == a.stats["tests_shadow_ref"] and b.stats["n_shadow_rays"] == a.stats["n_shadow_rays"]
         c = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=2)  # streaming form (fall-back)
         _same_frames(a, c)
+        d = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=3)  # auto (picks the default sweeps here)
+        _same_frames(a, d)
     # bands and multi-sample in cull mode
     s, W, H = cases[0][0], 100, 77
     cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
@@ -399,3 +401,21 @@ def test_render_frame_is_ordered_on_torchs_stream(renderer):
         a, _ = tdist.render_frame(renderer, rs, cam, W, H, seed=5)
         b, _ = tdist.render_frame(renderer, rs, cam, W, H, seed=5, bundle_cull=True)
     assert np.array_equal(a.cpu().numpy(), want) and np.array_equal(b.cpu().numpy(), want)
+
+
+def test_bundle_cull_falls_back_to_streaming_when_keys_do_not_fit(renderer):
+    """two-phase mode: when phase A's survivor keys would not fit their buffer the sweep must fall back to the
+    streaming form and still produce the default mode's frame (the buffer limit is faked with TRACER_L0_CAP)."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+
+    s = scenes.soup_scene(20000, 40, 3, seed=6)
+    W, H = 96, 64
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True)
+    os.environ["TRACER_L0_CAP"] = "100"
+    try:
+        b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=1)
+    finally:
+        del os.environ["TRACER_L0_CAP"]
+    _same_frames(a, b)
