@@ -357,11 +357,12 @@ def main():
             pass
         prim_bytes = 48.0 * scene.n_tris * (1 + scene.n_lights * 2) + 36.0 * scene.n_tris
         hbm_gbs = (prim_bytes + 3.0 * W * H / world) * args.steps / (ms * 1e-3) / 1e9
-        traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic = traffic_detail = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = {"bytes_per_launch": tj["traffic_bytes_per_launch"], "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
-                       "kernel": tj["kernel"], "capture_config": tj["config_of_capture"], "source": tj["capture"]}
+            traffic = tj["traffic_bytes_per_launch"]
+            traffic_detail = {"algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"], "kernel": tj["kernel"],
+                              "capture_config": tj["config_of_capture"], "source": tj["capture"], "note": tj.get("algorithmic_note")}
         except Exception:
             pass
         cpu = None
@@ -376,7 +377,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_detail": traffic_detail,
                 "peak_source": "own FFMA/FFMA2 microbenchmark in this process (tracer_cuda_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "peak_variants_tflops": peaks,
                 "flop_per_pair": {"primary": flop_primary, "shadow": flop_shadow,
