@@ -33,9 +33,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_PAIR = 12.0      # 6 FFMA (2-D affine edge rows) per (ray, triangle) pair: shadow sweeps, and primary sweeps with jitter.
-                          # Primary sweeps without jitter share the inner term of each row among the 8 rays of a thread:
-                          # 2*(3+3*8)/8 = 6.75 flop per pair (the library reports the figure it ran: stats flop_primary)
+FLOP_PER_PAIR = 12.0      # 6 FFMA (2-D affine edge rows) per (ray, triangle) pair when every ray evaluates its own rows.
+                          # The sweeps share the q-term of each row among the 8 rays of a thread: primary 2*(3+3*8)/8 = 6.75
+                          # (same image row: exact), shadow 2*(6+3*8)/8 = 7.5 (q-sorted rays: mean q + |B|*spread); the library
+                          # reports the figures it ran (stats flop_primary / flop_shadow)
 FLOP_PER_PAIR_REF = 46.0  # Moller-Trumbore with precomputed edges, reported beside it
 EYE, LOOK = (0.0, 1.0, 3.0), (0.0, 1.0, 0.0)
 
@@ -381,9 +382,10 @@ def main():
                 "peak_source": "own FFMA/FFMA2 microbenchmark in this process (tracer_cuda_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "peak_variants_tflops": peaks,
                 "flop_per_pair": {"primary": flop_primary, "shadow": flop_shadow,
-                                  "note": "flops the sweeps execute per (ray, triangle) pair: 6 FFMA = 12 (three 2-D affine edge rows); the "
-                                          "closest-hit sweep computes the q-term of each row once per thread (8 rays of one image row): "
-                                          "(3 + 3*8) FFMA / 8 pairs = 6.75"},
+                                  "note": "flops the sweeps execute per (ray, triangle) pair.  Three 2-D affine edge rows = 6 FFMA = 12 when "
+                                          "each ray evaluates its own; both sweeps compute the q-term of each row once per thread: closest hit "
+                                          "(3 + 3*8) FFMA / 8 pairs = 6.75 (8 rays of one image row share q exactly), shadow (6 + 3*8) / 8 = 7.5 "
+                                          "(8 consecutive rays of the q-sorted list: mean q plus |B| * spread, still a necessary condition)"},
                 "algorithmic_pairs_per_step": alg_pairs / args.steps,
                 "swept_pairs_per_step": swept_pairs / args.steps, "sweep_ms_per_step": sweep_ms_max / args.steps,
                 "executed_tflops": swept_flop / world / sweep_s / 1e12,
@@ -397,9 +399,10 @@ def main():
                     "frac_of_measured_peak": FLOP_PER_PAIR * alg_pairs / world / sweep_s / 1e12 / peak_tflops,
                     "note": "NOT roofline.frac: what the rate would be called if every pair were charged the 12 flop of an "
                             "independent evaluation of its three edge rows; the closest-hit sweep avoids 5.25 of them per pair"},
-                "ceiling_note": "shadow sweeps: 6 FFMA + 1.5 LOP3 + 0.5 LDS/SHF per pair = 8 instr at the measured issue ceiling IPC ~0.8: 0.58 of nominal; "
-                                "closest-hit sweep with shared q: 3.4 FFMA + 1.1 LOP3 + 0.5 per pair = 5 instr, 1.4x faster per pair but only 68% of its "
-                                "instructions are FFMA, so its FMA fraction is lower (tools/sweep_mb.cu, DESIGN.md 4)",
+                "ceiling_note": "every instruction mix tried issues at IPC ~0.8 per scheduler.  One q per ray: 6 FFMA + 1.5 LOP3 + 0.5 LDS/SHF = 8 instr "
+                                "per pair (0.58 of nominal FMA peak).  Shared q-terms: 3.4-3.75 FFMA + 1.1-1.5 LOP3 + 0.5 = 5-5.75 instr per pair: 1.3-1.4x "
+                                "faster per pair, but only ~2/3 of the instructions are FFMA, so the executed-flop fraction is lower "
+                                "(tools/sweep_mb.cu, DESIGN.md 4)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
                         "streams": "filter tables (48 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
             },

@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
             for (int r = 1; r < R; ++r) rq[r] = q0;
         }
         unsigned done = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, sweep::RaySrc{}, rp, rq,
-                                                 valid, done, gtile, n_strict, n_swept, n_miss);
+        sweep::sweep_table<R, false, EXHAUSTIVE, false>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, sweep::RaySrc{}, rp, rq,
+                                                        0.f, 0.f, valid, done, gtile, n_strict, n_swept, n_miss);
         const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
 #pragma unroll
@@ -346,7 +346,8 @@ struct LightStepParams {
     int *seg_count;    // [F_k] histogram of rays per light vertex
     sweep::Counters *counters;
     int *dbg_occ;      // [n_px*L] or null
-    int cull_cells;    // != 0: bundle-cull mode, also write the 64-bit sort key (group << 32 | Morton code of (p,q))
+    int cull_cells;    // also write a 64-bit sort key: 1 = group << 32 | Morton code of (p,q) (bundle-cull mode),
+                       // 2 = group << 32 | order-preserving bits of q (default mode with shared q-terms)
     unsigned long long *rkey; // [n_px] sort keys (bundle-cull mode), all-ones for pixels without a shadow ray
 };
 
@@ -471,7 +472,10 @@ __global__ void __launch_bounds__(256) light_step_kernel(const LightStepParams p
                 p.px.re[kpx] = ok ? da * inv : 0.f;
                 p.px.re[n + kpx] = ok ? db * inv : 0.f;
                 const int key = fid * NFACE + face;
-                if (p.cull_cells) { // sort key: ray group, then the 16+16-bit Morton code of (p,q) on the face
+                if (p.cull_cells == 2) { // sort key: ray group, then q (default mode: the rays of a thread share a q-term)
+                    const unsigned qb = __float_as_uint(ok ? db * inv : 0.f);
+                    rkey_mine = ((unsigned long long)(unsigned)key << 32) | ((qb & 0x80000000u) ? ~qb : (qb | 0x80000000u));
+                } else if (p.cull_cells) { // sort key: ray group, then the 16+16-bit Morton code of (p,q) on the face
                     unsigned mx = ok ? (unsigned)fminf(65535.f, fmaxf(0.f, (da * inv + 1.f) * 32767.5f)) : 0u;
                     unsigned my = ok ? (unsigned)fminf(65535.f, fmaxf(0.f, (db * inv + 1.f) * 32767.5f)) : 0u;
                     mx = (mx | (mx << 8)) & 0x00ff00ffu, mx = (mx | (mx << 4)) & 0x0f0f0f0fu, mx = (mx | (mx << 2)) & 0x33333333u, mx = (mx | (mx << 1)) & 0x55555555u;
@@ -575,8 +579,10 @@ struct ShadowParams {
     int *work;
 };
 
-// one (ray block, triangle slice) work item with RR rays per thread; the slot arrays are laid out for RS >= RR
-template <int RR, int RS, bool EXHAUSTIVE>
+// one (ray block, triangle slice) work item with RR rays per thread; the slot arrays are laid out for RS >= RR.
+// QBAR: the list is ordered by q inside each group (and compaction keeps it so); a thread then takes RR CONSECUTIVE
+// rays, whose q differ by ~1e-6, and evaluates them with one q-term per edge row (sweep::edge_sign_qbar).
+template <int RR, int RS, bool EXHAUSTIVE, bool QBAR>
 __device__ __forceinline__ void shadow_item(sweep::Smem<RS> &sm, const ShadowParams &p, int base, int seg_end, int lo, int hi,
                                             const float4 *__restrict__ tab, unsigned &gtile, unsigned &n_strict, unsigned &n_miss,
                                             unsigned long long &tests) {
@@ -587,7 +593,7 @@ __device__ __forceinline__ void shadow_item(sweep::Smem<RS> &sm, const ShadowPar
     unsigned valid = 0, done = 0;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
-        int e = base + r * sweep::THREADS + tid;
+        int e = QBAR ? base + tid * RR + r : base + r * sweep::THREADS + tid;
         if (e < seg_end) valid |= 1u << r;
         e = min(e, seg_end - 1);
         const int k = p.list_in[e];
@@ -600,9 +606,18 @@ __device__ __forceinline__ void shadow_item(sweep::Smem<RS> &sm, const ShadowPar
         const unsigned long long seen = p.px.best_occ[k];
         if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
     }
+    float qbar = 0.f, qdelta = 0.f;
+    if (QBAR) { // rays past the end of the list are duplicates of the last one, so all RR values count
+        float qmin = rq[0], qmax = rq[0];
+#pragma unroll
+        for (int r = 1; r < RR; ++r) qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+        qbar = 0.5f * (qmin + qmax);
+        // >= max |q_r - qbar| with room for the roundings of this line and of the one extra FFMA per row
+        qdelta = fmaxf(qmax - qbar, qbar - qmin) * 1.0001f + 2.4e-7f * (fabsf(qbar) + 1.f);
+    }
     unsigned swept = 0;
-    sweep::sweep_table<RR, true, EXHAUSTIVE>(sm, tab, lo, hi, p.n_tris, p.tri_verts, sweep::RaySrc{p.px.ro, p.px.rd, p.px.rt, n}, rp,
-                                             rq, valid, done, gtile, n_strict, swept, n_miss);
+    sweep::sweep_table<RR, true, EXHAUSTIVE, QBAR>(sm, tab, lo, hi, p.n_tris, p.tri_verts, sweep::RaySrc{p.px.ro, p.px.rd, p.px.rt, n},
+                                                   rp, rq, qbar, qdelta, valid, done, gtile, n_strict, swept, n_miss);
     tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
@@ -612,7 +627,7 @@ __device__ __forceinline__ void shadow_item(sweep::Smem<RS> &sm, const ShadowPar
     }
 }
 
-template <int R, bool EXHAUSTIVE>
+template <int R, bool EXHAUSTIVE, bool QBAR>
 __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
@@ -656,17 +671,17 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
         bool swept_it = false;
         if constexpr (R >= 8) {
             if (cnt > 4 * sweep::THREADS) {
-                shadow_item<8, R, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                shadow_item<8, R, EXHAUSTIVE, QBAR>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
                 swept_it = true;
             }
         }
         if constexpr (R >= 4) {
             if (!swept_it && cnt > 2 * sweep::THREADS) {
-                shadow_item<4, R, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                shadow_item<4, R, EXHAUSTIVE, QBAR>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
                 swept_it = true;
             }
         }
-        if (!swept_it) shadow_item<2, R, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+        if (!swept_it) shadow_item<2, R, EXHAUSTIVE, QBAR>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
         __syncthreads();
     }
     atomicAdd(&p.counters->tests_shadow, tests);
@@ -698,6 +713,91 @@ __global__ void compact_kernel(const int *__restrict__ list_in, const int *__res
             if (k >= 0) list_out[begin + base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = k;
         }
     }
+}
+
+// ORDER-PRESERVING compaction (QBAR sweeps keep each group's list sorted by q): pass 1 counts the survivors of
+// every block of CBLK list entries, pass 2 sums the counts of the blocks before its own and writes its survivors
+// in list order.  grid = (blocks of the longest group, F).
+constexpr int CBLK = 1024;
+__global__ void __launch_bounds__(256) compact_count_kernel(const int *__restrict__ list_in, const int *__restrict__ seg_off,
+                                                            const int *__restrict__ cnt_in, int F,
+                                                            const unsigned long long *__restrict__ best_occ, int *__restrict__ blk_cnt,
+                                                            int max_blocks) {
+    const int j = blockIdx.y, bx = blockIdx.x;
+    if (j >= F) return;
+    const int begin = seg_off[j], count = cnt_in[j];
+    if (bx * CBLK >= count) return;
+    int alive = 0;
+#pragma unroll
+    for (int c = 0; c < CBLK / 256; ++c) {
+        const int i = bx * CBLK + threadIdx.x * (CBLK / 256) + c;
+        if (i < count && best_occ[list_in[begin + i]] == KEY_NONE) ++alive;
+    }
+    __shared__ int wsum[8];
+    int v = alive;
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        blk_cnt[(size_t)j * max_blocks + bx] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const int *__restrict__ list_in, const int *__restrict__ seg_off,
+                                                              const int *__restrict__ cnt_in, int F,
+                                                              const unsigned long long *__restrict__ best_occ,
+                                                              const int *__restrict__ blk_cnt, int max_blocks, int *__restrict__ list_out,
+                                                              int *cnt_out) {
+    const int j = blockIdx.y, bx = blockIdx.x;
+    if (j >= F) return;
+    const int begin = seg_off[j], count = cnt_in[j];
+    if (bx * CBLK >= count) return;
+    __shared__ int wsum[8], s_off;
+    // survivors in the blocks before this one
+    int before = 0;
+    for (int b = threadIdx.x; b < bx; b += 256) before += blk_cnt[(size_t)j * max_blocks + b];
+    for (int o = 16; o; o >>= 1) before += __shfl_down_sync(0xffffffffu, before, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        s_off = t;
+    }
+    __syncthreads();
+    const int off = s_off;
+    // this block's survivors, in list order: thread t owns CBLK/256 consecutive entries
+    int ks[CBLK / 256], alive = 0;
+#pragma unroll
+    for (int c = 0; c < CBLK / 256; ++c) {
+        const int i = bx * CBLK + threadIdx.x * (CBLK / 256) + c;
+        int k = -1;
+        if (i < count) {
+            k = list_in[begin + i];
+            if (best_occ[k] != KEY_NONE) k = -1;
+        }
+        ks[c] = k;
+        alive += k >= 0;
+    }
+    int incl = alive; // inclusive scan over the 256 threads
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __syncthreads(); // wsum is reused
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int i = 0; i < w; ++i) wbase += wsum[i];
+    int pos = off + wbase + incl - alive;
+#pragma unroll
+    for (int c = 0; c < CBLK / 256; ++c)
+        if (ks[c] >= 0) list_out[begin + pos++] = ks[c];
+    if ((bx + 1) * CBLK >= count && threadIdx.x == 255) cnt_out[j] = off + wbase + incl; // the group's last block: new count
 }
 
 // extension: spheres are tested after all triangles, in order, by the rays that found no triangle

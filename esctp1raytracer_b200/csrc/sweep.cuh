@@ -141,6 +141,17 @@ __device__ __forceinline__ unsigned edge_sign(const float4 rb, const float4 rc, 
     return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
 }
 
+// QBAR form: the R rays of a thread are evaluated with ONE q-term per edge row.  With qbar the thread's mean q and
+// qdelta >= max |q_r - qbar| the row value p*A + (qbar*B + |B|*qdelta + C) is >= the ray's own p*A + q_r*B + C, so
+// the test stays a necessary condition while the inner term costs 2 FFMA per thread instead of 1 per ray
+// (shadow rays sorted by q: qdelta ~ 1e-6, far inside the margin K already in C).
+__device__ __forceinline__ unsigned edge_sign_qbar(const float4 rb, const float4 rc, const float4 rd, float p, float qbar, float qdelta) {
+    const float x = fmaf(p, rb.x, fmaf(fabsf(rb.y), qdelta, fmaf(qbar, rb.y, rb.z)));
+    const float y = fmaf(p, rc.x, fmaf(fabsf(rc.y), qdelta, fmaf(qbar, rc.y, rc.z)));
+    const float z = fmaf(p, rd.x, fmaf(fabsf(rd.y), qdelta, fmaf(qbar, rd.y, rd.z)));
+    return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
+}
+
 // ---- strict path: the reference's own test on the surviving pairs ---------------
 // mask: rays (bit r) that are candidates for triangle tri.
 // CLOSEST: cpp_intersect semantics (main.cpp:176-192) — keep going, lower index wins ties.
@@ -184,11 +195,11 @@ __device__ __noinline__ unsigned strict_tri(Smem<RS> &sm, int tid, unsigned mask
 // rp/rq: the rays' parameters in the table's direction parametrisation
 // valid: bit r set = ray r exists; done: bit r set = ray r needs no more tests
 // gtile: running tile counter of this CTA (mbarrier phase bookkeeping across ray blocks)
-template <int R, bool ANYHIT, bool EXHAUSTIVE, int RS>
+template <int R, bool ANYHIT, bool EXHAUSTIVE, bool QBAR, int RS>
 __device__ __forceinline__ void sweep_table(Smem<RS> &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
                                             int n_tris, const float *__restrict__ tri_verts, const RaySrc rsrc, const float (&rp)[R],
-                                            const float (&rq)[R], unsigned valid, unsigned &done, unsigned &gtile,
-                                            unsigned &n_strict, unsigned &n_tiles_swept, unsigned &n_miss) {
+                                            const float (&rq)[R], float qbar, float qdelta, unsigned valid, unsigned &done,
+                                            unsigned &gtile, unsigned &n_strict, unsigned &n_tiles_swept, unsigned &n_miss) {
     const int tid = threadIdx.x;
     const int n_tiles = tile_hi - tile_lo;
     const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
@@ -219,7 +230,8 @@ __device__ __forceinline__ void sweep_table(Smem<RS> &sm, const float4 *__restri
                     const float4 rb = tp[3 * (b0 + k)], rc = tp[3 * (b0 + k) + 1], rd = tp[3 * (b0 + k) + 2];
                     unsigned A = 0xffffffffu;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) A &= edge_sign(rb, rc, rd, rp[r], rq[r]);
+                    for (int r = 0; r < R; ++r)
+                        A &= QBAR ? edge_sign_qbar(rb, rc, rd, rp[r], qbar, qdelta) : edge_sign(rb, rc, rd, rp[r], rq[r]);
                     neg = __funnelshift_l(A, neg, 1);
                 }
 #ifdef SWEEP_NO_STRICT // development microbenchmark only (tools/sweep_mb.cu): timing without the strict path
@@ -239,6 +251,7 @@ __device__ __forceinline__ void sweep_table(Smem<RS> &sm, const float4 *__restri
                     unsigned mask = 0;
 #pragma unroll
                     for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                    // (QBAR sweeps hand the rays' exact q in rq as well: the candidate masks are as tight as ever)
                     const unsigned live = valid & ~done;
                     if (EXHAUSTIVE) {
                         // validation mode: strict-test every pair, count accepts the filter would have lost

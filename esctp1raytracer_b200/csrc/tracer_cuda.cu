@@ -40,7 +40,7 @@ int fail(int code, const std::string &msg) {
     do {                                                                                                    \
         cudaError_t e_ = (call);                                                                            \
         if (e_ != cudaSuccess)                                                                              \
-            return fail(TRACER_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+            return fail(TRACER_ERR_CUDA, std::string(#call) + " failed (tracer_cuda.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e_)); \
     } while (0)
 
 // Device-memory pool: the drop-in call (tracer_cuda_render) creates and destroys a resident scene per
@@ -138,6 +138,8 @@ struct tracer_scene_dev {
     float *accum_total = nullptr;
     // bundle-cull mode: candidate (ray<<32|triangle) buffers, their count, radix-sort scratch
     unsigned long long *cand_a = nullptr, *cand_b = nullptr, *cand_count = nullptr, *rkey = nullptr, *rkey_sorted = nullptr;
+    int *blk_cnt = nullptr;            // order-preserving compaction: survivors per (group, block of CBLK entries)
+    size_t blk_cnt_cap = 0;
     cull::BlockBoxes *boxes = nullptr; // two-phase bundle cull: boxes of every ray block
     size_t boxes_cap = 0;
     int *iota = nullptr;
@@ -197,23 +199,27 @@ int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     // rays of one thread share q unless the sample positions are jittered (extension)
     return p.bands.spp_n > 1 ? launch_primary_q<R, EX, false>(p, grid, st) : launch_primary_q<R, EX, true>(p, grid, st);
 }
-template <int R, bool EX>
-int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st) {
+template <int R, bool EX, bool QB>
+int launch_shadow_q(const trk::ShadowParams &p, int grid, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem<R>);
-    CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trk::shadow_kernel<R, EX><<<grid, sweep::THREADS, smem, st>>>(p);
+    CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trk::shadow_kernel<R, EX, QB><<<grid, sweep::THREADS, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
+}
+template <int R, bool EX>
+int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st, bool qbar) {
+    return qbar ? launch_shadow_q<R, EX, true>(p, grid, st) : launch_shadow_q<R, EX, false>(p, grid, st);
 }
 int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
     if (R == 4) return ex ? launch_primary_t<4, true>(p, grid, st) : launch_primary_t<4, false>(p, grid, st);
     return ex ? launch_primary_t<2, true>(p, grid, st) : launch_primary_t<2, false>(p, grid, st);
 }
-int launch_shadow(int R, bool ex, const trk::ShadowParams &p, int grid, cudaStream_t st) {
-    if (R == 8) return ex ? launch_shadow_t<8, true>(p, grid, st) : launch_shadow_t<8, false>(p, grid, st);
-    if (R == 4) return ex ? launch_shadow_t<4, true>(p, grid, st) : launch_shadow_t<4, false>(p, grid, st);
-    return ex ? launch_shadow_t<2, true>(p, grid, st) : launch_shadow_t<2, false>(p, grid, st);
+int launch_shadow(int R, bool ex, bool qbar, const trk::ShadowParams &p, int grid, cudaStream_t st) {
+    if (R == 8) return ex ? launch_shadow_t<8, true>(p, grid, st, qbar) : launch_shadow_t<8, false>(p, grid, st, qbar);
+    if (R == 4) return ex ? launch_shadow_t<4, true>(p, grid, st, qbar) : launch_shadow_t<4, false>(p, grid, st, qbar);
+    return ex ? launch_shadow_t<2, true>(p, grid, st, qbar) : launch_shadow_t<2, false>(p, grid, st, qbar);
 }
 
 // Work decomposition of a sweep: R rays per thread (8 preferred: best amortisation of the row loads) and
@@ -330,7 +336,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->seg_count), dev_free(s->seg_off), dev_free(s->blk_off), dev_free(s->cursor), dev_free(s->work);
     dev_free(s->n_slices);
     dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count), dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
-    dev_free(s->boxes);
+    dev_free(s->boxes), dev_free(s->blk_cnt);
     g_pool.release(s->sort_tmp), g_pool.release(s->pair_tmp);
     dev_free(s->counters);
     for (auto &e : s->ev)
@@ -375,7 +381,7 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
         cudaError_t e_ = (call);                                                                            \
         if (e_ != cudaSuccess) {                                                                            \
             tracer_cuda_scene_destroy(s);                                                                   \
-            return fail(TRACER_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+            return fail(TRACER_ERR_CUDA, std::string(#call) + " failed (tracer_cuda.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e_)); \
         }                                                                                                   \
     } while (0)
     TRY(dev_alloc(&s->tri_verts, (size_t)N * 9));
@@ -562,7 +568,13 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             s->cand_cap = cap;
         }
     }
-    if (cull && s->rkey_npx < n_px) { // shadow rays are ordered by (group, Morton code) with a radix sort of (key, pixel) pairs
+    // default mode: shadow rays ordered by (group, q) so that the rays of a thread can share a q-term (sweep::edge_sign_qbar)
+    static const bool qbar_env = [] {
+        const char *e = std::getenv("TRACER_SHADOW_QBAR");
+        return e ? std::atoi(e) != 0 : true; // development knob: 0 = pixel-ordered lists, one q per ray
+    }();
+    const bool qbar = !cull && qbar_env;
+    if ((cull || qbar) && s->rkey_npx < n_px) { // shadow rays are ordered by (group, Morton code) with a radix sort of (key, pixel) pairs
         dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
         g_pool.release(s->pair_tmp);
         s->pair_tmp = nullptr;
@@ -742,7 +754,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.rng_mode = o.rng_mode, lp.seed = seed_s, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
         lp.seg_count = s->seg_count, lp.counters = s->counters;
         lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
-        lp.cull_cells = cull ? 1 : 0, lp.rkey = s->rkey;
+        lp.cull_cells = cull ? 1 : (qbar ? 2 : 0), lp.rkey = s->rkey;
         if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
         CK_CUDA(cudaGetLastError());
@@ -813,8 +825,24 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         }
         trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
         CK_CUDA(cudaGetLastError());
-        trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
-        CK_CUDA(cudaGetLastError());
+        const int max_cblocks = (n_px + trk::CBLK - 1) / trk::CBLK + 1;
+        if (qbar) { // group-major, q-minor order (pixels without a shadow ray carry the all-ones key and sort last)
+            int group_bits = 1;
+            while ((1 << group_bits) < F) ++group_bits;
+            CK_CUDA(cub::DeviceRadixSort::SortPairs(s->pair_tmp, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0,
+                                                    32 + group_bits + 1, st));
+            CK_CUDA(cudaMemcpyAsync(s->cursor, s->seg_count, sizeof(int) * F, cudaMemcpyDeviceToDevice, st));
+            const size_t need = (size_t)max_cblocks * F;
+            if (need > s->blk_cnt_cap) {
+                dev_free(s->blk_cnt);
+                s->blk_cnt_cap = 0;
+                if (dev_alloc(&s->blk_cnt, need)) return TRACER_ERR_NOMEM;
+                s->blk_cnt_cap = need;
+            }
+        } else {
+            trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
+            CK_CUDA(cudaGetLastError());
+        }
         launches += 2;
         CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
@@ -840,7 +868,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
         const dim3 cgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
         bool live = true;
-        int Rk = 8;
+        int Rk = 8, max_live_group = 0; // longest group list at the last host look (lists only shrink)
         for (int c = 0; c < n_chunks; ++c) {
             // The host looks at the live-ray counts only at the first chunk (which face tables to build, ray
             // block size) and every 8th chunk (stop early); everything else is sized on the device, so
@@ -851,7 +879,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                     CK_CUDA(cudaStreamSynchronize(st));
                 }
                 int64_t n_live = 0;
-                for (int j = 0; j < F; ++j) n_live += h_cnt[j];
+                max_live_group = 0;
+                for (int j = 0; j < F; ++j) n_live += h_cnt[j], max_live_group = std::max(max_live_group, h_cnt[j]);
                 if (n_live == 0) { // every shadow ray of this light already has its occluder
                     live = false;
                     break;
@@ -871,8 +900,16 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
             sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, sp, g.n_sms, st)) return rc;
-            trk::compact_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, list_out, cnt_out);
+            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, qbar, sp, g.n_sms, st)) return rc;
+            if (qbar) { // order-preserving: the lists stay sorted by q
+                const dim3 bgrid((unsigned)std::max(1, (max_live_group + trk::CBLK - 1) / trk::CBLK), (unsigned)F);
+                trk::compact_count_kernel<<<bgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, s->blk_cnt, max_cblocks);
+                trk::compact_scatter_kernel<<<bgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, s->blk_cnt, max_cblocks,
+                                                                    list_out, cnt_out);
+                ++launches;
+            } else {
+                trk::compact_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, list_out, cnt_out);
+            }
             CK_CUDA(cudaGetLastError());
             launches += 3;
             std::swap(list_in, list_out), std::swap(cnt_in, cnt_out);
@@ -950,7 +987,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.strict_evals = (int64_t)hc.strict_evals;
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.kernel_launches = launches;
-    s->stats.flop_primary = flop_primary, s->stats.flop_shadow = cull ? 0.0 : 12.0;
+    // shadow sweeps: 6 FFMA per pair, or (6 + 3R) FFMA per R pairs when a thread's R = 8 rays share the q-terms
+    s->stats.flop_primary = flop_primary, s->stats.flop_shadow = cull ? 0.0 : (qbar ? 2.0 * (6 + 3 * 8) / 8 : 12.0);
     if (hc.cull_overflow)
         return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow; use the default mode for this scene");
     if (getenv("TRACER_CULL_DIAG"))

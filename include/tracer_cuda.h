@@ -143,7 +143,8 @@ typedef struct tracer_frame_stats {
     int32_t n_sms;
     double flop_primary;    /* FP32 flops the closest-hit sweep executes per swept pair: 2*(3+3R)/R when the R rays of a
                                thread share q (no jitter), else 12; 0 in bundle-cull mode                       */
-    double flop_shadow;     /* same for the any-hit sweeps: 12 (6 FFMA)                                         */
+    double flop_shadow;     /* same for the any-hit sweeps: 2*(6+3R)/R = 7.5 (R = 8 q-sorted rays of a thread share one
+                               q-term per edge row), 12 with TRACER_SHADOW_QBAR=0                              */
 } tracer_frame_stats;
 
 typedef struct tracer_device_info {

@@ -419,3 +419,25 @@ def test_bundle_cull_falls_back_to_streaming_when_keys_do_not_fit(renderer):
     finally:
         del os.environ["TRACER_L0_CAP"]
     _same_frames(a, b)
+
+
+def test_shadow_sweeps_with_shared_q_terms_never_miss(renderer, restated):
+    """Default-mode shadow sweeps order each (light vertex, face) list by q and evaluate the 8 consecutive rays of a
+    thread with one q-term per edge row (qbar + |B|*qdelta).  That must stay a necessary condition: exhaustive mode
+    strict-tests every pair and counts accepts the filter would have lost (0), frames equal the oracle, and the
+    order-preserving compaction is exercised with many chunks."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    for s, W, H, chunks in ((scenes.soup_scene(30000, 30, 4, seed=12, edge=(0.02, 0.25)), 160, 100, 24),
+                            (scenes.coplanar_scene(), 120, 90, 5),
+                            (scenes.soup_scene(9000, 9, 3, seed=4, with_normals=True, specular=True, n_spheres=11), 75, 49, 0)):
+        cam = Camera.for_frame((0, 1, 2.9), (0, 1, 0), W, H)
+        rs = renderer.upload(s)
+        a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=7, debug=True, shadow_chunks=chunks)
+        b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=7, debug=True, shadow_chunks=chunks, exhaustive_strict=True)
+        assert b.stats["filter_misses"] == 0
+        _same_frames(a, b)
+        o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=hash_faceids(7, W, H, s.faces_per_light))
+        has_pow = bool(s.geom_material[:, 6:9].any() or s.sphere_material[:, 6:9].any())
+        _check_frame(a, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), has_pow, occ=o.occ_tri)
+        assert a.stats["tests_shadow_ref"] == o.n_tests[1]

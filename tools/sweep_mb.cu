@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) k_prod(const float4 *table,
 #pragma unroll
         for (int r = 0; r < R; ++r) ex[r] = seed * (tid + 1) * (r + 1 + blk), ey[r] = seed * (tid + 7) * (r + 3);
         unsigned done = 0;
-        sweep::sweep_table<R, false, false>(sm, table, 0, n_tiles, n_tiles * 256, nullptr, sweep::RaySrc{}, ex, ey, 0xffu >> (8 - R), done, gtile,
+        sweep::sweep_table<R, false, false, false>(sm, table, 0, n_tiles, n_tiles * 256, nullptr, sweep::RaySrc{}, ex, ey, 0.f, 0.f, 0xffu >> (8 - R), done, gtile,
                                             n_strict, n_swept, n_miss);
         __syncthreads();
     }
