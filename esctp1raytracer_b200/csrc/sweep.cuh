@@ -3,7 +3,8 @@
 //
 // What the reference does per (ray, triangle) pair: full Moller-Trumbore with
 // a double-precision divide (ray_triangle.h:7-57, ~52 flop).  What this kernel
-// does per pair: 6 FFMA + 1.5 LOP3.  The saving comes from two
+// does per pair: at most 6 FFMA + 1.5 LOP3 (3.4-3.75 FFMA when the rays of a
+// thread share the q-term of each row, see 3.).  The saving comes from these
 // observations.
 //
 //  1. Every sweep is a bundle of rays through ONE common point.  Primary rays
@@ -36,12 +37,20 @@
 //     occluder in order` rule and all the chaotic self-shadow decisions come
 //     out bit-identical to the serial path.
 //
+//  3. The R rays of a thread can share the q-term B*q + C of every row.  Closest-hit
+//     ray blocks are screen tiles in which a thread holds R consecutive pixels of one
+//     image row: same q, the compiler merges the R identical inner FFMAs (kernels.cuh,
+//     primary_kernel SHAREDQ).  Shadow-ray lists are sorted by q, a thread takes R
+//     consecutive rays and uses qbar*B + |B|*qdelta + C with qdelta >= max|q_r - qbar|,
+//     which is >= every ray's own term, so the test stays a necessary condition
+//     (edge_sign_qbar; sweep_table QBAR).
+//
 // Mapping to the SM (choices measured with tools/sweep_mb.cu):
 //  * rows stream HBM/L2 -> shared memory in 12 KB tiles via TMA 1-D bulk copies
 //    (cp.async.bulk + mbarrier complete_tx, UBLKCP in SASS), STAGES deep;
 //  * every lane of every warp reads the SAME row at the same time, so the three
 //    LDS.128 per triangle are pure broadcasts, amortised over R rays per thread
-//    held in registers (R = 8: 48 FFMA per 3 loads);
+//    held in registers (R = 8: 27-48 FFMA per 3 loads);
 //  * "all three >= 0" is tested on the sign bits: (u'|v'|w') as integers (one LOP3),
 //    AND-ed over the R rays; FMNMX3 measured ~2 issue slots next to FFMA, LOP3 ~1.3;
 //  * the inner loop has NO per-triangle branch: the resulting sign bit is shifted
@@ -50,6 +59,9 @@
 //    the hot loop a straight FFMA/LOP3/LDS stream;
 //  * scalar FFMA, not packed fma.rn.f32x2: with honest operands the packed form
 //    measured no faster in this loop on B200;
+//  * closest-hit sweeps recycle a tile stage without a block-wide barrier (per-warp
+//    arrival count in shared memory, the last warp issues the refill); any-hit sweeps
+//    keep __syncthreads_and, which also carries the "every ray occluded" early exit;
 //  * 512 threads (16 warps, 4 per scheduler) per CTA, one CTA per SM.
 #pragma once
 #include <cstdint>
