@@ -217,7 +217,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from esctp1raytracer_b200 import RNG_HASH, Camera, Renderer
+    from esctp1raytracer_b200 import Camera, Renderer
     from esctp1raytracer_b200 import dist as tdist
 
     if not torch.cuda.is_available():

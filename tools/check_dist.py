@@ -7,7 +7,7 @@ streaming) through dist.render_frame on N ranks and compares every assembled fra
 GPU renders alone.  Expected output: 0 differing rows everywhere."""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from esctp1raytracer_b200 import RNG_HASH, Camera, Renderer, scenes
+from esctp1raytracer_b200 import Camera, Renderer, scenes
 from esctp1raytracer_b200 import dist as tdist
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
