@@ -4,7 +4,6 @@ import os
 import sys
 import time
 
-import numpy as np
 
 sys.path.insert(0, ".")
 from esctp1raytracer_b200 import RNG_HASH, Camera, Renderer, scenes
