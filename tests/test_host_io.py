@@ -83,3 +83,21 @@ def test_ppm_writer_matches_reference_format(tmp_path):
     assert p3.read_text() == want
     write_ppm(str(p6), img, binary=True)
     assert p6.read_bytes() == b"P6\n5 7\n255\n" + img.tobytes()
+
+
+def test_bench_model_workloads_load_the_reference_models():
+    """bench.py --workload c1|c3 run on the reference's own models: the flat scenes its loader produced, stored
+    with the golden frames (the OBJ files themselves stay in the reference tree)."""
+    import argparse
+    import importlib
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    a = argparse.Namespace(tris=0, width=0, height=0)
+    sc, W, H = bench.make_scene("c1", a)
+    assert (sc.n_tris, W, H, sc.n_lights) == (36, 1024, 768, 1) and bench.EYE == (0.0, 1.0, 2.0)
+    sc, W, H = bench.make_scene("c3", a)
+    assert (sc.n_tris, W, H, sc.n_lights) == (7088, 1920, 1080, 1) and sc.tri_normals is not None
+    assert "reference model" in bench.workload_config("c3", sc, W, H)["workload"]
