@@ -175,7 +175,7 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s (primary+shadow)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, scene, W, H), "cpu_baseline": c,
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
