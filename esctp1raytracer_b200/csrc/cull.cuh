@@ -220,7 +220,7 @@ __device__ __forceinline__ void sweep_cull_emit(EmitSmem &sm, const float4 *__re
                 unsigned mask = 0;                                                          // level 2: per-ray filter
                 ++d_l1;
 #pragma unroll
-                for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
+                for (int r = 0; r < R; ++r) mask |= (unsigned)sweep::edge_pass(rb, rc, rd, rp[r], rq[r]) << r;
                 mask &= valid;
                 if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
                 emit_pairs<R>(em, wc, mask, ray_id, (unsigned)((tile_lo + it) * CTILE + k));

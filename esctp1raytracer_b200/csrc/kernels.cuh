@@ -90,16 +90,34 @@ __device__ __forceinline__ f3 primary_dir(const Cam &c, const Bands &b, int w, i
 // Direction parametrisation of the ray group this table serves: d' = p*U + q*V + W with
 // |d'| <= dmax.  A 3-D row (vec, K) valid for unit directions becomes the affine 2-D row
 // (U.vec, V.vec, W.vec + K*dmax): d'.vec + K|d'| >= 0 is relaxed to d'.vec + K*dmax >= 0.
+//
+// SATURATING FORM.  The sweeps decide "all three rows >= 0" in the FMA pipe: each row value is
+// clamped to [0,1] by the FFMA itself (fma.sat) and the three are multiplied, so a pair is a
+// candidate iff the product is exactly 1.  For that every row carries a SECOND margin K2 (equal to the
+// first one, K*dmax, for edge rows) and is scaled by a power of two S with S * 0.9 * K2 >= 1: a pair the
+// reference could accept evaluates to >= 0 without K2, hence to >= K2 less a few ulps with it,
+// hence to >= 1 after the (exact, power-of-two) scaling — it saturates to exactly 1 on all three
+// rows.  Sign tests on the scaled rows (bundle-cull mode) remain valid: they are only looser.
 struct TableParam {
     double o[3], U[3], V[3], W[3], dmax, lmax;
 };
 
-__device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K) {
+// K: the margin for unit directions; K2u: the second margin (same units); returns the scaled float row
+__device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K, double K2u) {
     const double A = tp.U[0] * vx + tp.U[1] * vy + tp.U[2] * vz;
     const double B = tp.V[0] * vx + tp.V[1] * vy + tp.V[2] * vz;
-    const double C = tp.W[0] * vx + tp.W[1] * vy + tp.W[2] * vz + K * tp.dmax * 1.0001;
-    // + 0.0f: a stored -0 would make the sign-bit test treat an exact zero as negative
-    return make_float4((float)A, (float)B, (float)C + 0.0f, 0.f);
+    const double K1 = K2u * tp.dmax;
+    const double C = tp.W[0] * vx + tp.W[1] * vy + tp.W[2] * vz + K * tp.dmax * 1.0001 + K1; // first margin + K2
+    // S = 2^k >= 1 / (0.9 K2).  |row| / K2 is bounded by ~1/(8 eps) by construction, so the scaled row stays far inside
+    // the float range; should that ever fail (or K2 be 0) the row becomes "always candidate": the strict path decides.
+    const double mag = fmax(fabs(A), fmax(fabs(B), fabs(C)));
+    if (!(K1 > 0.0) || !(mag < 1e30)) return make_float4(0.f, 0.f, 1.f, 0.f);
+    const int k = (int)ceil(-log2(0.9 * K1));
+    if (k > 100 || k < -100 || k + (int)ceil(log2(mag)) > 100) return make_float4(0.f, 0.f, 1.f, 0.f);
+    // (float)x * 2^k is exact at these magnitudes, so the scaled row is the float row times S and its evaluation is
+    // S times the unscaled evaluation, bit for bit
+    const float Sf = (float)exp2((double)k);
+    return make_float4((float)A * Sf, (float)B * Sf, (float)C * Sf, 0.f);
 }
 
 __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tris, int n_pad, const TableParam tp,
@@ -150,8 +168,10 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
                 if (rho > 4.0 * delta) {
                     const double kappa = (h + delta) / (rho - delta) * 1.01 + 8.0 * eps;
                     if (kappa < 1.0) {
-                        rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37);
-                        rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37);
+                        // second margin: a fraction of the slab's own width, never below the evaluation noise of a unit row
+                        const double k2 = fmax(kappa / 8.0, 16.0 * eps);
+                        rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37, k2);
+                        rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37, k2);
                     }
                 }
             }
@@ -159,9 +179,9 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
             const double s = tprime > 0 ? 1.0 : -1.0;
             // round K up a little so the float row never under-states it
             const double Kd = K * 1.0000002 + 1e-37;
-            rb = project_row(tp, s * Bx, s * By, s * Bz, Kd);
-            rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd);
-            rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd);
+            rb = project_row(tp, s * Bx, s * By, s * Bz, Kd, Kd);
+            rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd, Kd);
+            rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd, Kd);
         }
         // rb.w (bundle-cull mode only): a lower bound of the distance from O to any point X of the triangle,
         // |X - O| >= |V - O| - |X - V| >= max(la, lb, lc) - emax, less a slack far above the float noise of the
@@ -206,20 +226,45 @@ struct PrimaryParams {
     int tx_log2;         // threads across a tile (the host picks the shape that wastes the fewest pixels at the frame's edges)
 };
 
+// The reference's own test for the rays (bits of mask) of one thread against triangle tri, eye rays
+// (cpp_intersect, main.cpp:176-192).  Every accepted pair is merged into the pixel's closest-hit key; the
+// lexicographic minimum of (t, index) over all accepted pairs is what the serial loop ends with (t2 >= t
+// rejects, ray_triangle.h:49, so among equal t the lowest index stays), whatever the order of evaluation.
+// k0: local pixel index of the thread's ray 0 (ray r = pixel k0 + r).  filt: rays the filter passed (validation).
+// Returns evaluations | filter misses << 16.
+__device__ __noinline__ unsigned strict_primary(const PrimaryParams &p, int k0, unsigned mask, int tri, unsigned filt) {
+    const float *q = p.tri_verts + 9 * (size_t)tri;
+    const f3 v0 = strict::mk(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+    const f3 v1 = strict::mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
+    const f3 v2 = strict::mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+    const f3 o = strict::ld(p.cam.o);
+    unsigned ret = 0;
+    while (mask) {
+        const int r = __ffs(mask) - 1;
+        mask &= mask - 1;
+        int w, h;
+        p.bands.map(k0 + r, w, h);
+        const f3 d = primary_dir(p.cam, p.bands, w, h);
+        float t = FLT_MAX, v = 0.f; // main.cpp:715-717
+        ++ret;
+        if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
+            atomicMin(&p.best[k0 + r], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri);
+            if (!((filt >> r) & 1u)) ret += 1u << 16;
+        }
+    }
+    return ret;
+}
+
 // Ray block = screen tile, each thread holding R horizontally consecutive pixels of ONE image row.  Without
 // jitter those R rays share the filter parameter q (SHAREDQ), so the inner term B*q + C of every edge function is
 // computed once per thread and triangle instead of once per ray: 3 + 3R FFMA per triangle instead of 6R (the
 // values — and therefore the filter's decisions — are bit-identical, the compiler merely sees one q).
 template <int R, bool EXHAUSTIVE, bool SHAREDQ>
-__global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const PrimaryParams p) {
+__global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const __grid_constant__ PrimaryParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1), sm.consumed[s] = 0;
-        sweep::fence_barrier_init();
-    }
-    __syncthreads();
+    sweep::smem_init(sm);
     unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0;
     unsigned long long tests = 0;
     const int n_items = p.n_blocks * p.n_slices;
@@ -235,44 +280,34 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) primary_kernel(const Primar
         const int W = p.bands.W;
         const int tile_y = blk / p.tiles_x, tile_x = blk - tile_y * p.tiles_x;
         const int txn = 1 << p.tx_log2;
-        const int x0 = (tile_x * txn + (tid & (txn - 1))) * R, ly = tile_y * (sweep::THREADS >> p.tx_log2) + (tid >> p.tx_log2);
+        const int x0 = (tile_x * txn + (tid & (txn - 1))) * R, ly = tile_y * (sweep::NT >> p.tx_log2) + (tid >> p.tx_log2);
         float rp[R], rq[R];
-        int kp[R];
         unsigned valid = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (x0 + r < W && ly < p.n_rows) valid |= 1u << r;
-            const int k = min(ly, p.n_rows - 1) * W + min(x0 + r, W - 1);
-            kp[r] = k;
             int w, h;
-            p.bands.map(k, w, h);
-            const f3 d = primary_dir(p.cam, p.bands, w, h);
+            p.bands.map(min(ly, p.n_rows - 1) * W + min(x0 + r, W - 1), w, h);
             // filter parameters: the ray's own (s,t) on the image plane (main.cpp:709-710)
             p.bands.pixel_st(w, h, rp[r], rq[r]);
-            sm.ox[r][tid] = p.cam.o[0], sm.oy[r][tid] = p.cam.o[1], sm.oz[r][tid] = p.cam.o[2];
-            sm.dx[r][tid] = d.x, sm.dy[r][tid] = d.y, sm.dz[r][tid] = d.z;
-            sm.t[r][tid] = FLT_MAX; // main.cpp:715-717
-            sm.v[r][tid] = 0.f;
-            sm.tri[r][tid] = -1;
         }
         if (SHAREDQ) { // same image row, no jitter: every rq[r] holds the same bits; say so to the compiler
             const float q0 = rq[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) rq[r] = q0;
         }
+        const int k0 = ly * W + x0; // valid rays are pixels k0 + r
         unsigned done = 0;
-        sweep::sweep_table<R, false, EXHAUSTIVE, false>(sm, p.table, tile_lo, tile_hi, p.n_tris, p.tri_verts, sweep::RaySrc{}, rp, rq,
-                                                        0.f, 0.f, valid, done, gtile, n_strict, n_swept, n_miss);
+        sweep::sweep_table<R, SHAREDQ ? sweep::MODE_SHAREDQ : sweep::MODE_OWNQ, false, EXHAUSTIVE>(
+            sm, p.table, tile_lo, tile_hi, p.n_tris, rp, rq, 0.f, 0.f, valid, done, gtile, n_swept,
+            [&](unsigned mask, int tri, unsigned filt) {
+                const unsigned c = strict_primary(p, k0, mask, tri, filt);
+                n_strict += c & 0xffffu, n_miss += c >> 16;
+                return 0u;
+            });
         const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (!((valid >> r) & 1u)) continue;
-            const float t = sm.t[r][tid];
-            const int tri = sm.tri[r][tid];
-            if (tri >= 0) atomicMin(&p.best[kp[r]], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)tri);
-        }
-        __syncthreads(); // slots are rewritten by the next item
+        __syncthreads(); // sm.blk is rewritten by the next item
     }
     atomicAdd(&p.counters->tests_primary, tests);
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
@@ -517,23 +552,6 @@ __global__ void list_prefix_kernel(const int *seg_count, int F, int *seg_off, in
     }
 }
 
-// after this kernel cursor[j] == number of rays in segment j: it doubles as the first chunk's count
-__global__ void list_scatter_kernel(const int *__restrict__ rj, int n_px, const int *__restrict__ seg_off, int *cursor,
-                                    int *__restrict__ list) {
-    const int kpx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = kpx < n_px ? rj[kpx] : -1;
-    const unsigned active = __ballot_sync(0xffffffffu, j >= 0);
-    if (j >= 0) {
-        const unsigned peers = __match_any_sync(active, j);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[j], __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
-        list[seg_off[j] + base + rank] = kpx;
-    }
-}
-
 // before each triangle chunk: live-ray counts per ray group -> ray-block offsets; reset the
 // survivors' counters and the work counter
 // The triangle-slice count of the chunk is chosen here, on the device, from the live block count (so the
@@ -579,64 +597,78 @@ struct ShadowParams {
     int *work;
 };
 
-// one (ray block, triangle slice) work item with RR rays per thread; the slot arrays are laid out for RS >= RR.
-// QBAR: the list is ordered by q inside each group (and compaction keeps it so); a thread then takes RR CONSECUTIVE
-// rays, whose q differ by ~1e-6, and evaluates them with one q-term per edge row (sweep::edge_sign_qbar).
-template <int RR, int RS, bool EXHAUSTIVE, bool QBAR>
-__device__ __forceinline__ void shadow_item(sweep::Smem<RS> &sm, const ShadowParams &p, int base, int seg_end, int lo, int hi,
+// The reference's own test for the rays (bits of mask) of one thread against triangle tri, shadow rays
+// (occlusion(), main.cpp:314-329): the first accepted face in order ends the ray and leaves t = t2 behind (the
+// multi-light carry).  Origin, direction and length stay in the pixel state and are fetched on demand: only a
+// few rays per work item ever get here.  Ray r of the thread is list entry min(e0 + r, e_last).
+// Returns newly occluded rays | evaluations << 8 | filter misses << 16.
+__device__ __noinline__ unsigned strict_shadow(const ShadowParams &p, int e0, int e_last, unsigned mask, int tri, unsigned filt) {
+    const float *q = p.tri_verts + 9 * (size_t)tri;
+    const f3 v0 = strict::mk(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+    const f3 v1 = strict::mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
+    const f3 v2 = strict::mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+    const size_t n = (size_t)p.n_px;
+    unsigned ret = 0;
+    while (mask) {
+        const int r = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int k = p.list_in[min(e0 + r, e_last)];
+        const f3 o = strict::mk(p.px.ro[k], p.px.ro[n + k], p.px.ro[2 * n + k]);
+        const f3 d = strict::mk(p.px.rd[k], p.px.rd[n + k], p.px.rd[2 * n + k]);
+        float t = p.px.rt[k], v = 0.f; // the ray has no occluder yet, so t is its initial length (main.cpp:764)
+        ret += 1u << 8;
+        if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
+            atomicMin(&p.px.best_occ[k], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(t));
+            ret |= 1u << r;
+            if (!((filt >> r) & 1u)) ret += 1u << 16;
+        }
+    }
+    return ret;
+}
+
+// one (ray block, triangle slice) work item with RR rays per thread.  The list is ordered by q inside each group
+// (and compaction keeps it so); a thread takes RR CONSECUTIVE rays, whose q differ by ~1e-6, and evaluates them
+// with one q-term per edge row (sweep::MODE_QBAR).
+template <int RR, bool EXHAUSTIVE>
+__device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowParams &p, int base, int seg_end, int lo, int hi,
                                             const float4 *__restrict__ tab, unsigned &gtile, unsigned &n_strict, unsigned &n_miss,
                                             unsigned long long &tests) {
-    static_assert(RR <= RS, "slot layout too small");
     const int tid = threadIdx.x, n = p.n_px;
     float rp[RR], rq[RR];
-    int kp[RR];
     unsigned valid = 0, done = 0;
+    const int e0 = base + tid * RR;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
-        int e = QBAR ? base + tid * RR + r : base + r * sweep::THREADS + tid;
-        if (e < seg_end) valid |= 1u << r;
-        e = min(e, seg_end - 1);
-        const int k = p.list_in[e];
-        kp[r] = k;
+        if (e0 + r < seg_end) valid |= 1u << r;
+        const int k = p.list_in[min(e0 + r, seg_end - 1)];
         rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
-        // origin, direction and length stay in the pixel state: the strict path fetches them on demand
-        // through the pixel index parked in the tri slot (sweep::RaySrc)
-        sm.tri[r][tid] = -2 - k;
         // an earlier slice may already have published an occluder below this slice: nothing to do
         const unsigned long long seen = p.px.best_occ[k];
         if (seen != KEY_NONE && (int)(unsigned)(seen >> 32) < lo * sweep::TILE) done |= 1u << r;
     }
-    float qbar = 0.f, qdelta = 0.f;
-    if (QBAR) { // rays past the end of the list are duplicates of the last one, so all RR values count
-        float qmin = rq[0], qmax = rq[0];
+    // rays past the end of the list are duplicates of the last one, so all RR values count
+    float qmin = rq[0], qmax = rq[0];
 #pragma unroll
-        for (int r = 1; r < RR; ++r) qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
-        qbar = 0.5f * (qmin + qmax);
-        // >= max |q_r - qbar| with room for the roundings of this line and of the one extra FFMA per row
-        qdelta = fmaxf(qmax - qbar, qbar - qmin) * 1.0001f + 2.4e-7f * (fabsf(qbar) + 1.f);
-    }
+    for (int r = 1; r < RR; ++r) qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+    const float qbar = 0.5f * (qmin + qmax);
+    // >= max |q_r - qbar| with room for the roundings of this line and of the one extra FFMA per row
+    const float qdelta = fmaxf(qmax - qbar, qbar - qmin) * 1.0001f + 2.4e-7f * (fabsf(qbar) + 1.f);
     unsigned swept = 0;
-    sweep::sweep_table<RR, true, EXHAUSTIVE, QBAR>(sm, tab, lo, hi, p.n_tris, p.tri_verts, sweep::RaySrc{p.px.ro, p.px.rd, p.px.rt, n},
-                                                   rp, rq, qbar, qdelta, valid, done, gtile, n_strict, swept, n_miss);
+    sweep::sweep_table<RR, sweep::MODE_QBAR, true, EXHAUSTIVE>(sm, tab, lo, hi, p.n_tris, rp, rq, qbar, qdelta, valid, done, gtile, swept,
+                                                              [&](unsigned mask, int tri, unsigned filt) {
+                                                                  const unsigned c = strict_shadow(p, e0, seg_end - 1, mask, tri, filt);
+                                                                  n_strict += (c >> 8) & 0xffu, n_miss += c >> 16;
+                                                                  return c & 0xffu;
+                                                              });
     tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
-#pragma unroll
-    for (int r = 0; r < RR; ++r) {
-        const int tri = sm.tri[r][tid];
-        if (((valid >> r) & 1u) && tri >= 0) // occlusion() leaves t = t2 behind (main.cpp:320-324): the multi-light carry
-            atomicMin(&p.px.best_occ[kp[r]], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(sm.t[r][tid]));
-    }
 }
 
-template <int R, bool EXHAUSTIVE, bool QBAR>
-__global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowParams p) {
+template <int R, bool EXHAUSTIVE>
+__global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_kernel(const __grid_constant__ ShadowParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem<R> &sm = *reinterpret_cast<sweep::Smem<R> *>(smem_raw);
+    sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        for (int s = 0; s < sweep::STAGES; ++s) sweep::mbar_init(&sm.full_bar[s], 1);
-        sweep::fence_barrier_init();
-    }
-    __syncthreads();
+    sweep::smem_init(sm);
     const int total_blocks = p.blk_off[p.F];
     const int n_slices = *p.n_slices;
     const int n_items = total_blocks * n_slices;
@@ -653,66 +685,40 @@ __global__ void __launch_bounds__(sweep::THREADS, 1) shadow_kernel(const ShadowP
             }
             sm.blk = it < n_items ? b : -1;
             sm.seg = j;
-            sm.base_out = sl;
+            sm.slice = sl;
         }
         __syncthreads();
-        const int blk = sm.blk, j = sm.seg, slice = sm.base_out;
+        const int blk = sm.blk, j = sm.seg, slice = sm.slice;
         if (blk < 0) break;
         const int lo = p.tile_lo + (int)((long long)n_tiles * slice / n_slices);
         const int hi = p.tile_lo + (int)((long long)n_tiles * (slice + 1) / n_slices);
         const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
-        const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::THREADS * R);
+        const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::NT * R);
         const int face = j % NFACE;
         const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-        // The last block of a ray group is rarely full.  Rays sit at base + r*THREADS + tid, so a block with at most
-        // THREADS*RR rays only has rays r < RR: sweep it with RR rays per thread instead of dragging empty lanes
-        // through every triangle (late chunks have few rays in many groups: this padding is a fixed cost per frame).
+        // The last block of a ray group is rarely full.  A block with at most NT*RR rays is swept with RR rays per
+        // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups:
+        // this padding is a fixed cost per frame).
         const int cnt = seg_end - base;
         bool swept_it = false;
         if constexpr (R >= 8) {
-            if (cnt > 4 * sweep::THREADS) {
-                shadow_item<8, R, EXHAUSTIVE, QBAR>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+            if (cnt > 4 * sweep::NT) {
+                shadow_item<8, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
                 swept_it = true;
             }
         }
         if constexpr (R >= 4) {
-            if (!swept_it && cnt > 2 * sweep::THREADS) {
-                shadow_item<4, R, EXHAUSTIVE, QBAR>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+            if (!swept_it && cnt > 2 * sweep::NT) {
+                shadow_item<4, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
                 swept_it = true;
             }
         }
-        if (!swept_it) shadow_item<2, R, EXHAUSTIVE, QBAR>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+        if (!swept_it) shadow_item<2, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
         __syncthreads();
     }
     atomicAdd(&p.counters->tests_shadow, tests);
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
     if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
-}
-
-// after a chunk: rays without an occluder yet go to the next chunk's list (same segment)
-__global__ void compact_kernel(const int *__restrict__ list_in, const int *__restrict__ seg_off, const int *__restrict__ cnt_in,
-                               int F, const unsigned long long *__restrict__ best_occ, int *__restrict__ list_out,
-                               int *cnt_out) {
-    // grid.y = ray group; grid.x strides over the group's entries
-    const int j = blockIdx.y;
-    if (j >= F) return;
-    const int begin = seg_off[j], count = cnt_in[j];
-    for (int i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        int k = -1;
-        if (i < count) {
-            k = list_in[begin + i];
-            if (best_occ[k] != KEY_NONE) k = -1;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
-        if (m) {
-            int base = 0;
-            const int leader = __ffs(m) - 1;
-            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cnt_out[j], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (k >= 0) list_out[begin + base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = k;
-        }
-    }
 }
 
 // ORDER-PRESERVING compaction (QBAR sweeps keep each group's list sorted by q): pass 1 counts the survivors of
@@ -1167,7 +1173,7 @@ __device__ __forceinline__ void cull2_body(const Bundles &bd, const BlockLists b
                 if (!(cull::box_sign(rb, rc, rd, lane_box) >> 31)) { // the box of this lane's own R rays
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        mask |= (((sweep::edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) & (unsigned)(rb.w <= rl[r])) << r;
+                        mask |= ((unsigned)sweep::edge_pass(rb, rc, rd, rp[r], rq[r]) & (unsigned)(rb.w <= rl[r])) << r;
                     mask &= valid;
                 }
                 if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;

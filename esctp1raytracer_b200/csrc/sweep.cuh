@@ -33,50 +33,72 @@
 //     float/double evaluation (see build_origin_table), so a pair the
 //     reference would accept is never filtered out.  Pairs that pass (a few
 //     per ray out of N) are re-evaluated in the reference's exact arithmetic
-//     (strict_math.cuh) in index order, so closest-hit ties, the `first
-//     occluder in order` rule and all the chaotic self-shadow decisions come
-//     out bit-identical to the serial path.
+//     (strict_math.cuh), so closest-hit ties, the `first occluder in order`
+//     rule and all the chaotic self-shadow decisions come out bit-identical
+//     to the serial path.  The strict results are MERGED IN GLOBAL MEMORY with
+//     one 64-bit atomicMin per accepted pair:
+//        closest hit  key = t bits << 32 | index   (cpp_intersect keeps the lexicographic
+//                                                   minimum of (t, index): t2 >= t rejects)
+//        occluder     key = index << 32  | t2 bits (occlusion() returns the lowest index)
+//     so the sweep keeps NO per-ray state in shared memory: a CTA's shared
+//     memory is the table-tile pipeline only (48 KB), and two 512-thread CTAs
+//     (32 warps) fit on an SM.
 //
 //  3. The R rays of a thread can share the q-term B*q + C of every row.  Closest-hit
 //     ray blocks are screen tiles in which a thread holds R consecutive pixels of one
-//     image row: same q, the compiler merges the R identical inner FFMAs (kernels.cuh,
-//     primary_kernel SHAREDQ).  Shadow-ray lists are sorted by q, a thread takes R
-//     consecutive rays and uses qbar*B + |B|*qdelta + C with qdelta >= max|q_r - qbar|,
-//     which is >= every ray's own term, so the test stays a necessary condition
-//     (edge_sign_qbar; sweep_table QBAR).
+//     image row: same q, the compiler merges the R identical inner FFMAs (MODE_SHAREDQ).
+//     Shadow-ray lists are sorted by q, a thread takes R consecutive rays and uses
+//     qbar*B + |B|*qdelta + C with qdelta >= max|q_r - qbar|, which is >= every ray's own
+//     term, so the test stays a necessary condition (MODE_QBAR).
 //
-// Mapping to the SM (choices measured with tools/sweep_mb.cu):
+// Mapping to the SM (choices measured with tools/sweep_mb2.cu):
 //  * rows stream HBM/L2 -> shared memory in 12 KB tiles via TMA 1-D bulk copies
 //    (cp.async.bulk + mbarrier complete_tx, UBLKCP in SASS), STAGES deep;
 //  * every lane of every warp reads the SAME row at the same time, so the three
 //    LDS.128 per triangle are pure broadcasts, amortised over R rays per thread
-//    held in registers (R = 8: 27-48 FFMA per 3 loads);
-//  * "all three >= 0" is tested on the sign bits: (u'|v'|w') as integers (one LOP3),
-//    AND-ed over the R rays; FMNMX3 measured ~2 issue slots next to FFMA, LOP3 ~1.3;
-//  * the inner loop has NO per-triangle branch: the resulting sign bit is shifted
-//    into a bit register and tested once per batch of BATCH triangles; candidates
-//    (a few per ray per sweep) are then re-evaluated in index order.  This keeps
-//    the hot loop a straight FFMA/LOP3/LDS stream;
-//  * scalar FFMA, not packed fma.rn.f32x2: with honest operands the packed form
-//    measured no faster in this loop on B200;
-//  * closest-hit sweeps recycle a tile stage without a block-wide barrier (per-warp
-//    arrival count in shared memory, the last warp issues the refill); any-hit sweeps
-//    keep __syncthreads_and, which also carries the "every ray occluded" early exit;
-//  * 512 threads (16 warps, 4 per scheduler) per CTA, one CTA per SM.
+//    held in registers (R = 8: 27-30 FFMA per 3 loads);
+//  * "all three >= 0" is decided IN THE FMA PIPE: rows are pre-scaled so that a pair the
+//    reference could accept saturates to exactly 1 on each row (fma.sat is free), the three
+//    are multiplied and accumulated: 3 FFMA.SAT + FMUL + FFMA per pair, no integer op.  The
+//    round-1 form (sign bits through LOP3 on the half-rate ALU pipe) measured 63 issue cycles
+//    per warp and triangle (8 rays per thread) against 59 for this one, and its FMA pipe was
+//    idle 55 % of the time; this loop runs at ~0.78 FMA-pipe instructions per cycle and
+//    scheduler, the scalar-FFMA issue ceiling of the part (own microbenchmark: 0.745);
+//  * the inner loop has NO per-triangle branch: an accumulator group of 4 triangles is
+//    tested once; candidates (a few per ray per sweep) are then re-evaluated one by one;
+//  * NO block-wide barrier per tile in either sweep: every warp counts itself out of a
+//    tile stage (shared-memory atomicAdd) and the last one issues the refill, so warps
+//    run up to STAGES-1 tiles apart.  An any-hit warp whose rays all have their occluder
+//    stops evaluating (it only keeps the stage counts going);
+//  * SWEEP_NT threads per CTA, SWEEP_MINB CTAs per SM (launch bounds cap the registers).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "strict_math.cuh"
 
+#ifndef SWEEP_NT
+#define SWEEP_NT 256
+#endif
+#ifndef SWEEP_MINB
+#define SWEEP_MINB 3
+#endif
+#ifndef SWEEP_STAGES
+#define SWEEP_STAGES 4
+#endif
+
 namespace sweep {
 
 constexpr int TILE = 256;          // triangles per shared-memory stage (48-byte rows: 12 KB)
 constexpr int BATCH = 16;          // triangles between candidate checks
-constexpr int STAGES = 4;          // TMA pipeline depth
-constexpr int THREADS = 512;       // threads per CTA
+constexpr int STAGES = SWEEP_STAGES; // TMA pipeline depth
+constexpr int THREADS = 512;       // threads per CTA of the bundle-cull kernels (cull.cuh)
+constexpr int NT = SWEEP_NT;       // threads per CTA of the default sweeps
+constexpr int MINB = SWEEP_MINB;   // CTAs per SM of the default sweeps
 constexpr float CK = 64.f;         // safety factor of the filter margins (units of FLT_EPSILON)
 constexpr uint32_t TILE_BYTES = TILE * 3 * sizeof(float4);
+
+enum { MODE_OWNQ = 0, MODE_SHAREDQ = 1, MODE_QBAR = 2 };
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+; sm_100a here) -------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,28 +136,12 @@ __device__ __forceinline__ float4 lds128_opaque(const float4 *p) {
     return v;
 }
 
-// ---- shared memory of one sweep CTA -------------------------------------------
-template <int R>
+// ---- shared memory of one sweep CTA: the table-tile pipeline and nothing else -------------------
 struct __align__(128) Smem {
     float4 tile[STAGES][TILE * 3];
-    // per-ray state touched only on the (rare) strict path; SoA over threads => conflict-free
-    float ox[R][THREADS], oy[R][THREADS], oz[R][THREADS];
-    float dx[R][THREADS], dy[R][THREADS], dz[R][THREADS];
-    float t[R][THREADS], v[R][THREADS];
-    int tri[R][THREADS];
     uint64_t full_bar[STAGES];
-    int blk, seg, scan[THREADS / 32], base_out;
-    int consumed[STAGES]; // closest-hit sweeps: warps that have finished the tile in this stage
-};
-
-// Where the strict path finds a ray.  Closest-hit sweeps compute their rays in the item prologue and keep them
-// in the shared-memory slots (src.ro == nullptr).  Any-hit sweeps would have to GATHER origin, direction and
-// length of 512*R rays per work item although only a few rays per item ever reach the strict path, so they
-// leave them in the pixel state and the strict path fetches them on demand through the pixel index, which is
-// parked in the (otherwise unused) tri slot as -2 - k until the ray finds its occluder.
-struct RaySrc {
-    const float *ro, *rd, *rt; // [3][n], [3][n], [n]
-    int n;
+    int consumed[STAGES]; // warps that have finished the tile in this stage
+    int blk, seg, slice;  // the work item the CTA is on
 };
 
 struct Counters {
@@ -144,8 +150,25 @@ struct Counters {
     unsigned long long cull_overflow; // bundle-cull: a candidate buffer was too small (the frame is rejected)
 };
 
-// One 48-byte row triple per triangle: rb = (A,B,C,-) of s*u', rc of s*v', rd of s*w'.
-// Sign word of the three edge functions at the ray parameters (p,q): sign bit clear <=> all three >= 0.
+__device__ __forceinline__ void smem_init(Smem &sm) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full_bar[s], 1), sm.consumed[s] = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+}
+
+// One 48-byte row triple per triangle: rb = (A,B,C,-) of s*u', rc of s*v', rd of s*w', in SATURATING FORM
+// (kernels.cuh, build_origin_table): a pair the reference could accept evaluates to >= 1 on all three rows.
+// Per-ray test used by the (rare) candidate path: bit clear = some row < 1.
+__device__ __forceinline__ bool edge_pass(const float4 rb, const float4 rc, const float4 rd, float p, float q) {
+    const float x = fmaf(p, rb.x, fmaf(q, rb.y, rb.z));
+    const float y = fmaf(p, rc.x, fmaf(q, rc.y, rc.z));
+    const float z = fmaf(p, rd.x, fmaf(q, rd.y, rd.z));
+    return fminf(fminf(x, y), z) >= 1.f;
+}
+// Sign word of the three edge functions at the ray parameters (p,q): sign bit clear <=> all three >= 0 (bundle-cull
+// mode and the LOP3 form of the hot loop; only looser than the saturating test on the same rows).
 __device__ __forceinline__ unsigned edge_sign(const float4 rb, const float4 rc, const float4 rd, float p, float q) {
     const float x = fmaf(p, rb.x, fmaf(q, rb.y, rb.z));
     const float y = fmaf(p, rc.x, fmaf(q, rc.y, rc.z));
@@ -157,130 +180,147 @@ __device__ __forceinline__ unsigned edge_sign(const float4 rb, const float4 rc, 
 // qdelta >= max |q_r - qbar| the row value p*A + (qbar*B + |B|*qdelta + C) is >= the ray's own p*A + q_r*B + C, so
 // the test stays a necessary condition while the inner term costs 2 FFMA per thread instead of 1 per ray
 // (shadow rays sorted by q: qdelta ~ 1e-6, far inside the margin K already in C).
-__device__ __forceinline__ unsigned edge_sign_qbar(const float4 rb, const float4 rc, const float4 rd, float p, float qbar, float qdelta) {
-    const float x = fmaf(p, rb.x, fmaf(fabsf(rb.y), qdelta, fmaf(qbar, rb.y, rb.z)));
-    const float y = fmaf(p, rc.x, fmaf(fabsf(rc.y), qdelta, fmaf(qbar, rc.y, rc.z)));
-    const float z = fmaf(p, rd.x, fmaf(fabsf(rd.y), qdelta, fmaf(qbar, rd.y, rd.z)));
-    return __float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z);
+__device__ __forceinline__ float qterm_qbar(const float4 row, float qbar, float qdelta) {
+    return fmaf(fabsf(row.y), qdelta, fmaf(qbar, row.y, row.z));
 }
 
-// ---- strict path: the reference's own test on the surviving pairs ---------------
-// mask: rays (bit r) that are candidates for triangle tri.
-// CLOSEST: cpp_intersect semantics (main.cpp:176-192) — keep going, lower index wins ties.
-// ANYHIT : occlusion() semantics (main.cpp:314-329) — the first accepted face in order ends
-//          the ray; it leaves t = t2 behind (the multi-light carry).  Returns newly-done rays.
-template <int R, bool ANYHIT, int RS> // RS: rays per thread the slot arrays are laid out for (>= R)
-__device__ __noinline__ unsigned strict_tri(Smem<RS> &sm, int tid, unsigned mask, int tri,
-                                            const float *__restrict__ tri_verts, const RaySrc src, unsigned &n_strict) {
-    unsigned newly = 0;
-    const float *p = tri_verts + 9 * (size_t)tri;
-    const strict::f3 v0 = strict::mk(__ldg(p), __ldg(p + 1), __ldg(p + 2));
-    const strict::f3 v1 = strict::mk(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5));
-    const strict::f3 v2 = strict::mk(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8));
-    while (mask) {
-        const int r = __ffs(mask) - 1;
-        mask &= mask - 1;
-        strict::f3 o, d;
-        float t, v;
-        if (ANYHIT && src.ro) { // on demand from the pixel state; the ray has no occluder yet, so t is its initial length
-            const int k = -2 - sm.tri[r][tid];
-            o = strict::mk(src.ro[k], src.ro[src.n + k], src.ro[2 * (size_t)src.n + k]);
-            d = strict::mk(src.rd[k], src.rd[src.n + k], src.rd[2 * (size_t)src.n + k]);
-            t = src.rt[k], v = 0.f;
-        } else {
-            o = strict::mk(sm.ox[r][tid], sm.oy[r][tid], sm.oz[r][tid]);
-            d = strict::mk(sm.dx[r][tid], sm.dy[r][tid], sm.dz[r][tid]);
-            t = sm.t[r][tid], v = sm.v[r][tid];
+// ---- the hot loop: BATCH triangles of a staged tile against the R rays of this thread ---------------
+// Everything runs in the FMA pipe (measured on B200, tools/sweep_mb3.cu: a scalar FMA-pipe instruction costs ~1.3
+// issue cycles, a LOP3/SHF/FMNMX on the half-rate ALU pipe ~2, and the two do not overlap in this loop):
+//   x' = sat(p*A_u + q_u)   y' = sat(p*A_v + q_v)   z' = sat(p*A_w + q_w)      3 FFMA.SAT per pair
+//   acc += (x' * y') * z'                                                        1 FMUL + 1 FFMA per pair
+// A candidate pair contributes exactly 1, any other pair something in [0,1), so after GROUP triangles
+// "sum of the accumulators >= 1" is a necessary condition for the group to hold a candidate.  Straight-line FFMA /
+// FMUL / LDS.128 stream, no branch per triangle.  Returns bit g set = triangles [g*GROUP, (g+1)*GROUP) may hold one.
+constexpr int GROUP = 4; // triangles per accumulator group
+constexpr int NACC = 4;  // independent accumulators (dependent FFMA chains) per group
+
+template <int R, int MODE>
+__device__ __forceinline__ unsigned eval_batch(const float4 *__restrict__ tp, const float (&rp)[R], const float (&rq)[R], float qbar,
+                                               float qdelta) {
+    constexpr int NA = R < NACC ? R : NACC;
+    unsigned cand = 0;
+#pragma unroll
+    for (int g = 0; g < BATCH / GROUP; ++g) {
+        float acc[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) acc[a] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < GROUP; ++kk) {
+            const int k = g * GROUP + kk;
+            const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
+            if (MODE == MODE_OWNQ) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float x = __saturatef(fmaf(rp[r], rb.x, fmaf(rq[r], rb.y, rb.z)));
+                    const float y = __saturatef(fmaf(rp[r], rc.x, fmaf(rq[r], rc.y, rc.z)));
+                    const float z = __saturatef(fmaf(rp[r], rd.x, fmaf(rq[r], rd.y, rd.z)));
+                    acc[r % NA] = fmaf(__fmul_rn(x, y), z, acc[r % NA]);
+                }
+            } else {
+                const float qx = MODE == MODE_QBAR ? qterm_qbar(rb, qbar, qdelta) : fmaf(rq[0], rb.y, rb.z);
+                const float qy = MODE == MODE_QBAR ? qterm_qbar(rc, qbar, qdelta) : fmaf(rq[0], rc.y, rc.z);
+                const float qz = MODE == MODE_QBAR ? qterm_qbar(rd, qbar, qdelta) : fmaf(rq[0], rd.y, rd.z);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float x = __saturatef(fmaf(rp[r], rb.x, qx));
+                    const float y = __saturatef(fmaf(rp[r], rc.x, qy));
+                    const float z = __saturatef(fmaf(rp[r], rd.x, qz));
+                    acc[r % NA] = fmaf(__fmul_rn(x, y), z, acc[r % NA]);
+                }
+            }
         }
-        ++n_strict;
-        if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
-            sm.t[r][tid] = t;
-            sm.v[r][tid] = v;
-            sm.tri[r][tid] = tri;
-            if (ANYHIT) newly |= 1u << r;
-        }
+        float sum = acc[0];
+#pragma unroll
+        for (int a = 1; a < NA; ++a) sum += acc[a];
+        if (sum >= 1.f) cand |= 1u << g;
     }
-    return newly;
+    return cand;
+}
+
+// The LOP3 form of the same loop (round 1; kept for tools/sweep_mb3.cu): sign bits OR-ed per ray, AND-ed over rays,
+// shifted into a bit register.  Returns bit (BATCH-1-k) CLEAR = some ray of this thread may hit triangle k.
+template <int R, int MODE, int UNROLL>
+__device__ __forceinline__ unsigned eval_batch_lop3(const float4 *__restrict__ tp, const float (&rp)[R], const float (&rq)[R], float qbar,
+                                                    float qdelta) {
+    unsigned neg = 0xffffffffu;
+#pragma unroll UNROLL
+    for (int k = 0; k < BATCH; ++k) {
+        const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
+        unsigned A = 0xffffffffu;
+        if (MODE == MODE_OWNQ) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) A &= edge_sign(rb, rc, rd, rp[r], rq[r]);
+        } else {
+            const float qx = MODE == MODE_QBAR ? qterm_qbar(rb, qbar, qdelta) : fmaf(rq[0], rb.y, rb.z);
+            const float qy = MODE == MODE_QBAR ? qterm_qbar(rc, qbar, qdelta) : fmaf(rq[0], rc.y, rc.z);
+            const float qz = MODE == MODE_QBAR ? qterm_qbar(rd, qbar, qdelta) : fmaf(rq[0], rd.y, rd.z);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                A &= __float_as_uint(fmaf(rp[r], rb.x, qx)) | __float_as_uint(fmaf(rp[r], rc.x, qy)) |
+                     __float_as_uint(fmaf(rp[r], rd.x, qz));
+        }
+        neg = __funnelshift_l(A, neg, 1);
+    }
+    return neg;
 }
 
 // ---- the sweep over tiles [tile_lo, tile_hi) of one origin table, for the R rays of each thread ---
-// rp/rq: the rays' parameters in the table's direction parametrisation
+// rp/rq: the rays' parameters in the table's direction parametrisation (rq exact also in MODE_QBAR: the candidate
+//        masks handed to the strict path are as tight as ever)
 // valid: bit r set = ray r exists; done: bit r set = ray r needs no more tests
-// gtile: running tile counter of this CTA (mbarrier phase bookkeeping across ray blocks)
-template <int R, bool ANYHIT, bool EXHAUSTIVE, bool QBAR, int RS>
-__device__ __forceinline__ void sweep_table(Smem<RS> &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi,
-                                            int n_tris, const float *__restrict__ tri_verts, const RaySrc rsrc, const float (&rp)[R],
-                                            const float (&rq)[R], float qbar, float qdelta, unsigned valid, unsigned &done,
-                                            unsigned &gtile, unsigned &n_strict, unsigned &n_tiles_swept, unsigned &n_miss) {
+// gtile: running tile counter of this CTA (mbarrier phase bookkeeping across work items)
+// strict(mask, tri, filt) -> newly done rays: the reference's own test on the surviving pairs (kernels.cuh);
+//        mask = rays to test, filt = rays the filter passed (differs from mask only in EXHAUSTIVE validation mode)
+template <int R, int MODE, bool ANYHIT, bool EXHAUSTIVE, class Strict>
+__device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi, int n_tris,
+                                            const float (&rp)[R], const float (&rq)[R], float qbar, float qdelta, unsigned valid,
+                                            unsigned &done, unsigned &gtile, unsigned &n_tiles_swept, Strict &&strict) {
     const int tid = threadIdx.x;
     const int n_tiles = tile_hi - tile_lo;
     const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
-    int last_issued = (n_tiles < STAGES ? n_tiles : STAGES) - 1;
     if (tid == 0) {
-        for (int i = 0; i <= last_issued; ++i) {
+        const int first = n_tiles < STAGES ? n_tiles : STAGES;
+        for (int i = 0; i < first; ++i) {
             const unsigned g = gtile + i;
             mbar_expect_tx(&sm.full_bar[g % STAGES], TILE_BYTES);
             tma_load_1d(sm.tile[g % STAGES], src + (size_t)i * TILE * 3, TILE_BYTES, &sm.full_bar[g % STAGES]);
         }
     }
-    bool stop = false;
-    int it = 0;
-    for (; it < n_tiles; ++it) {
+    for (int it = 0; it < n_tiles; ++it) {
         const unsigned g = gtile + it;
         const int s = g % STAGES;
         mbar_wait(&sm.full_bar[s], (g / STAGES) & 1u);
-        if (!stop) {
+        // any-hit: a warp whose rays all have their occluder has nothing left to evaluate
+        const bool idle = ANYHIT && __all_sync(0xffffffffu, (done | ~valid) == 0xffffffffu);
+        if (!idle) {
             ++n_tiles_swept;
             const float4 *__restrict__ tp = sm.tile[s];
 #pragma unroll 1
             for (int b0 = 0; b0 < TILE; b0 += BATCH) {
-                // hot loop: straight-line, no branch per triangle.  neg collects, per triangle, the AND
-                // over rays of sign(u'|v'|w'): 0 = some ray may hit that triangle.
-                unsigned neg = 0xffffffffu;
-#pragma unroll 4
-                for (int k = 0; k < BATCH; ++k) {
-                    const float4 rb = tp[3 * (b0 + k)], rc = tp[3 * (b0 + k) + 1], rd = tp[3 * (b0 + k) + 2];
-                    unsigned A = 0xffffffffu;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        A &= QBAR ? edge_sign_qbar(rb, rc, rd, rp[r], qbar, qdelta) : edge_sign(rb, rc, rd, rp[r], rq[r]);
-                    neg = __funnelshift_l(A, neg, 1);
-                }
-#ifdef SWEEP_NO_STRICT // development microbenchmark only (tools/sweep_mb.cu): timing without the strict path
-                if (~neg & 0xffffu) ++n_strict;
+                unsigned cand = eval_batch<R, MODE>(tp + 3 * b0, rp, rq, qbar, qdelta);
+#ifdef SWEEP_NO_STRICT // development microbenchmark only (tools/sweep_mb2.cu): timing without the strict path
+                if (cand) ++done;
 #else
-                unsigned cand = EXHAUSTIVE ? 0xffffu : (~neg & 0xffffu); // bit (BATCH-1-k) = triangle b0+k
+                if (EXHAUSTIVE) cand = (1u << (BATCH / GROUP)) - 1u;
                 while (cand) {
-                    // rare: rebuild the per-ray candidate mask of this triangle, then the reference's own
-                    // arithmetic.  The row is re-read through an opaque load so that the compiler cannot
-                    // merge this with the hot evaluation above.
-                    const int hb = 31 - __clz(cand);
-                    cand &= ~(1u << hb);
-                    const int k = BATCH - 1 - hb;
-                    const int tri = (tile_lo + it) * TILE + b0 + k;
-                    const float4 rb = lds128_opaque(&tp[3 * (b0 + k)]), rc = lds128_opaque(&tp[3 * (b0 + k) + 1]),
-                                 rd = lds128_opaque(&tp[3 * (b0 + k) + 2]);
-                    unsigned mask = 0;
+                    // rare: a group of GROUP triangles may hold a candidate.  Rebuild the per-ray candidate mask of each
+                    // of its triangles (each ray's own q, exact threshold), then the reference's own arithmetic.  The rows
+                    // are re-read through opaque loads so that the compiler cannot merge this with the hot evaluation.
+                    const int gq = __ffs(cand) - 1; // ascending triangle order
+                    cand &= cand - 1;
+#pragma unroll 1
+                    for (int kk = 0; kk < GROUP; ++kk) {
+                        const int k = b0 + gq * GROUP + kk;
+                        const int tri = (tile_lo + it) * TILE + k;
+                        const float4 rb = lds128_opaque(&tp[3 * k]), rc = lds128_opaque(&tp[3 * k + 1]), rd = lds128_opaque(&tp[3 * k + 2]);
+                        unsigned filt = 0;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) mask |= ((edge_sign(rb, rc, rd, rp[r], rq[r]) >> 31) ^ 1u) << r;
-                    // (QBAR sweeps hand the rays' exact q in rq as well: the candidate masks are as tight as ever)
-                    const unsigned live = valid & ~done;
-                    if (EXHAUSTIVE) {
-                        // validation mode: strict-test every pair, count accepts the filter would have lost
-                        if (tri < n_tris && live) {
-                            int before[R];
-#pragma unroll
-                            for (int r = 0; r < R; ++r) before[r] = sm.tri[r][tid];
-                            const unsigned nw = strict_tri<R, ANYHIT, RS>(sm, tid, live, tri, tri_verts, rsrc, n_strict);
-                            if (ANYHIT) done |= nw;
-#pragma unroll
-                            for (int r = 0; r < R; ++r)
-                                if (sm.tri[r][tid] != before[r] && !((mask >> r) & 1u)) ++n_miss;
-                        }
-                    } else {
-                        mask &= live;
-                        if (mask) {
-                            const unsigned nw = strict_tri<R, ANYHIT, RS>(sm, tid, mask, tri, tri_verts, rsrc, n_strict);
+                        for (int r = 0; r < R; ++r) filt |= (unsigned)edge_pass(rb, rc, rd, rp[r], rq[r]) << r;
+                        const unsigned live = valid & ~done;
+                        const unsigned mask = EXHAUSTIVE ? live : (filt & live);
+                        if (mask && tri < n_tris) {
+                            const unsigned nw = strict(mask, tri, filt);
                             if (ANYHIT) done |= nw;
                         }
                     }
@@ -288,40 +328,23 @@ __device__ __forceinline__ void sweep_table(Smem<RS> &sm, const float4 *__restri
 #endif
             }
         }
-        if (!ANYHIT) {
-            // Closest hit never stops early, so no block-wide barrier is needed per tile: every warp counts
-            // itself out of stage s, and the LAST one refills it.  Warps run up to STAGES-1 tiles apart, which
-            // absorbs the skew of the (rare, long) strict evaluations instead of stalling 15 warps behind one.
-            __syncwarp();
-            if ((tid & 31) == 0) {
-                __threadfence_block(); // this warp's reads of the stage are done before the count is visible
-                if (atomicAdd(&sm.consumed[s], 1) == THREADS / 32 - 1) {
-                    sm.consumed[s] = 0;
-                    __threadfence_block();
-                    if (it + STAGES < n_tiles) {
-                        mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
-                        tma_load_1d(sm.tile[s], src + (size_t)(it + STAGES) * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
-                    }
+        // No block-wide barrier per tile: every warp counts itself out of stage s, and the LAST one refills it.
+        // Warps run up to STAGES-1 tiles apart, which absorbs the skew of the (rare, long) strict evaluations
+        // instead of stalling every warp behind one.
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            __threadfence_block(); // this warp's reads of the stage are done before the count is visible
+            if (atomicAdd(&sm.consumed[s], 1) == (int)(blockDim.x >> 5) - 1) {
+                sm.consumed[s] = 0;
+                __threadfence_block();
+                if (it + STAGES < n_tiles) {
+                    mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
+                    tma_load_1d(sm.tile[s], src + (size_t)(it + STAGES) * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
                 }
             }
-            continue;
-        }
-        // everyone is done with stage s (also: have all rays of the CTA found their occluder?)
-        const int all_done = __syncthreads_and((done | ~valid) == 0xffffffffu);
-        if (all_done) stop = true;
-        if (!stop && it + STAGES < n_tiles) {
-            last_issued = it + STAGES;
-            if (tid == 0) {
-                mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
-                tma_load_1d(sm.tile[s], src + (size_t)last_issued * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
-            }
-        }
-        if (stop && it >= last_issued) {
-            ++it;
-            break;
         }
     }
-    gtile += it; // every issued tile has been waited for
+    gtile += n_tiles; // every issued tile has been waited for
 }
 
 }  // namespace sweep

@@ -188,9 +188,9 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
 
 template <int R, bool EX, bool SQ>
 int launch_primary_q(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(sweep::Smem<R>);
+    const size_t smem = sizeof(sweep::Smem);
     CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trk::primary_kernel<R, EX, SQ><<<grid, sweep::THREADS, smem, st>>>(p);
+    trk::primary_kernel<R, EX, SQ><<<grid, sweep::NT, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -199,27 +199,23 @@ int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     // rays of one thread share q unless the sample positions are jittered (extension)
     return p.bands.spp_n > 1 ? launch_primary_q<R, EX, false>(p, grid, st) : launch_primary_q<R, EX, true>(p, grid, st);
 }
-template <int R, bool EX, bool QB>
-int launch_shadow_q(const trk::ShadowParams &p, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(sweep::Smem<R>);
-    CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trk::shadow_kernel<R, EX, QB><<<grid, sweep::THREADS, smem, st>>>(p);
+template <int R, bool EX>
+int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(sweep::Smem);
+    CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trk::shadow_kernel<R, EX><<<grid, sweep::NT, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
-}
-template <int R, bool EX>
-int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st, bool qbar) {
-    return qbar ? launch_shadow_q<R, EX, true>(p, grid, st) : launch_shadow_q<R, EX, false>(p, grid, st);
 }
 int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
     if (R == 4) return ex ? launch_primary_t<4, true>(p, grid, st) : launch_primary_t<4, false>(p, grid, st);
     return ex ? launch_primary_t<2, true>(p, grid, st) : launch_primary_t<2, false>(p, grid, st);
 }
-int launch_shadow(int R, bool ex, bool qbar, const trk::ShadowParams &p, int grid, cudaStream_t st) {
-    if (R == 8) return ex ? launch_shadow_t<8, true>(p, grid, st, qbar) : launch_shadow_t<8, false>(p, grid, st, qbar);
-    if (R == 4) return ex ? launch_shadow_t<4, true>(p, grid, st, qbar) : launch_shadow_t<4, false>(p, grid, st, qbar);
-    return ex ? launch_shadow_t<2, true>(p, grid, st, qbar) : launch_shadow_t<2, false>(p, grid, st, qbar);
+int launch_shadow(int R, bool ex, const trk::ShadowParams &p, int grid, cudaStream_t st) {
+    if (R == 8) return ex ? launch_shadow_t<8, true>(p, grid, st) : launch_shadow_t<8, false>(p, grid, st);
+    if (R == 4) return ex ? launch_shadow_t<4, true>(p, grid, st) : launch_shadow_t<4, false>(p, grid, st);
+    return ex ? launch_shadow_t<2, true>(p, grid, st) : launch_shadow_t<2, false>(p, grid, st);
 }
 
 // Work decomposition of a sweep: R rays per thread (8 preferred: best amortisation of the row loads) and
@@ -242,7 +238,7 @@ int items_per_sm(bool closest) {
 Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks) {
     const int slices_possible = std::max(1, n_tiles / 4); // at least 4 tiles per slice
     auto blocks_for = [&](int R) {
-        return (int)((n_rays + (int64_t)sweep::THREADS * R - 1) / ((int64_t)sweep::THREADS * R)) + extra_blocks;
+        return (int)((n_rays + (int64_t)sweep::NT * R - 1) / ((int64_t)sweep::NT * R)) + extra_blocks;
     };
     Decomp d{2, blocks_for(2), 1};
     if (forced_R == 2 || forced_R == 4 || forced_R == 8) {
@@ -568,13 +564,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             s->cand_cap = cap;
         }
     }
-    // default mode: shadow rays ordered by (group, q) so that the rays of a thread can share a q-term (sweep::edge_sign_qbar)
-    static const bool qbar_env = [] {
-        const char *e = std::getenv("TRACER_SHADOW_QBAR");
-        return e ? std::atoi(e) != 0 : true; // development knob: 0 = pixel-ordered lists, one q per ray
-    }();
-    const bool qbar = !cull && qbar_env;
-    if ((cull || qbar) && s->rkey_npx < n_px) { // shadow rays are ordered by (group, Morton code) with a radix sort of (key, pixel) pairs
+    // default mode: shadow rays ordered by (group, q) so that the rays of a thread can share a q-term (sweep::MODE_QBAR);
+    // bundle-cull mode: ordered by (group, Morton code of (p,q)).  Either way a radix sort of (key, pixel) pairs.
+    if (s->rkey_npx < n_px) {
         dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
         g_pool.release(s->pair_tmp);
         s->pair_tmp = nullptr;
@@ -678,14 +670,14 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.best = s->best, p.counters = s->counters, p.work = s->work;
         p.n_rows = n_rows, p.n_blocks = 0; // ray blocks = screen tiles of (TX R) x (512 / TX) pixels: least edge waste wins
         for (int lg = 3; lg <= 6; ++lg) {
-            const int tw = (1 << lg) * d.R, th = sweep::THREADS >> lg;
+            const int tw = (1 << lg) * d.R, th = sweep::NT >> lg;
             const int tx = (W + tw - 1) / tw, nb = tx * ((n_rows + th - 1) / th);
             if (!p.n_blocks || nb < p.n_blocks) p.n_blocks = nb, p.tiles_x = tx, p.tx_log2 = lg;
         }
         p.n_slices = d.n_slices;
         if (p.n_blocks < items_per_sm(true) * g.n_sms) // same sizing rule as pick_decomp, on the real block count
             p.n_slices = std::max(1, std::min((items_per_sm(true) * g.n_sms + p.n_blocks - 1) / p.n_blocks, std::max(1, n_tiles / 4)));
-        const int grid = std::min(p.n_blocks * p.n_slices, g.n_sms);
+        const int grid = std::min(p.n_blocks * p.n_slices, sweep::MINB * g.n_sms);
         flop_primary = bands.spp_n > 1 ? 12.0 : 2.0 * (3 + 3 * d.R) / d.R;
         if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, p, grid, st)) return rc;
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
@@ -754,7 +746,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         lp.rng_mode = o.rng_mode, lp.seed = seed_s, lp.faceid = s->faceid, lp.lmax = (k + 1) * diag;
         lp.seg_count = s->seg_count, lp.counters = s->counters;
         lp.dbg_occ = o.out_occ_tri ? s->dbg_occ : nullptr;
-        lp.cull_cells = cull ? 1 : (qbar ? 2 : 0), lp.rkey = s->rkey;
+        lp.cull_cells = cull ? 1 : 2, lp.rkey = s->rkey;
         if (k < L) CK_CUDA(cudaMemsetAsync(s->seg_count, 0, sizeof(int) * ((size_t)s->maxF * trk::NFACE + 1), st));
         trk::light_step_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(lp);
         CK_CUDA(cudaGetLastError());
@@ -826,7 +818,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
         CK_CUDA(cudaGetLastError());
         const int max_cblocks = (n_px + trk::CBLK - 1) / trk::CBLK + 1;
-        if (qbar) { // group-major, q-minor order (pixels without a shadow ray carry the all-ones key and sort last)
+        { // group-major, q-minor order (pixels without a shadow ray carry the all-ones key and sort last)
             int group_bits = 1;
             while ((1 << group_bits) < F) ++group_bits;
             CK_CUDA(cub::DeviceRadixSort::SortPairs(s->pair_tmp, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0,
@@ -839,9 +831,6 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 if (dev_alloc(&s->blk_cnt, need)) return TRACER_ERR_NOMEM;
                 s->blk_cnt_cap = need;
             }
-        } else {
-            trk::list_scatter_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->rj, n_px, s->seg_off, s->cursor, s->list);
-            CK_CUDA(cudaGetLastError());
         }
         launches += 2;
         CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
@@ -890,7 +879,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             if (c == 0)
                 if (int rc = build_face_tables(k, h_cnt)) return rc;
             const int tile_lo = bounds[c], tile_hi = bounds[c + 1];
-            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::THREADS * Rk, tile_hi - tile_lo, g.n_sms, s->blk_off, cnt_out,
+            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::NT * Rk, tile_hi - tile_lo, sweep::MINB * g.n_sms, s->blk_off, cnt_out,
                                                        s->work, s->n_slices, items_per_sm(false), 4);
             CK_CUDA(cudaGetLastError());
             trk::ShadowParams sp{};
@@ -900,15 +889,13 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
             sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, qbar, sp, g.n_sms, st)) return rc;
-            if (qbar) { // order-preserving: the lists stay sorted by q
+            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, sp, sweep::MINB * g.n_sms, st)) return rc;
+            { // order-preserving compaction: the lists stay sorted by q
                 const dim3 bgrid((unsigned)std::max(1, (max_live_group + trk::CBLK - 1) / trk::CBLK), (unsigned)F);
                 trk::compact_count_kernel<<<bgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, s->blk_cnt, max_cblocks);
                 trk::compact_scatter_kernel<<<bgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, s->blk_cnt, max_cblocks,
                                                                     list_out, cnt_out);
                 ++launches;
-            } else {
-                trk::compact_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, list_out, cnt_out);
             }
             CK_CUDA(cudaGetLastError());
             launches += 3;
@@ -988,7 +975,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.kernel_launches = launches;
     // shadow sweeps: 6 FFMA per pair, or (6 + 3R) FFMA per R pairs when a thread's R = 8 rays share the q-terms
-    s->stats.flop_primary = flop_primary, s->stats.flop_shadow = cull ? 0.0 : (qbar ? 2.0 * (6 + 3 * 8) / 8 : 12.0);
+    s->stats.flop_primary = flop_primary, s->stats.flop_shadow = cull ? 0.0 : 2.0 * (6 + 3 * 8) / 8;
     if (hc.cull_overflow)
         return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow; use the default mode for this scene");
     if (getenv("TRACER_CULL_DIAG"))
