@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
 ]
 # include/tracer_host.h
 HOST_SYMBOLS = ["tracer_scene_load_obj", "tracer_scene_host_flat", "tracer_scene_host_free", "tracer_host_last_error",
-                "tracer_write_ppm"]
+                "tracer_write_ppm", "tracer_scene_flatten_sorted", "tracer_scene_host_origin"]
 
 
 class TracerError(RuntimeError):
@@ -112,6 +112,8 @@ def load():
     lib.tracer_scene_host_free.argtypes = [C.c_void_p]
     lib.tracer_scene_host_free.restype = None
     lib.tracer_host_last_error.restype = C.c_char_p
+    lib.tracer_scene_flatten_sorted.argtypes = [C.POINTER(SceneFlat), C.POINTER(C.c_void_p)]
+    lib.tracer_scene_host_origin.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]
     lib.tracer_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     _lib = lib
     return lib

@@ -92,15 +92,36 @@ class Scene:
         if lib.tracer_scene_load_obj(path.encode(), C.byref(h)) != 0:
             raise TracerError(lib.tracer_host_last_error().decode())
         try:
-            f = lib.tracer_scene_host_flat(h).contents
-            G = f.n_geoms
-            off = np.ctypeslib.as_array(f.geom_tri_offset, (G + 1,)).copy()
-            N = int(off[-1])
-            grab = lambda ptr, shape, dt: (np.ctypeslib.as_array(ptr, shape).astype(dt).copy() if int(np.prod(shape)) else np.zeros(shape, dt))
-            hasn = grab(f.geom_has_normals, (G,), np.int32)
-            return Scene(off, grab(f.tri_verts, (N, 3, 3), np.float32), grab(f.geom_material, (G, 13), np.float32),
-                         grab(f.light_geom, (f.n_lights,), np.int32),
-                         tri_normals=grab(f.tri_normals, (N, 3, 3), np.float32) if hasn.any() else None, geom_has_normals=hasn)
+            return Scene._from_host(lib, h)
+        finally:
+            lib.tracer_scene_host_free(h)
+
+    @staticmethod
+    def _from_host(lib, h) -> "Scene":
+        f = lib.tracer_scene_host_flat(h).contents
+        G = f.n_geoms
+        off = np.ctypeslib.as_array(f.geom_tri_offset, (G + 1,)).copy()
+        N = int(off[-1])
+        grab = lambda ptr, shape, dt: (np.ctypeslib.as_array(ptr, shape).astype(dt).copy() if int(np.prod(shape)) and ptr else np.zeros(shape, dt))
+        hasn = grab(f.geom_has_normals, (G,), np.int32)
+        return Scene(off, grab(f.tri_verts, (N, 3, 3), np.float32), grab(f.geom_material, (G, 13), np.float32),
+                     grab(f.light_geom, (f.n_lights,), np.int32),
+                     tri_normals=grab(f.tri_normals, (N, 3, 3), np.float32) if hasn.any() else None, geom_has_normals=hasn)
+
+    def flatten_sorted(self):
+        """flatten_scene (src/simplify/flatten.cpp:50-82): flat triangle array sorted by vertices[0].x, through the
+        library's host helper (tracer_scene_flatten_sorted).  Returns (Scene in sorted iteration order,
+        origin_geom [N'], origin_prim [N']) — the (geom_id, prim_id) every sorted triangle keeps (flatten.cpp:62-63)."""
+        lib = _lib.load()
+        h = C.c_void_p()
+        cs = self.c_struct()
+        if lib.tracer_scene_flatten_sorted(C.byref(cs), C.byref(h)) != 0:
+            raise TracerError(lib.tracer_host_last_error().decode())
+        try:
+            sc = Scene._from_host(lib, h)
+            pg, pp = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+            _lib.check(lib.tracer_scene_host_origin(h, C.byref(pg), C.byref(pp)))
+            return sc, np.ctypeslib.as_array(pg, (sc.n_tris,)).copy(), np.ctypeslib.as_array(pp, (sc.n_tris,)).copy()
         finally:
             lib.tracer_scene_host_free(h)
 

@@ -3,6 +3,7 @@
 // not from its code: a line tokenizer over std::string_view, explicit shape/material state.
 #include <cctype>
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,7 +19,18 @@
 struct tracer_scene_host {
     std::vector<int32_t> geom_tri_offset{0}, geom_has_normals, light_geom;
     std::vector<float> tri_verts, tri_normals, geom_material;
+    std::vector<int32_t> origin_geom, origin_prim; // flatten+sort only: where each triangle came from
     tracer_scene_flat flat{};
+    void bind() {
+        flat.n_geoms = (int32_t)geom_has_normals.size();
+        flat.geom_tri_offset = geom_tri_offset.data();
+        flat.tri_verts = tri_verts.data();
+        flat.tri_normals = tri_normals.empty() ? nullptr : tri_normals.data();
+        flat.geom_has_normals = geom_has_normals.data();
+        flat.geom_material = geom_material.data();
+        flat.n_lights = (int32_t)light_geom.size();
+        flat.light_geom = light_geom.data();
+    }
 };
 
 namespace {
@@ -388,19 +400,84 @@ int tracer_scene_load_obj(const char *obj_path, tracer_scene_host **out) {
         h->geom_tri_offset.push_back(h->geom_tri_offset.back() + (int32_t)(sh.corners.size() / 3));
         if (ke2 > 0) h->light_geom.push_back((int32_t)h->geom_has_normals.size() - 1);
     }
-    h->flat.n_geoms = (int32_t)h->geom_has_normals.size();
-    h->flat.geom_tri_offset = h->geom_tri_offset.data();
-    h->flat.tri_verts = h->tri_verts.data();
-    h->flat.tri_normals = h->tri_normals.data();
-    h->flat.geom_has_normals = h->geom_has_normals.data();
-    h->flat.geom_material = h->geom_material.data();
-    h->flat.n_lights = (int32_t)h->light_geom.size();
-    h->flat.light_geom = h->light_geom.data();
+    h->bind();
     *out = h;
     return TRACER_OK;
 }
 
 const tracer_scene_flat *tracer_scene_host_flat(const tracer_scene_host *scene) { return scene ? &scene->flat : nullptr; }
+
+// flatten + sort, src/simplify/flatten.cpp:50-82 with the comparator of flatten.cpp:20-27 (see tracer_host.h)
+int tracer_scene_flatten_sorted(const tracer_scene_flat *in, tracer_scene_host **out) {
+    if (!out) return TRACER_ERR_INVALID;
+    *out = nullptr;
+    if (!in || in->n_geoms < 0 || (in->n_geoms > 0 && (!in->geom_tri_offset || !in->geom_material))) {
+        g_host_err = "flatten_sorted: bad scene";
+        return TRACER_ERR_INVALID;
+    }
+    if (in->n_spheres > 0) {
+        g_host_err = "flatten_sorted: the reference's flatten pass knows triangles only";
+        return TRACER_ERR_INVALID;
+    }
+    const int G = in->n_geoms;
+    const int N = G > 0 ? in->geom_tri_offset[G] : 0;
+    std::vector<int32_t> tri_geom((size_t)N), order((size_t)N);
+    for (int g = 0; g < G; ++g)
+        for (int t = in->geom_tri_offset[g]; t < in->geom_tri_offset[g + 1]; ++t) tri_geom[t] = g;
+    for (int t = 0; t < N; ++t) order[t] = t; // flatten.cpp:53-75: geometry major, face minor
+    // flatten.cpp:78 sorts with leftMostTriangle (vertices[0].x ascending, flatten.cpp:20-27).  std::sort leaves the
+    // order of equal keys unspecified; a stable sort is one of its valid outcomes and makes the order reproducible.
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return in->tri_verts[9 * (size_t)a] < in->tri_verts[9 * (size_t)b]; });
+    auto *h = new tracer_scene_host();
+    bool any_normals = false;
+    for (int g = 0; g < G && in->geom_has_normals; ++g) any_normals |= in->geom_has_normals[g] != 0;
+    any_normals = any_normals && in->tri_normals;
+    auto open_geom = [&](int g) {
+        h->geom_has_normals.push_back(in->geom_has_normals ? in->geom_has_normals[g] : 0);
+        h->geom_material.insert(h->geom_material.end(), in->geom_material + 13 * (size_t)g, in->geom_material + 13 * (size_t)g + 13);
+        h->geom_tri_offset.push_back(h->geom_tri_offset.back());
+    };
+    auto push_tri = [&](int t) {
+        h->tri_verts.insert(h->tri_verts.end(), in->tri_verts + 9 * (size_t)t, in->tri_verts + 9 * (size_t)t + 9);
+        if (any_normals) h->tri_normals.insert(h->tri_normals.end(), in->tri_normals + 9 * (size_t)t, in->tri_normals + 9 * (size_t)t + 9);
+        h->origin_geom.push_back(tri_geom[t]);
+        h->origin_prim.push_back(t - in->geom_tri_offset[tri_geom[t]]); // c_triangle.prim_id, flatten.cpp:63
+        ++h->geom_tri_offset.back();
+    };
+    // maximal runs of one original geometry become geometries of the output: iteration order == sorted order,
+    // material / has-normals of every triangle unchanged
+    for (int i = 0; i < N; ++i) {
+        const int t = order[i];
+        if (i == 0 || tri_geom[t] != tri_geom[order[i - 1]]) open_geom(tri_geom[t]);
+        push_tri(t);
+    }
+    // light geometries once more, at the end, in their ORIGINAL face order: main.cpp:749 samples light.vertex[faceID]
+    // from the light's own vertex list, which sorting must not permute.  The copies cannot change any result: a copy
+    // lies behind its original in the iteration order and computes the same t2, which `t2 >= t` rejects in the
+    // closest-hit loop (ray_triangle.h:49), and an occlusion ray that would stop at a copy has already stopped at
+    // the original (main.cpp:317-325).
+    for (int l = 0; l < in->n_lights; ++l) {
+        const int g = in->light_geom[l];
+        if (g < 0 || g >= G) {
+            delete h;
+            g_host_err = "flatten_sorted: light_geom index out of range";
+            return TRACER_ERR_INVALID;
+        }
+        open_geom(g);
+        for (int t = in->geom_tri_offset[g]; t < in->geom_tri_offset[g + 1]; ++t) push_tri(t);
+        h->light_geom.push_back((int32_t)h->geom_has_normals.size() - 1);
+    }
+    h->bind();
+    *out = h;
+    return TRACER_OK;
+}
+
+int tracer_scene_host_origin(const tracer_scene_host *scene, const int32_t **geom, const int32_t **prim) {
+    if (!scene || scene->origin_geom.empty()) return TRACER_ERR_INVALID;
+    if (geom) *geom = scene->origin_geom.data();
+    if (prim) *prim = scene->origin_prim.data();
+    return TRACER_OK;
+}
 
 void tracer_scene_host_free(tracer_scene_host *scene) { delete scene; }
 

@@ -579,22 +579,40 @@ __global__ void iota_kernel(int *a, int n) {
 }
 
 // ---------------------------------------------------------------------------------
-// First in-order occluder, one triangle chunk [tile_lo, tile_hi) per launch, the chunk itself cut
-// into n_slices slices swept by different CTAs (merged by atomicMin on index<<32|t2).  Rays are
-// grouped by (light vertex, cube face): segment j of the list, table j.  After each chunk the rays
-// that are still unoccluded are compacted into the next list (compact_kernel), so the pairs
-// actually swept track the reference's own early-exit count (main.cpp:324).
-struct ShadowParams {
-    const float4 *tables;  // face tables of the current light's vertices: group g=(j,f<6) at + (j*6+f)*table_stride
+// First in-order occluder (occlusion(), main.cpp:314-329): ONE persistent cooperative kernel per light.
+// Rays are grouped by (light vertex, cube face): segment j of the q-sorted list, table j.  The triangle table is cut
+// into chunks; inside the kernel every chunk is
+//     A. swept: (ray block, triangle slice) work items pulled from an atomic counter, merged by atomicMin on
+//        index<<32|t2;                                                                         grid barrier
+//     B. compacted, order preserving (the lists stay sorted by q): survivors counted per block of CBLK entries,
+//                                                                                              grid barrier
+//     C. ... and written in list order to the other list; new per-group counts;               grid barrier
+// so the pairs actually swept track the reference's own early-exit count (main.cpp:324) and the host is not in
+// the loop at all: block offsets, slice counts, the chunk scheme and the early stop ("every ray has its occluder")
+// are decided on the device.  Round 1 ran A/B/C as 4 launches per chunk with host read-backs in between.
+constexpr int SL_MAXF = 1022;   // ray groups per launch (the host batches bigger lights: 146 vertices x NFACE)
+constexpr int SL_MAXCHUNK = 64;
+constexpr int CBLK = 1024;      // list entries per compaction block
+
+struct ShadowLightParams {
+    const float4 *tables;  // face tables of this launch's first light vertex: group g=(j,f<6) at + (j*6+f)*table_stride
     const float4 *allcand; // table of group f == 6
     size_t table_stride;   // in float4
-    int tile_lo, tile_hi, n_tris, F, n_px; // F = number of ray groups (light vertices * NFACE)
-    const int *n_slices;                   // device: slices of this chunk (chunk_prefix_kernel)
+    int n_tris, n_tiles, F, n_px; // F = ray groups of this launch (light vertices * NFACE)
+    int n_chunks[2];              // [0] geometric scheme (few rays), [1] equal chunks (>= many_rays live rays)
+    int bounds[2][SL_MAXCHUNK + 1]; // chunk boundaries in tiles
+    long long many_rays;
+    int items_per_cta;            // (ray block, slice) items wanted per resident CTA
     const float *tri_verts;
-    const int *list_in, *seg_off, *cnt_in, *blk_off;
+    int *list[2];                 // ping-pong ray lists, [0] = the sorted input
+    const int *seg_off;           // [F+1] segment starts of this launch's groups (absolute list positions)
+    int *cnt[2];                  // [F] live rays per group, ping-pong; [0] = initial counts
+    int *blk_cnt;                 // compaction scratch: survivors per compaction block (<= n_px/CBLK + F entries)
     PixelState px;
+    const float4 *spheres;        // extension: tested after all triangles by the rays that found none
+    int n_spheres;
     sweep::Counters *counters;
-    int *work;
+    int *work;                    // [SL_MAXCHUNK] work counters, zeroed by the host
 };
 
 // The reference's own test for the rays (bits of mask) of one thread against triangle tri, shadow rays
@@ -602,23 +620,24 @@ struct ShadowParams {
 // multi-light carry).  Origin, direction and length stay in the pixel state and are fetched on demand: only a
 // few rays per work item ever get here.  Ray r of the thread is list entry min(e0 + r, e_last).
 // Returns newly occluded rays | evaluations << 8 | filter misses << 16.
-__device__ __noinline__ unsigned strict_shadow(const ShadowParams &p, int e0, int e_last, unsigned mask, int tri, unsigned filt) {
-    const float *q = p.tri_verts + 9 * (size_t)tri;
+__device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float *__restrict__ tri_verts, const int *__restrict__ list_in,
+                                               int n_px, int e0, int e_last, unsigned mask, int tri, unsigned filt) {
+    const float *q = tri_verts + 9 * (size_t)tri;
     const f3 v0 = strict::mk(__ldg(q), __ldg(q + 1), __ldg(q + 2));
     const f3 v1 = strict::mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
     const f3 v2 = strict::mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
-    const size_t n = (size_t)p.n_px;
+    const size_t n = (size_t)n_px;
     unsigned ret = 0;
     while (mask) {
         const int r = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int k = p.list_in[min(e0 + r, e_last)];
-        const f3 o = strict::mk(p.px.ro[k], p.px.ro[n + k], p.px.ro[2 * n + k]);
-        const f3 d = strict::mk(p.px.rd[k], p.px.rd[n + k], p.px.rd[2 * n + k]);
-        float t = p.px.rt[k], v = 0.f; // the ray has no occluder yet, so t is its initial length (main.cpp:764)
+        const int k = list_in[min(e0 + r, e_last)];
+        const f3 o = strict::mk(px.ro[k], px.ro[n + k], px.ro[2 * n + k]);
+        const f3 d = strict::mk(px.rd[k], px.rd[n + k], px.rd[2 * n + k]);
+        float t = px.rt[k], v = 0.f; // the ray has no occluder yet, so t is its initial length (main.cpp:764)
         ret += 1u << 8;
         if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
-            atomicMin(&p.px.best_occ[k], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(t));
+            atomicMin(&px.best_occ[k], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(t));
             ret |= 1u << r;
             if (!((filt >> r) & 1u)) ret += 1u << 16;
         }
@@ -630,9 +649,9 @@ __device__ __noinline__ unsigned strict_shadow(const ShadowParams &p, int e0, in
 // (and compaction keeps it so); a thread takes RR CONSECUTIVE rays, whose q differ by ~1e-6, and evaluates them
 // with one q-term per edge row (sweep::MODE_QBAR).
 template <int RR, bool EXHAUSTIVE>
-__device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowParams &p, int base, int seg_end, int lo, int hi,
-                                            const float4 *__restrict__ tab, unsigned &gtile, unsigned &n_strict, unsigned &n_miss,
-                                            unsigned long long &tests) {
+__device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowLightParams &p, const int *__restrict__ list_in, int base,
+                                            int seg_end, int lo, int hi, const float4 *__restrict__ tab, unsigned &gtile,
+                                            unsigned &n_strict, unsigned &n_miss, unsigned long long &tests) {
     const int tid = threadIdx.x, n = p.n_px;
     float rp[RR], rq[RR];
     unsigned valid = 0, done = 0;
@@ -640,7 +659,7 @@ __device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowParams 
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
         if (e0 + r < seg_end) valid |= 1u << r;
-        const int k = p.list_in[min(e0 + r, seg_end - 1)];
+        const int k = list_in[min(e0 + r, seg_end - 1)];
         rp[r] = p.px.re[k], rq[r] = p.px.re[n + k];
         // an earlier slice may already have published an occluder below this slice: nothing to do
         const unsigned long long seen = p.px.best_occ[k];
@@ -654,156 +673,238 @@ __device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowParams 
     // >= max |q_r - qbar| with room for the roundings of this line and of the one extra FFMA per row
     const float qdelta = fmaxf(qmax - qbar, qbar - qmin) * 1.0001f + 2.4e-7f * (fabsf(qbar) + 1.f);
     unsigned swept = 0;
-    sweep::sweep_table<RR, sweep::MODE_QBAR, true, EXHAUSTIVE>(sm, tab, lo, hi, p.n_tris, rp, rq, qbar, qdelta, valid, done, gtile, swept,
-                                                              [&](unsigned mask, int tri, unsigned filt) {
-                                                                  const unsigned c = strict_shadow(p, e0, seg_end - 1, mask, tri, filt);
-                                                                  n_strict += (c >> 8) & 0xffu, n_miss += c >> 16;
-                                                                  return c & 0xffu;
-                                                              });
+    sweep::sweep_table<RR, sweep::MODE_QBAR, true, EXHAUSTIVE>(
+        sm, tab, lo, hi, p.n_tris, rp, rq, qbar, qdelta, valid, done, gtile, swept, [&](unsigned mask, int tri, unsigned filt) {
+            const unsigned c = strict_shadow(p.px, p.tri_verts, list_in, n, e0, seg_end - 1, mask, tri, filt);
+            n_strict += (c >> 8) & 0xffu, n_miss += c >> 16;
+            return c & 0xffu;
+        });
     tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
 }
 
-template <int R, bool EXHAUSTIVE>
-__global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_kernel(const __grid_constant__ ShadowParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
-    const int tid = threadIdx.x;
-    sweep::smem_init(sm);
-    const int total_blocks = p.blk_off[p.F];
-    const int n_slices = *p.n_slices;
-    const int n_items = total_blocks * n_slices;
-    const int n_tiles = p.tile_hi - p.tile_lo;
-    unsigned gtile = 0, n_strict = 0, n_miss = 0;
-    unsigned long long tests = 0;
-    for (;;) {
-        if (tid == 0) {
-            const int it = atomicAdd(p.work, 1);
-            int j = 0, b = 0, sl = 0;
-            if (it < n_items) {
-                sl = it / total_blocks, b = it - sl * total_blocks; // slice-major
-                while (b >= p.blk_off[j + 1]) ++j;
-            }
-            sm.blk = it < n_items ? b : -1;
-            sm.seg = j;
-            sm.slice = sl;
-        }
-        __syncthreads();
-        const int blk = sm.blk, j = sm.seg, slice = sm.slice;
-        if (blk < 0) break;
-        const int lo = p.tile_lo + (int)((long long)n_tiles * slice / n_slices);
-        const int hi = p.tile_lo + (int)((long long)n_tiles * (slice + 1) / n_slices);
-        const int seg_begin = p.seg_off[j], seg_end = seg_begin + p.cnt_in[j];
-        const int base = seg_begin + (blk - p.blk_off[j]) * (sweep::NT * R);
-        const int face = j % NFACE;
-        const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-        // The last block of a ray group is rarely full.  A block with at most NT*RR rays is swept with RR rays per
-        // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups:
-        // this padding is a fixed cost per frame).
-        const int cnt = seg_end - base;
-        bool swept_it = false;
-        if constexpr (R >= 8) {
-            if (cnt > 4 * sweep::NT) {
-                shadow_item<8, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
-                swept_it = true;
-            }
-        }
-        if constexpr (R >= 4) {
-            if (!swept_it && cnt > 2 * sweep::NT) {
-                shadow_item<4, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
-                swept_it = true;
-            }
-        }
-        if (!swept_it) shadow_item<2, EXHAUSTIVE>(sm, p, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
-        __syncthreads();
-    }
-    atomicAdd(&p.counters->tests_shadow, tests);
-    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
-    if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
-}
-
-// ORDER-PRESERVING compaction (QBAR sweeps keep each group's list sorted by q): pass 1 counts the survivors of
-// every block of CBLK list entries, pass 2 sums the counts of the blocks before its own and writes its survivors
-// in list order.  grid = (blocks of the longest group, F).
-constexpr int CBLK = 1024;
-__global__ void __launch_bounds__(256) compact_count_kernel(const int *__restrict__ list_in, const int *__restrict__ seg_off,
-                                                            const int *__restrict__ cnt_in, int F,
-                                                            const unsigned long long *__restrict__ best_occ, int *__restrict__ blk_cnt,
-                                                            int max_blocks) {
-    const int j = blockIdx.y, bx = blockIdx.x;
-    if (j >= F) return;
-    const int begin = seg_off[j], count = cnt_in[j];
-    if (bx * CBLK >= count) return;
-    int alive = 0;
+// exclusive prefix over the F groups of ceil(cnt[j] / unit), by the whole CTA into shared memory; returns the total
+__device__ __forceinline__ int cta_group_prefix(const int *__restrict__ cnt, int F, int unit, int *out /*[F+1] shared*/, int *scratch) {
+    constexpr int PER = (SL_MAXF + 1 + sweep::NT - 1) / sweep::NT;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int v[PER], sum = 0;
 #pragma unroll
-    for (int c = 0; c < CBLK / 256; ++c) {
-        const int i = bx * CBLK + threadIdx.x * (CBLK / 256) + c;
-        if (i < count && best_occ[list_in[begin + i]] == KEY_NONE) ++alive;
+    for (int i = 0; i < PER; ++i) {
+        const int j = tid * PER + i;
+        v[i] = j < F ? (cnt[j] + unit - 1) / unit : 0;
+        sum += v[i];
     }
-    __shared__ int wsum[8];
-    int v = alive;
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < 8; ++w) t += wsum[w];
-        blk_cnt[(size_t)j * max_blocks + bx] = t;
-    }
-}
-
-__global__ void __launch_bounds__(256) compact_scatter_kernel(const int *__restrict__ list_in, const int *__restrict__ seg_off,
-                                                              const int *__restrict__ cnt_in, int F,
-                                                              const unsigned long long *__restrict__ best_occ,
-                                                              const int *__restrict__ blk_cnt, int max_blocks, int *__restrict__ list_out,
-                                                              int *cnt_out) {
-    const int j = blockIdx.y, bx = blockIdx.x;
-    if (j >= F) return;
-    const int begin = seg_off[j], count = cnt_in[j];
-    if (bx * CBLK >= count) return;
-    __shared__ int wsum[8], s_off;
-    // survivors in the blocks before this one
-    int before = 0;
-    for (int b = threadIdx.x; b < bx; b += 256) before += blk_cnt[(size_t)j * max_blocks + b];
-    for (int o = 16; o; o >>= 1) before += __shfl_down_sync(0xffffffffu, before, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = before;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < 8; ++w) t += wsum[w];
-        s_off = t;
-    }
-    __syncthreads();
-    const int off = s_off;
-    // this block's survivors, in list order: thread t owns CBLK/256 consecutive entries
-    int ks[CBLK / 256], alive = 0;
-#pragma unroll
-    for (int c = 0; c < CBLK / 256; ++c) {
-        const int i = bx * CBLK + threadIdx.x * (CBLK / 256) + c;
-        int k = -1;
-        if (i < count) {
-            k = list_in[begin + i];
-            if (best_occ[k] != KEY_NONE) k = -1;
-        }
-        ks[c] = k;
-        alive += k >= 0;
-    }
-    int incl = alive; // inclusive scan over the 256 threads
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
     }
-    __syncthreads(); // wsum is reused
-    if (lane == 31) wsum[w] = incl;
+    __syncthreads(); // scratch / out may still be read from the previous use
+    if (lane == 31) scratch[w] = incl;
     __syncthreads();
-    int wbase = 0;
-    for (int i = 0; i < w; ++i) wbase += wsum[i];
-    int pos = off + wbase + incl - alive;
+    int base = 0, total = 0;
+    for (int i = 0; i < sweep::NT / 32; ++i) {
+        if (i < w) base += scratch[i];
+        total += scratch[i];
+    }
+    int run = base + incl - sum;
 #pragma unroll
-    for (int c = 0; c < CBLK / 256; ++c)
-        if (ks[c] >= 0) list_out[begin + pos++] = ks[c];
-    if ((bx + 1) * CBLK >= count && threadIdx.x == 255) cnt_out[j] = off + wbase + incl; // the group's last block: new count
+    for (int i = 0; i < PER; ++i) {
+        const int j = tid * PER + i;
+        if (j <= F) out[j] = run;
+        run += v[i];
+    }
+    __syncthreads();
+    return total;
+}
+
+// group of block b: largest j with off[j] <= b (off is non-decreasing, off[F] = total > b)
+__device__ __forceinline__ int group_of_block(const int *off, int F, int b) {
+    int lo = 0, hi = F; // invariant: off[lo] <= b < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= b) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// All CTAs of the launch are co-resident (cooperative launch).  Monotonic counter: arrive, then wait for the epoch's
+// total.  The counter is zeroed by the host before the launch.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned want = epoch * gridDim.x;
+        while (*(volatile unsigned *)bar < want) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool EXHAUSTIVE>
+__global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(const __grid_constant__ ShadowLightParams p, unsigned *bar) {
+    static_assert(CBLK % sweep::NT == 0, "compaction block must be a multiple of the CTA size");
+    constexpr int R = 8, CPT = CBLK / sweep::NT; // rays per thread of a full ray block; list entries per thread of a compaction block
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
+    __shared__ int s_blk_off[SL_MAXF + 1], s_cblk_off[SL_MAXF + 1], s_scratch[sweep::NT / 32], s_off;
+    const int tid = threadIdx.x, F = p.F;
+    sweep::smem_init(sm);
+    unsigned gtile = 0, n_strict = 0, n_miss = 0, epoch = 0;
+    unsigned long long tests = 0;
+    // chunk scheme: equal chunks keep the pairs swept past a ray's occluder lowest and win when the light has many
+    // rays; with few rays the per-chunk tails weigh more and boundaries that start fine and coarsen geometrically win
+    const long long live0 = cta_group_prefix(p.cnt[0], F, 1, s_blk_off, s_scratch);
+    const int scheme = live0 >= p.many_rays ? 1 : 0;
+    const int n_chunks = p.n_chunks[scheme];
+    const int *bounds = p.bounds[scheme];
+    int cur = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int *list_in = p.list[cur], *cnt_in = p.cnt[cur];
+        int *list_out = p.list[cur ^ 1], *cnt_out = p.cnt[cur ^ 1];
+        const int total_blocks = cta_group_prefix(cnt_in, F, sweep::NT * R, s_blk_off, s_scratch);
+        if (total_blocks == 0) break; // every shadow ray of this light already has its occluder (same on every CTA)
+        const int total_cblocks = cta_group_prefix(cnt_in, F, CBLK, s_cblk_off, s_scratch);
+        const int tile_lo = bounds[c], tile_hi = bounds[c + 1], n_tiles = tile_hi - tile_lo;
+        // enough (block, slice) items to keep every CTA busy to the end of the chunk, >= 4 tiles per slice
+        const int want = p.items_per_cta * (int)gridDim.x;
+        const int n_slices = max(1, min(total_blocks >= want ? 1 : (want + total_blocks - 1) / total_blocks, max(1, n_tiles / 4)));
+        const int n_items = total_blocks * n_slices;
+        // ---- A: sweep --------------------------------------------------------------------------------------
+        for (;;) {
+            if (tid == 0) {
+                const int it = atomicAdd(&p.work[c], 1);
+                int j = 0, b = -1, sl = 0;
+                if (it < n_items) {
+                    sl = it / total_blocks, b = it - sl * total_blocks; // slice-major
+                    j = group_of_block(s_blk_off, F, b);
+                }
+                sm.blk = b, sm.seg = j, sm.slice = sl;
+            }
+            __syncthreads();
+            const int blk = sm.blk, j = sm.seg, slice = sm.slice;
+            if (blk < 0) break;
+            const int lo = tile_lo + (int)((long long)n_tiles * slice / n_slices);
+            const int hi = tile_lo + (int)((long long)n_tiles * (slice + 1) / n_slices);
+            const int seg_begin = p.seg_off[j], seg_end = seg_begin + cnt_in[j];
+            const int base = seg_begin + (blk - s_blk_off[j]) * (sweep::NT * R);
+            const int face = j % NFACE;
+            const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
+            // The last block of a ray group is rarely full.  A block with at most NT*RR rays is swept with RR rays per
+            // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups).
+            const int cnt = seg_end - base;
+            if (cnt > 4 * sweep::NT)
+                shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+            else if (cnt > 2 * sweep::NT)
+                shadow_item<4, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+            else
+                shadow_item<2, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+            __syncthreads();
+        }
+        if (c == n_chunks - 1) break; // nothing left to sweep: the lists are not needed compacted
+        grid_barrier(bar, epoch);
+        // ---- B: survivors per compaction block ------------------------------------------------------------------
+        for (int cb = blockIdx.x; cb < total_cblocks; cb += gridDim.x) {
+            const int j = group_of_block(s_cblk_off, F, cb), bx = cb - s_cblk_off[j];
+            const int begin = p.seg_off[j], count = cnt_in[j];
+            int alive = 0;
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) {
+                const int i = bx * CBLK + tid * CPT + q;
+                if (i < count && p.px.best_occ[list_in[begin + i]] == KEY_NONE) ++alive;
+            }
+            for (int o = 16; o; o >>= 1) alive += __shfl_down_sync(0xffffffffu, alive, o);
+            __syncthreads();
+            if ((tid & 31) == 0) s_scratch[tid >> 5] = alive;
+            __syncthreads();
+            if (tid == 0) {
+                int t = 0;
+                for (int w = 0; w < sweep::NT / 32; ++w) t += s_scratch[w];
+                p.blk_cnt[cb] = t;
+            }
+        }
+        grid_barrier(bar, epoch);
+        // ---- C: write the survivors in list order ---------------------------------------------------------------
+        for (int cb = blockIdx.x; cb < total_cblocks; cb += gridDim.x) {
+            const int j = group_of_block(s_cblk_off, F, cb), bx = cb - s_cblk_off[j];
+            const int begin = p.seg_off[j], count = cnt_in[j];
+            int before = 0; // survivors in the group's blocks before this one
+            for (int b = tid; b < bx; b += sweep::NT) before += p.blk_cnt[s_cblk_off[j] + b];
+            for (int o = 16; o; o >>= 1) before += __shfl_down_sync(0xffffffffu, before, o);
+            __syncthreads();
+            if ((tid & 31) == 0) s_scratch[tid >> 5] = before;
+            __syncthreads();
+            if (tid == 0) {
+                int t = 0;
+                for (int w = 0; w < sweep::NT / 32; ++w) t += s_scratch[w];
+                s_off = t;
+            }
+            __syncthreads();
+            const int off = s_off;
+            int ks[CPT], alive = 0;
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) {
+                const int i = bx * CBLK + tid * CPT + q;
+                int k = -1;
+                if (i < count) {
+                    k = list_in[begin + i];
+                    if (p.px.best_occ[k] != KEY_NONE) k = -1;
+                }
+                ks[q] = k;
+                alive += k >= 0;
+            }
+            int incl = alive; // inclusive scan over the CTA
+            const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            __syncthreads(); // s_scratch is reused
+            if (lane == 31) s_scratch[w] = incl;
+            __syncthreads();
+            int wbase = 0;
+            for (int i = 0; i < w; ++i) wbase += s_scratch[i];
+            int pos = off + wbase + incl - alive;
+#pragma unroll
+            for (int q = 0; q < CPT; ++q)
+                if (ks[q] >= 0) list_out[begin + pos++] = ks[q];
+            if ((bx + 1) * CBLK >= count && tid == sweep::NT - 1) cnt_out[j] = off + wbase + incl; // the group's last block
+            __syncthreads();
+        }
+        // groups without entries keep a zero count
+        for (int j = blockIdx.x * sweep::NT + tid; j < F; j += gridDim.x * sweep::NT)
+            if (cnt_in[j] == 0) cnt_out[j] = 0;
+        grid_barrier(bar, epoch);
+        cur ^= 1;
+    }
+    // ---- extension: spheres come after all triangles in the object order --------------------------------------------
+    if (p.n_spheres > 0) {
+        grid_barrier(bar, epoch); // every sweep of the last chunk has published its occluders
+        const int *list_in = p.list[cur], *cnt_in = p.cnt[cur];
+        const size_t n = (size_t)p.n_px;
+        for (int j = 0; j < F; ++j) {
+            const int begin = p.seg_off[j], count = cnt_in[j];
+            for (int i = blockIdx.x * sweep::NT + tid; i < count; i += gridDim.x * sweep::NT) {
+                const int k = list_in[begin + i];
+                if (p.px.best_occ[k] != KEY_NONE) continue;
+                const f3 o = strict::mk(p.px.ro[k], p.px.ro[n + k], p.px.ro[2 * n + k]);
+                const f3 d = strict::mk(p.px.rd[k], p.px.rd[n + k], p.px.rd[2 * n + k]);
+                float t = p.px.rt[k];
+                for (int s = 0; s < p.n_spheres; ++s)
+                    if (strict::intersect_sphere(o, d, __ldg(&p.spheres[s]), t)) {
+                        p.px.best_occ[k] = ((unsigned long long)(unsigned)(p.n_tris + s) << 32) | __float_as_uint(t);
+                        break;
+                    }
+            }
+        }
+    }
+    atomicAdd(&p.counters->tests_shadow, tests);
+    atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
+    if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
 }
 
 // extension: spheres are tested after all triangles, in order, by the rays that found no triangle

@@ -126,6 +126,8 @@ struct tracer_scene_dev {
     double bb_lo[3], bb_hi[3];
     float4 *eye_table = nullptr, *light_tables = nullptr, *allcand_table = nullptr;
     std::vector<double> table_lmax; // per (light vertex, cube face): reach bound it was built for, < 0 = not built
+    int table_slots = 1;            // light vertices whose 6 face tables fit at once (and per persistent-kernel launch)
+    bool tables_resident = true;    // every light vertex has its own slot: tables are kept across lights and frames
     bool allcand_built = false;
     size_t table_stride = 0; // float4 per table
     // per-frame workspace
@@ -199,40 +201,44 @@ int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     // rays of one thread share q unless the sample positions are jittered (extension)
     return p.bands.spp_n > 1 ? launch_primary_q<R, EX, false>(p, grid, st) : launch_primary_q<R, EX, true>(p, grid, st);
 }
-template <int R, bool EX>
-int launch_shadow_t(const trk::ShadowParams &p, int grid, cudaStream_t st) {
+constexpr int WORK_INTS = trk::SL_MAXCHUNK + 8; // per-chunk work counters + the grid-barrier counter of the persistent kernel
+
+template <bool EX>
+int launch_shadow_light_t(const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem);
-    CK_CUDA(cudaFuncSetAttribute(trk::shadow_kernel<R, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trk::shadow_kernel<R, EX><<<grid, sweep::NT, smem, st>>>(p);
-    CK_CUDA(cudaGetLastError());
+    static int ctas_per_sm = 0; // co-resident CTAs: a cooperative launch may not exceed them
+    if (!ctas_per_sm) {
+        CK_CUDA(cudaFuncSetAttribute(trk::shadow_light_kernel<EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, trk::shadow_light_kernel<EX>, sweep::NT, smem));
+        if (ctas_per_sm < 1) return fail(TRACER_ERR_CUDA, "shadow_light_kernel does not fit on an SM");
+        ctas_per_sm = std::min(ctas_per_sm, sweep::MINB);
+    }
+    void *args[] = {(void *)&p, (void *)&bar};
+    CK_CUDA(cudaLaunchCooperativeKernel((const void *)trk::shadow_light_kernel<EX>, dim3((unsigned)(ctas_per_sm * g.n_sms)), dim3(sweep::NT), args, smem, st));
     return 0;
+}
+int launch_shadow_light(bool ex, const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
+    return ex ? launch_shadow_light_t<true>(p, bar, st) : launch_shadow_light_t<false>(p, bar, st);
 }
 int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
     if (R == 4) return ex ? launch_primary_t<4, true>(p, grid, st) : launch_primary_t<4, false>(p, grid, st);
     return ex ? launch_primary_t<2, true>(p, grid, st) : launch_primary_t<2, false>(p, grid, st);
 }
-int launch_shadow(int R, bool ex, const trk::ShadowParams &p, int grid, cudaStream_t st) {
-    if (R == 8) return ex ? launch_shadow_t<8, true>(p, grid, st) : launch_shadow_t<8, false>(p, grid, st);
-    if (R == 4) return ex ? launch_shadow_t<4, true>(p, grid, st) : launch_shadow_t<4, false>(p, grid, st);
-    return ex ? launch_shadow_t<2, true>(p, grid, st) : launch_shadow_t<2, false>(p, grid, st);
-}
-
 // Work decomposition of a sweep: R rays per thread (8 preferred: best amortisation of the row loads) and
 // n_slices triangle slices, chosen so that ray blocks x slices keeps every SM busy for several items.
 struct Decomp {
     int R, n_blocks, n_slices;
 };
-// (ray block, triangle slice) work items wanted per SM.  The tail of a sweep is at most one item long, but
-// every item pays for its own ray set-up: closest-hit items compute their rays (cheap) and are cut fine,
-// shadow items gather theirs from the pixel state and stay coarser.  (TRACER_ITEMS_PER_SM overrides both:
-// development knob.)
-int items_per_sm(bool closest) {
+// (ray block, triangle slice) work items wanted per resident CTA: the tail of a sweep is at most one item long, and
+// an item's set-up (ray parameters; the shadow sweeps gather theirs through the sorted list) is a few microseconds.
+// (TRACER_ITEMS_PER_CTA overrides: development knob.)
+int items_per_cta() {
     static const int forced = [] {
-        const char *e = std::getenv("TRACER_ITEMS_PER_SM");
+        const char *e = std::getenv("TRACER_ITEMS_PER_CTA");
         return e ? std::atoi(e) : 0;
     }();
-    return forced > 0 ? forced : closest ? 32 : 12;
+    return forced > 0 ? forced : 24;
 }
 
 Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks) {
@@ -249,7 +255,7 @@ Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int ext
             if ((int64_t)d.n_blocks * slices_possible >= 4 * (int64_t)n_sms) break;
         }
     }
-    const int64_t ips = items_per_sm(true);
+    const int64_t ips = (int64_t)items_per_cta() * sweep::MINB;
     const int64_t want = (ips * (int64_t)n_sms + d.n_blocks - 1) / std::max(1, d.n_blocks);
     d.n_slices = d.n_blocks >= ips * n_sms ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want, slices_possible));
     return d;
@@ -440,17 +446,23 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     TRY_CUDA(cudaMemcpy(s->light_vbase, s->h_light_vbase.data(), s->h_light_vbase.size() * sizeof(int), cudaMemcpyHostToDevice));
     TRY(dev_alloc(&s->light_verts, s->h_light_verts.size()));
     TRY_CUDA(cudaMemcpy(s->light_verts, s->h_light_verts.data(), s->h_light_verts.size() * sizeof(float), cudaMemcpyHostToDevice));
-    {
+    {   // Filter tables of the shadow sweeps: 6 cube-face tables of 48 B per triangle for every light vertex.  Two quad
+        // lights need 0.6 GB at 1M triangles; an emissive MESH with hundreds of faces would need more than the GPU has.
+        // Budget = half of the free HBM: when all vertices fit, every vertex owns a slot and its tables are built once
+        // and kept; otherwise the slots are reused batch by batch within each light (rebuilt per frame: O(N) per table,
+        // small next to the O(rays x N) sweep it serves).  The reference renders any light size, and so does this.
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const size_t need = (size_t)(6 * s->V + 2) * s->table_stride * sizeof(float4);
-        if (need > free_b / 2) {
-            tracer_cuda_scene_destroy(s);
-            return fail(TRACER_ERR_NOMEM, "light-vertex face tables (" + std::to_string(need >> 20) + " MiB) exceed half of free HBM");
-        }
+        const size_t per_vertex = 6 * s->table_stride * sizeof(float4);
+        const size_t budget = free_b / 2;
+        const char *cap_env = std::getenv("TRACER_TABLE_SLOTS"); // test knob: pretend only this many vertices fit
+        size_t fit = std::max<size_t>(1, budget / per_vertex);
+        if (cap_env) fit = std::max<size_t>(1, std::min<size_t>(fit, (size_t)std::atoll(cap_env)));
+        s->tables_resident = (size_t)s->V <= fit;
+        s->table_slots = (int)std::min<size_t>(fit, (size_t)trk::SL_MAXF / trk::NFACE);
     }
     TRY(dev_alloc(&s->eye_table, s->table_stride));
-    TRY(dev_alloc(&s->light_tables, s->table_stride * (size_t)std::max(1, 6 * s->V)));
+    TRY(dev_alloc(&s->light_tables, s->table_stride * 6 * (size_t)std::max(1, s->tables_resident ? s->V : s->table_slots)));
     TRY(dev_alloc(&s->allcand_table, s->table_stride));
     s->table_lmax.assign((size_t)6 * s->V, -1.0);
     const size_t n_groups = (size_t)s->maxF * trk::NFACE;
@@ -459,7 +471,7 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     TRY(dev_alloc(&s->blk_off, n_groups + 2));
     TRY(dev_alloc(&s->cursor, n_groups + 1));
     TRY(dev_alloc(&s->cnt_b, n_groups + 1));
-    TRY(dev_alloc(&s->work, 1));
+    TRY(dev_alloc(&s->work, (size_t)WORK_INTS));
     TRY(dev_alloc(&s->n_slices, 1));
     TRY(dev_alloc(&s->counters, 1));
     for (auto &e : s->ev) TRY_CUDA(cudaEventCreate(&e));
@@ -551,7 +563,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // bundle_cull: 1 two-phase, 2 streaming, 3 auto = two-phase unless the default sweeps are estimated to be the
     // faster of the two (tiny scenes: the mode has a fixed cost of a few ms in sorts and count read-backs)
     const double est_default_ms = (double)n_px * (double)s->n_tris * (1.0 + 0.25 * L) / 4.0e9;
-    const bool cull = o.bundle_cull == 3 ? est_default_ms > 6.0 : o.bundle_cull != 0;
+    // (the optional mode keeps every light vertex's tables resident; a light too big for that renders in the default mode)
+    const bool cull = s->tables_resident && (o.bundle_cull == 3 ? est_default_ms > 6.0 : o.bundle_cull != 0);
     if (cull) { // candidate buffers: 24 per ray + slack (a few per ray are typical), sorted with a radix sort
         const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
         if (cap > s->cand_cap) {
@@ -675,8 +688,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             if (!p.n_blocks || nb < p.n_blocks) p.n_blocks = nb, p.tiles_x = tx, p.tx_log2 = lg;
         }
         p.n_slices = d.n_slices;
-        if (p.n_blocks < items_per_sm(true) * g.n_sms) // same sizing rule as pick_decomp, on the real block count
-            p.n_slices = std::max(1, std::min((items_per_sm(true) * g.n_sms + p.n_blocks - 1) / p.n_blocks, std::max(1, n_tiles / 4)));
+        const int want_items = items_per_cta() * sweep::MINB * g.n_sms;
+        if (p.n_blocks < want_items) // same sizing rule as pick_decomp, on the real block count
+            p.n_slices = std::max(1, std::min((want_items + p.n_blocks - 1) / p.n_blocks, std::max(1, n_tiles / 4)));
         const int grid = std::min(p.n_blocks * p.n_slices, sweep::MINB * g.n_sms);
         flop_primary = bands.spp_n > 1 ? 12.0 : 2.0 * (3 + 3 * d.R) / d.R;
         if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, p, grid, st)) return rc;
@@ -815,16 +829,16 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
             continue;
         }
+        // ---- default mode: q-sorted lists, then ONE persistent cooperative kernel per batch of light vertices ----
         trk::list_prefix_kernel<<<1, 32, 0, st>>>(s->seg_count, F, s->seg_off, s->cursor);
         CK_CUDA(cudaGetLastError());
-        const int max_cblocks = (n_px + trk::CBLK - 1) / trk::CBLK + 1;
         { // group-major, q-minor order (pixels without a shadow ray carry the all-ones key and sort last)
             int group_bits = 1;
             while ((1 << group_bits) < F) ++group_bits;
             CK_CUDA(cub::DeviceRadixSort::SortPairs(s->pair_tmp, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0,
                                                     32 + group_bits + 1, st));
             CK_CUDA(cudaMemcpyAsync(s->cursor, s->seg_count, sizeof(int) * F, cudaMemcpyDeviceToDevice, st));
-            const size_t need = (size_t)max_cblocks * F;
+            const size_t need = (size_t)n_px / trk::CBLK + (size_t)F + 2;
             if (need > s->blk_cnt_cap) {
                 dev_free(s->blk_cnt);
                 s->blk_cnt_cap = 0;
@@ -835,76 +849,64 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         launches += 2;
         CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
-        // triangle chunks: after each one the still-unoccluded rays are compacted (early exit, main.cpp:324)
-        // Chunk boundaries (in tiles).  Equal chunks keep the pairs swept past a ray's occluder lowest (x1.12 at 32
-        // chunks) and win when a light has many shadow rays; with few rays (small frames, one band share of a
-        // multi-GPU frame) the per-launch tails weigh more and boundaries that start fine (1/64 of the triangles: most
-        // occluded rays find their occluder early) and coarsen geometrically win (12 launches, x1.19).
+        if (!s->allcand_built) {
+            trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table);
+            CK_CUDA(cudaGetLastError());
+            s->allcand_built = true, ++launches;
+        }
+        // Triangle chunks: after each one the still-unoccluded rays are compacted (early exit, main.cpp:324).  Equal chunks
+        // keep the pairs swept past a ray's occluder lowest (x1.12 at 32 chunks) and win when a light has many shadow
+        // rays; with few rays (small frames, one band share of a multi-GPU frame) the per-chunk tails weigh more and
+        // boundaries that start fine (1/64 of the triangles: most occluded rays find their occluder early) and coarsen
+        // geometrically win (12 chunks, x1.19).  The kernel picks the scheme from the live-ray count it finds.
         // opts.shadow_chunks asks for that many equal chunks.
-        std::vector<int> h_cnt((size_t)F);
-        CK_CUDA(cudaMemcpyAsync(h_cnt.data(), s->cursor, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
-        CK_CUDA(cudaStreamSynchronize(st));
-        int64_t n_live0 = 0;
-        for (int j = 0; j < F; ++j) n_live0 += h_cnt[j];
-        std::vector<int> bounds{0};
-        if (o.shadow_chunks > 0 || n_tiles < 64 || n_live0 >= ((int64_t)1 << 20)) {
-            const int nc = std::min(n_tiles, o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(32, n_tiles / 8)));
-            for (int c = 1; c <= nc; ++c) bounds.push_back((int)((int64_t)n_tiles * c / nc));
-        } else {
-            for (int f : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64}) bounds.push_back((int)((int64_t)n_tiles * f / 64));
-        }
-        const int n_chunks = (int)bounds.size() - 1;
-        int *list_in = s->list, *list_out = s->list_b, *cnt_in = s->cursor, *cnt_out = s->cnt_b;
-        const dim3 cgrid((unsigned)std::min(1024, (n_px + 255) / 256), (unsigned)F);
-        bool live = true;
-        int Rk = 8, max_live_group = 0; // longest group list at the last host look (lists only shrink)
-        for (int c = 0; c < n_chunks; ++c) {
-            // The host looks at the live-ray counts only at the first chunk (which face tables to build, ray
-            // block size) and every 8th chunk (stop early); everything else is sized on the device, so
-            // the chunk launches queue back to back.
-            if (c % 8 == 0) {
-                if (c) {
-                    CK_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt_in, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
-                    CK_CUDA(cudaStreamSynchronize(st));
-                }
-                int64_t n_live = 0;
-                max_live_group = 0;
-                for (int j = 0; j < F; ++j) n_live += h_cnt[j], max_live_group = std::max(max_live_group, h_cnt[j]);
-                if (n_live == 0) { // every shadow ray of this light already has its occluder
-                    live = false;
-                    break;
-                }
-                Rk = pick_decomp(n_live, bounds[c + 1] - bounds[c], g.n_sms, o.rays_per_thread, F).R;
+        trk::ShadowLightParams sp{};
+        {
+            const int nc = std::min({n_tiles, trk::SL_MAXCHUNK, o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(32, n_tiles / 8))});
+            sp.n_chunks[1] = nc;
+            for (int c = 0; c <= nc; ++c) sp.bounds[1][c] = (int)((int64_t)n_tiles * c / nc);
+            if (o.shadow_chunks > 0 || n_tiles < 64) {
+                sp.n_chunks[0] = nc;
+                std::memcpy(sp.bounds[0], sp.bounds[1], sizeof sp.bounds[0]);
+            } else {
+                const int fr[] = {0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+                sp.n_chunks[0] = 12;
+                for (int c = 0; c <= 12; ++c) sp.bounds[0][c] = (int)((int64_t)n_tiles * fr[c] / 64);
             }
-            if (c == 0)
-                if (int rc = build_face_tables(k, h_cnt)) return rc;
-            const int tile_lo = bounds[c], tile_hi = bounds[c + 1];
-            trk::chunk_prefix_kernel<<<1, 32, 0, st>>>(cnt_in, F, sweep::NT * Rk, tile_hi - tile_lo, sweep::MINB * g.n_sms, s->blk_off, cnt_out,
-                                                       s->work, s->n_slices, items_per_sm(false), 4);
-            CK_CUDA(cudaGetLastError());
-            trk::ShadowParams sp{};
-            sp.tables = s->light_tables + (size_t)s->h_light_vbase[k] * 6 * s->table_stride, sp.table_stride = s->table_stride;
-            sp.allcand = s->allcand_table;
-            sp.tile_lo = tile_lo, sp.tile_hi = tile_hi, sp.n_slices = s->n_slices;
-            sp.n_tris = s->n_tris, sp.F = F, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
-            sp.list_in = list_in, sp.seg_off = s->seg_off, sp.cnt_in = cnt_in, sp.blk_off = s->blk_off, sp.px = px;
-            sp.counters = s->counters, sp.work = s->work;
-            if (int rc = launch_shadow(Rk, o.exhaustive_strict != 0, sp, sweep::MINB * g.n_sms, st)) return rc;
-            { // order-preserving compaction: the lists stay sorted by q
-                const dim3 bgrid((unsigned)std::max(1, (max_live_group + trk::CBLK - 1) / trk::CBLK), (unsigned)F);
-                trk::compact_count_kernel<<<bgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, s->blk_cnt, max_cblocks);
-                trk::compact_scatter_kernel<<<bgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, s->best_occ, s->blk_cnt, max_cblocks,
-                                                                    list_out, cnt_out);
-                ++launches;
-            }
-            CK_CUDA(cudaGetLastError());
-            launches += 3;
-            std::swap(list_in, list_out), std::swap(cnt_in, cnt_out);
         }
-        if (live && s->n_spheres > 0) { // extension: spheres come after all triangles in the object order
-            trk::shadow_spheres_kernel<<<cgrid, 256, 0, st>>>(list_in, s->seg_off, cnt_in, F, px, n_px, s->spheres, s->n_spheres,
-                                                               s->n_tris);
-            CK_CUDA(cudaGetLastError());
+        sp.many_rays = (long long)1 << 20;
+        sp.items_per_cta = items_per_cta();
+        sp.allcand = s->allcand_table, sp.table_stride = s->table_stride;
+        sp.n_tris = s->n_tris, sp.n_tiles = n_tiles, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
+        sp.list[0] = s->list, sp.list[1] = s->list_b;
+        sp.blk_cnt = s->blk_cnt, sp.px = px, sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;
+        sp.counters = s->counters;
+        // light vertices in batches: as many as have table slots (all of them unless the light is a big mesh)
+        const int Fk = s->h_light_F[k], vb = s->h_light_vbase[k];
+        for (int b0 = 0; b0 < Fk; b0 += s->table_slots) {
+            const int b1 = std::min(Fk, b0 + s->table_slots);
+            for (int v = b0; v < b1; ++v)
+                for (int face = 0; face < 6; ++face) {
+                    // every vertex has its own slot when they all fit (tables are then kept across frames and lights);
+                    // otherwise the slots are reused batch by batch and rebuilt every time
+                    const size_t slot = s->tables_resident ? (size_t)(vb + v) : (size_t)(v - b0);
+                    const double need = (k + 1) * diag;
+                    if (s->tables_resident) {
+                        double &built = s->table_lmax[slot * 6 + face];
+                        if (built >= need) continue;
+                        built = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
+                    }
+                    const trk::TableParam tp = face_param(&s->h_light_verts[3 * (size_t)(vb + v)], face, need * 1.5);
+                    if (int rc = build_table(s, tp, s->light_tables + (slot * 6 + face) * s->table_stride, st)) return rc;
+                    ++launches;
+                }
+            sp.tables = s->light_tables + (s->tables_resident ? (size_t)(vb + b0) : 0) * 6 * s->table_stride;
+            sp.F = (b1 - b0) * trk::NFACE;
+            sp.seg_off = s->seg_off + b0 * trk::NFACE;
+            sp.cnt[0] = s->cursor + b0 * trk::NFACE, sp.cnt[1] = s->cnt_b + b0 * trk::NFACE;
+            sp.work = s->work;
+            CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int) * WORK_INTS, st));
+            if (int rc = launch_shadow_light(o.exhaustive_strict != 0, sp, (unsigned *)(s->work + trk::SL_MAXCHUNK), st)) return rc;
             ++launches;
         }
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));

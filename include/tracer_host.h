@@ -30,6 +30,20 @@ typedef struct tracer_scene_host tracer_scene_host; /* owns the arrays a tracer_
  * Returns 0 and *out, or TRACER_ERR_INVALID with the message in tracer_host_last_error(). */
 int tracer_scene_load_obj(const char *obj_path, tracer_scene_host **out);
 const tracer_scene_flat *tracer_scene_host_flat(const tracer_scene_host *scene);
+
+/* The reference's optional flatten pass, flatten_scene (src/simplify/flatten.cpp:50-82): every face of
+ * every geometry copied into one flat triangle array (geometry major, face minor, each triangle keeping
+ * its geom_id / prim_id, flatten.cpp:62-63) and sorted by the x coordinate of its FIRST vertex
+ * (comparator leftMostTriangle, flatten.cpp:20-27).  Triangle count is unchanged; what changes is the
+ * iteration order, i.e. which triangle wins a tie in t and which occluder is "first in order".
+ * std::sort (flatten.cpp:78) leaves equal keys in unspecified order; this helper sorts stably.
+ * The result is an ordinary flat scene: maximal runs of one original geometry become geometries (same
+ * material), and each light geometry is appended once more at the end in its original face order so
+ * that light.vertex[faceID] (src/main.cpp:749) is unchanged — the copies cannot alter any hit or
+ * occlusion decision (see host_io.cpp).  tracer_scene_host_origin() maps a triangle of the sorted
+ * scene back to (geom_id, prim_id) of the input. */
+int tracer_scene_flatten_sorted(const tracer_scene_flat *in, tracer_scene_host **out);
+int tracer_scene_host_origin(const tracer_scene_host *scene, const int32_t **geom, const int32_t **prim);
 void tracer_scene_host_free(tracer_scene_host *scene);
 const char *tracer_host_last_error(void);
 
