@@ -18,6 +18,8 @@ ABI_SYMBOLS = [
     "tracer_cuda_device_info", "tracer_cuda_render", "tracer_cuda_scene_create", "tracer_cuda_scene_destroy",
     "tracer_cuda_render_scene", "tracer_cuda_last_stats", "tracer_band_row_count", "tracer_cuda_assemble_bands",
     "tracer_mt19937_faceids", "tracer_cuda_fp32_peak", "tracer_camera_lookat",
+    "tracer_cuda_init_multi", "tracer_cuda_multi_gpu_count", "tracer_cuda_render_multi", "tracer_cuda_scene_create_multi",
+    "tracer_cuda_scene_destroy_multi", "tracer_cuda_render_scene_multi", "tracer_cuda_last_stats_multi",
 ]
 # include/tracer_host.h
 HOST_SYMBOLS = ["tracer_scene_load_obj", "tracer_scene_host_flat", "tracer_scene_host_free", "tracer_host_last_error",
@@ -61,6 +63,7 @@ class FrameStats(C.Structure):
         ("tests_primary", C.c_int64), ("tests_shadow", C.c_int64), ("tests_shadow_ref", C.c_int64),
         ("strict_evals", C.c_int64), ("filter_misses", C.c_int64), ("kernel_launches", C.c_int32),
         ("n_sms", C.c_int32), ("flop_primary", C.c_double), ("flop_shadow", C.c_double),
+        ("flop_primary_edges", C.c_double), ("flop_shadow_edges", C.c_double),
     ]
 
     def asdict(self):
@@ -96,6 +99,15 @@ def load():
     lib.tracer_cuda_render.argtypes = [C.POINTER(SceneFlat), C.POINTER(CameraC), C.c_int32, C.c_int32,
                                        C.POINTER(RenderOpts), C.c_void_p]
     lib.tracer_cuda_last_stats.argtypes = [C.c_void_p, C.POINTER(FrameStats)]
+    lib.tracer_cuda_init_multi.argtypes = [C.c_int]
+    lib.tracer_cuda_scene_create_multi.argtypes = [C.POINTER(SceneFlat), C.POINTER(C.c_void_p)]
+    lib.tracer_cuda_scene_destroy_multi.argtypes = [C.c_void_p]
+    lib.tracer_cuda_scene_destroy_multi.restype = None
+    lib.tracer_cuda_render_scene_multi.argtypes = [C.c_void_p, C.POINTER(CameraC), C.c_int32, C.c_int32,
+                                                   C.POINTER(RenderOpts), C.c_void_p]
+    lib.tracer_cuda_render_multi.argtypes = [C.POINTER(SceneFlat), C.POINTER(CameraC), C.c_int32, C.c_int32,
+                                             C.POINTER(RenderOpts), C.c_void_p]
+    lib.tracer_cuda_last_stats_multi.argtypes = [C.c_void_p, C.POINTER(FrameStats)]
     lib.tracer_band_row_count.argtypes = [C.c_int32] * 4
     lib.tracer_band_row_count.restype = C.c_int32
     lib.tracer_cuda_assemble_bands.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

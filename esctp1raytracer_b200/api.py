@@ -224,8 +224,66 @@ class ResidentScene:
             pass
 
 
+class MultiRenderer:
+    """All GPUs of the box behind one call, one process (tracer_cuda_init_multi): interleaved 8-row bands, scene
+    replicated, packed bands gathered on GPU 0 with NCCL inside the library.  The multi-process form (one rank per
+    GPU, torch.distributed) lives in dist.py; both produce the bytes a single GPU produces."""
+
+    def __init__(self, n_gpus: int):
+        self.lib = _lib.load()
+        _lib.check(self.lib.tracer_cuda_init_multi(n_gpus))
+        self.n_gpus = n_gpus
+
+    def upload(self, scene: Scene):
+        h = C.c_void_p()
+        cs = scene.c_struct()
+        _lib.check(self.lib.tracer_cuda_scene_create_multi(C.byref(cs), C.byref(h)))
+        return _MultiScene(self, scene, h)
+
+    def trace(self, scene, camera: "Camera", width: int, height: int, *, rng_mode=RNG_HASH, seed=1, faceid=None,
+              samples_per_pixel=0, bundle_cull=False, band_rows=0) -> "Frame":
+        sc = scene.scene if isinstance(scene, _MultiScene) else scene
+        o = _lib.RenderOpts()
+        o.struct_size = C.sizeof(_lib.RenderOpts)
+        o.rng_mode, o.seed = rng_mode, seed & 0xFFFFFFFF
+        keep = None
+        if rng_mode == RNG_EXPLICIT:
+            keep = np.ascontiguousarray(faceid, np.int32)
+            o.faceid = _ptr(keep, C.c_int32)
+        o.samples_per_pixel, o.bundle_cull, o.band_rows = samples_per_pixel, int(bundle_cull), band_rows
+        out = np.zeros((height, width, 3), np.uint8)
+        stats = {}
+        if isinstance(scene, _MultiScene):
+            _lib.check(self.lib.tracer_cuda_render_scene_multi(scene.handle, C.byref(camera.c), width, height, C.byref(o),
+                                                               out.ctypes.data_as(C.c_void_p)))
+            st = _lib.FrameStats()
+            _lib.check(self.lib.tracer_cuda_last_stats_multi(scene.handle, C.byref(st)))
+            stats = st.asdict()
+        else:
+            cs = sc.c_struct()
+            _lib.check(self.lib.tracer_cuda_render_multi(C.byref(cs), C.byref(camera.c), width, height, C.byref(o),
+                                                         out.ctypes.data_as(C.c_void_p)))
+        return Frame(rgb8=out, stats=stats)
+
+
+class _MultiScene:
+    def __init__(self, renderer, scene, handle):
+        self.renderer, self.scene, self.handle = renderer, scene, handle
+
+    def close(self):
+        if self.handle:
+            self.renderer.lib.tracer_cuda_scene_destroy_multi(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Renderer:
-    """One CUDA device per process (tracer_cuda_init)."""
+    """One CUDA device (tracer_cuda_init); see MultiRenderer for all GPUs of the box in one process."""
 
     def __init__(self, device: int = 0):
         self.lib = _lib.load()

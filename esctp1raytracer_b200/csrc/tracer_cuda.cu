@@ -13,6 +13,9 @@
 
 #include "../../include/tracer_cuda.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <thread>
 
 #include "kernels.cuh"
 
@@ -21,14 +24,6 @@ extern "C" int tracer__mt19937_scan(uint32_t seed, int32_t n_lights, const int32
 
 namespace {
 
-
-struct Ctx {
-    bool inited = false;
-    int device = -1;
-    int n_sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaDeviceProp prop{};
-} g;
 
 thread_local std::string g_err = "";
 
@@ -97,24 +92,45 @@ struct Pool {
         std::lock_guard<std::mutex> lk(mu);
         release_all_locked();
     }
-} g_pool;
+};
+
+// One context per GPU.  tracer_cuda_init(d) sets up device d and makes it the process's CURRENT context (what
+// scene_create uses); tracer_cuda_init_multi sets up several.  A resident scene remembers its context.
+constexpr int MAX_GPUS = 16;
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    Pool pool;
+    int sl_ctas[2] = {0, 0}; // co-resident CTAs per SM of shadow_light_kernel<false/true> (cooperative launch limit)
+} g_ctx[MAX_GPUS];
+Ctx *g_cur = nullptr;
+thread_local Pool *t_pool = nullptr; // pool of the context the calling thread is working on
 
 template <typename T>
 int dev_alloc(T **p, size_t n) {
     if (n == 0) n = 1;
-    *p = (T *)g_pool.alloc(n * sizeof(T));
+    *p = (T *)t_pool->alloc(n * sizeof(T));
     if (!*p) return fail(TRACER_ERR_NOMEM, "device memory allocation of " + std::to_string((n * sizeof(T)) >> 20) + " MiB failed");
     return 0;
 }
 template <typename T>
 void dev_free(T *&p) {
-    g_pool.release((void *)p);
+    t_pool->release((void *)p);
     p = nullptr;
 }
 
 }  // namespace
 
+struct tracer_scene_multi {
+    std::vector<tracer_scene_dev *> dev; // one replica per GPU
+    tracer_frame_stats stats{};
+};
+
 struct tracer_scene_dev {
+    Ctx *ctx = nullptr;
     int n_geoms = 0, n_tris = 0, n_pad = 0, n_lights = 0, n_spheres = 0, V = 0;
     float *tri_verts = nullptr, *tri_normals = nullptr, *geom_material = nullptr, *sphere_material = nullptr;
     int *tri_geom = nullptr, *geom_has_normals = nullptr;
@@ -201,12 +217,82 @@ int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     // rays of one thread share q unless the sample positions are jittered (extension)
     return p.bands.spp_n > 1 ? launch_primary_q<R, EX, false>(p, grid, st) : launch_primary_q<R, EX, true>(p, grid, st);
 }
+int scene_create_on(Ctx &g, const tracer_scene_flat *sc, tracer_scene_dev **out);
+
+// NCCL is needed by the multi-GPU entry points only: resolved at tracer_cuda_init_multi, so that a single-GPU user
+// (and a box without NCCL) never touches it.  Types come from <nccl.h>; libnccl.so.2 is whichever copy the process
+// already maps (torch bundles one) or the system's.
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (lib) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) {
+            err = std::string("multi-GPU needs NCCL: ") + dlerror();
+            return false;
+        }
+        auto sym = [&](const char *n) { return dlsym(lib, n); };
+        CommInitAll = (decltype(CommInitAll))sym("ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!CommInitAll || !CommDestroy || !GroupStart || !GroupEnd || !Send || !Recv || !GetErrorString) {
+            err = "libnccl lacks a symbol this library needs";
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+} g_nccl;
+
+struct Multi {
+    int n = 0; // GPUs set up by tracer_cuda_init_multi (0: not called)
+    bool have_comms = false;
+    ncclComm_t comms[MAX_GPUS] = {};
+    uint8_t *band_buf[MAX_GPUS] = {}; // GPU d's packed bands (send buffer), d > 0
+    size_t band_cap[MAX_GPUS] = {};
+    uint8_t *gathered = nullptr, *frame = nullptr; // GPU 0
+    size_t gathered_cap = 0, frame_cap = 0;
+} g_multi;
+
+void multi_shutdown() {
+    for (int d = 0; d < MAX_GPUS; ++d) {
+        if (g_multi.have_comms && g_multi.comms[d] && g_nccl.CommDestroy) g_nccl.CommDestroy(g_multi.comms[d]);
+        g_multi.comms[d] = nullptr;
+        if (g_multi.band_buf[d] && g_ctx[d].inited) {
+            cudaSetDevice(d);
+            g_ctx[d].pool.release(g_multi.band_buf[d]);
+        }
+        g_multi.band_buf[d] = nullptr, g_multi.band_cap[d] = 0;
+    }
+    if (g_ctx[0].inited) {
+        cudaSetDevice(0);
+        g_ctx[0].pool.release(g_multi.gathered), g_ctx[0].pool.release(g_multi.frame);
+    }
+    g_multi.gathered = g_multi.frame = nullptr;
+    g_multi.gathered_cap = g_multi.frame_cap = 0;
+    g_multi.have_comms = false;
+    g_multi.n = 0;
+}
 constexpr int WORK_INTS = trk::SL_MAXCHUNK + 8; // per-chunk work counters + the grid-barrier counter of the persistent kernel
 
 template <bool EX>
-int launch_shadow_light_t(const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
+int launch_shadow_light_t(Ctx &g, const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem);
-    static int ctas_per_sm = 0; // co-resident CTAs: a cooperative launch may not exceed them
+    int &ctas_per_sm = g.sl_ctas[EX ? 1 : 0]; // co-resident CTAs: a cooperative launch may not exceed them
     if (!ctas_per_sm) {
         CK_CUDA(cudaFuncSetAttribute(trk::shadow_light_kernel<EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, trk::shadow_light_kernel<EX>, sweep::NT, smem));
@@ -217,8 +303,8 @@ int launch_shadow_light_t(const trk::ShadowLightParams &p, unsigned *bar, cudaSt
     CK_CUDA(cudaLaunchCooperativeKernel((const void *)trk::shadow_light_kernel<EX>, dim3((unsigned)(ctas_per_sm * g.n_sms)), dim3(sweep::NT), args, smem, st));
     return 0;
 }
-int launch_shadow_light(bool ex, const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
-    return ex ? launch_shadow_light_t<true>(p, bar, st) : launch_shadow_light_t<false>(p, bar, st);
+int launch_shadow_light(Ctx &g, bool ex, const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
+    return ex ? launch_shadow_light_t<true>(g, p, bar, st) : launch_shadow_light_t<false>(g, p, bar, st);
 }
 int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
@@ -290,7 +376,8 @@ int tracer_cuda_init(int device_ordinal) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
         return fail(TRACER_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0"));
-    if (device_ordinal < 0 || device_ordinal >= n) return fail(TRACER_ERR_INVALID, "device ordinal out of range");
+    if (device_ordinal < 0 || device_ordinal >= n || device_ordinal >= MAX_GPUS) return fail(TRACER_ERR_INVALID, "device ordinal out of range");
+    Ctx &g = g_ctx[device_ordinal];
     CK_CUDA(cudaSetDevice(device_ordinal));
     CK_CUDA(cudaGetDeviceProperties(&g.prop, device_ordinal));
     if (g.prop.major < 10)
@@ -299,23 +386,32 @@ int tracer_cuda_init(int device_ordinal) {
     if (!g.stream) CK_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     g.device = device_ordinal;
     g.n_sms = g.prop.multiProcessorCount;
-    g_pool.limit = g.prop.totalGlobalMem / 4;
+    g.pool.limit = g.prop.totalGlobalMem / 4;
     g.inited = true;
+    g_cur = &g;
+    t_pool = &g.pool;
     return TRACER_OK;
 }
 
 void tracer_cuda_shutdown(void) {
-    g_pool.release_all();
-    if (g.stream) cudaStreamDestroy(g.stream);
-    g.stream = nullptr;
-    g.inited = false;
+    multi_shutdown();
+    for (Ctx &g : g_ctx) {
+        if (!g.inited) continue;
+        cudaSetDevice(g.device);
+        g.pool.release_all();
+        if (g.stream) cudaStreamDestroy(g.stream);
+        g.stream = nullptr;
+        g.inited = false;
+    }
+    g_cur = nullptr;
 }
 
 int tracer_cuda_device_info(tracer_device_info *out) {
     if (!out) return fail(TRACER_ERR_INVALID, "null out");
-    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    if (!g_cur) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    const Ctx &g = *g_cur;
     std::memset(out, 0, sizeof *out);
-    std::snprintf(out->name, sizeof out->name, "%s", g.prop.name);
+    std::snprintf(out->name, sizeof out->name, "%.127s", g.prop.name);
     out->sm_count = g.prop.multiProcessorCount;
     out->cc_major = g.prop.major, out->cc_minor = g.prop.minor;
     int khz = 0;
@@ -328,6 +424,11 @@ int tracer_cuda_device_info(tracer_device_info *out) {
 
 void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     if (!s) return;
+    if (s->ctx) {
+        cudaSetDevice(s->ctx->device);
+        cudaDeviceSynchronize(); // nothing of this scene is in flight (on any stream) when its blocks return to the pool
+        t_pool = &s->ctx->pool;
+    }
     dev_free(s->tri_verts), dev_free(s->tri_normals), dev_free(s->geom_material), dev_free(s->sphere_material);
     dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
     dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables), dev_free(s->allcand_table);
@@ -339,7 +440,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->n_slices);
     dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count), dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
     dev_free(s->boxes), dev_free(s->blk_cnt);
-    g_pool.release(s->sort_tmp), g_pool.release(s->pair_tmp);
+    t_pool->release(s->sort_tmp), t_pool->release(s->pair_tmp);
     dev_free(s->counters);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -348,9 +449,18 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
 }
 
 int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out) {
+    if (!g_cur) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    return scene_create_on(*g_cur, sc, out);
+}
+
+}  // extern "C"
+
+namespace {
+int scene_create_on(Ctx &g, const tracer_scene_flat *sc, tracer_scene_dev **out) {
     if (!out) return fail(TRACER_ERR_INVALID, "null out");
     *out = nullptr;
     if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    t_pool = &g.pool;
     if (!sc || sc->n_geoms < 0 || sc->n_lights < 0 || sc->n_spheres < 0) return fail(TRACER_ERR_INVALID, "bad scene");
     if (sc->n_geoms > 0 && (!sc->geom_tri_offset || !sc->geom_material)) return fail(TRACER_ERR_INVALID, "null scene array");
     const int G = sc->n_geoms;
@@ -367,6 +477,7 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
 
     CK_CUDA(cudaSetDevice(g.device));
     auto *s = new tracer_scene_dev();
+    s->ctx = &g;
     s->n_geoms = G, s->n_tris = N, s->n_lights = sc->n_lights, s->n_spheres = sc->n_spheres;
     s->n_pad = std::max(1, (N + cull::CTILE - 1) / cull::CTILE) * cull::CTILE; // multiple of both tile sizes
     s->table_stride = (size_t)s->n_pad * 3;
@@ -387,25 +498,25 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
         }                                                                                                   \
     } while (0)
     TRY(dev_alloc(&s->tri_verts, (size_t)N * 9));
-    TRY_CUDA(cudaMemcpy(s->tri_verts, sc->tri_verts, (size_t)N * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_CUDA(cudaMemcpyAsync(s->tri_verts, sc->tri_verts, (size_t)N * 9 * sizeof(float), cudaMemcpyHostToDevice, g.stream));
     if (any_normals) {
         TRY(dev_alloc(&s->tri_normals, (size_t)N * 9));
-        TRY_CUDA(cudaMemcpy(s->tri_normals, sc->tri_normals, (size_t)N * 9 * sizeof(float), cudaMemcpyHostToDevice));
+        TRY_CUDA(cudaMemcpyAsync(s->tri_normals, sc->tri_normals, (size_t)N * 9 * sizeof(float), cudaMemcpyHostToDevice, g.stream));
         TRY(dev_alloc(&s->geom_has_normals, (size_t)G));
-        TRY_CUDA(cudaMemcpy(s->geom_has_normals, sc->geom_has_normals, (size_t)G * sizeof(int), cudaMemcpyHostToDevice));
+        TRY_CUDA(cudaMemcpyAsync(s->geom_has_normals, sc->geom_has_normals, (size_t)G * sizeof(int), cudaMemcpyHostToDevice, g.stream));
     }
     TRY(dev_alloc(&s->geom_material, (size_t)G * 13));
-    TRY_CUDA(cudaMemcpy(s->geom_material, sc->geom_material, (size_t)G * 13 * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_CUDA(cudaMemcpyAsync(s->geom_material, sc->geom_material, (size_t)G * 13 * sizeof(float), cudaMemcpyHostToDevice, g.stream));
+    std::vector<int> tg((size_t)std::max(N, 1)); // lives until the upload has been waited for
     {
-        std::vector<int> tg((size_t)std::max(N, 1));
         for (int g2 = 0; g2 < G; ++g2)
             for (int t = sc->geom_tri_offset[g2]; t < sc->geom_tri_offset[g2 + 1]; ++t) tg[t] = g2;
         TRY(dev_alloc(&s->tri_geom, (size_t)N));
-        TRY_CUDA(cudaMemcpy(s->tri_geom, tg.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+        TRY_CUDA(cudaMemcpyAsync(s->tri_geom, tg.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, g.stream));
     }
     if (sc->n_spheres > 0) {
         TRY(dev_alloc(&s->spheres, (size_t)sc->n_spheres));
-        TRY_CUDA(cudaMemcpy(s->spheres, sc->sphere_cr, (size_t)sc->n_spheres * 4 * sizeof(float), cudaMemcpyHostToDevice));
+        TRY_CUDA(cudaMemcpyAsync(s->spheres, sc->sphere_cr, (size_t)sc->n_spheres * 4 * sizeof(float), cudaMemcpyHostToDevice, g.stream));
         TRY(dev_alloc(&s->sphere_material, (size_t)sc->n_spheres * 13));
         TRY_CUDA(cudaMemcpy(s->sphere_material, sc->sphere_material, (size_t)sc->n_spheres * 13 * sizeof(float),
                             cudaMemcpyHostToDevice));
@@ -443,9 +554,9 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     }
     s->V = s->h_light_vbase.back();
     TRY(dev_alloc(&s->light_vbase, s->h_light_vbase.size()));
-    TRY_CUDA(cudaMemcpy(s->light_vbase, s->h_light_vbase.data(), s->h_light_vbase.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRY_CUDA(cudaMemcpyAsync(s->light_vbase, s->h_light_vbase.data(), s->h_light_vbase.size() * sizeof(int), cudaMemcpyHostToDevice, g.stream));
     TRY(dev_alloc(&s->light_verts, s->h_light_verts.size()));
-    TRY_CUDA(cudaMemcpy(s->light_verts, s->h_light_verts.data(), s->h_light_verts.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_CUDA(cudaMemcpyAsync(s->light_verts, s->h_light_verts.data(), s->h_light_verts.size() * sizeof(float), cudaMemcpyHostToDevice, g.stream));
     {   // Filter tables of the shadow sweeps: 6 cube-face tables of 48 B per triangle for every light vertex.  Two quad
         // lights need 0.6 GB at 1M triangles; an emissive MESH with hundreds of faces would need more than the GPU has.
         // Budget = half of the free HBM: when all vertices fit, every vertex owns a slot and its tables are built once
@@ -477,16 +588,26 @@ int tracer_cuda_scene_create(const tracer_scene_flat *sc, tracer_scene_dev **out
     for (auto &e : s->ev) TRY_CUDA(cudaEventCreate(&e));
     s->ev_shadow.resize(2 * (size_t)std::max(1, s->n_lights));
     for (auto &e : s->ev_shadow) TRY_CUDA(cudaEventCreate(&e));
+    // uploads were queued on the context's stream (truly asynchronous from pinned host memory): one wait for all
+    if (cudaError_t e_ = cudaStreamSynchronize(g.stream); e_ != cudaSuccess) {
+        tracer_cuda_scene_destroy(s);
+        return fail(TRACER_ERR_CUDA, std::string("scene upload failed: ") + cudaGetErrorString(e_));
+    }
 #undef TRY
 #undef TRY_CUDA
     *out = s;
     return TRACER_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int32_t W, int32_t H,
                              const tracer_render_opts *opts_in, uint8_t *rgb_out) {
-    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
     if (!s || !cam || !rgb_out) return fail(TRACER_ERR_INVALID, "null argument");
+    if (!s->ctx || !s->ctx->inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    Ctx &g = *s->ctx;
+    t_pool = &g.pool;
     if (W < 2 || H < 2) return fail(TRACER_ERR_INVALID, "width and height must be >= 2 (the reference divides by W-1, H-1)");
     if ((int64_t)W * H > (int64_t)1 << 30) return fail(TRACER_ERR_INVALID, "frame too large");
     tracer_render_opts o;
@@ -569,11 +690,11 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
         if (cap > s->cand_cap) {
             dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count);
-            g_pool.release(s->sort_tmp);
+            t_pool->release(s->sort_tmp);
             s->sort_tmp = nullptr, s->cand_cap = 0;
             if (dev_alloc(&s->cand_a, cap) || dev_alloc(&s->cand_b, cap) || dev_alloc(&s->cand_count, 1)) return TRACER_ERR_NOMEM;
             CK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, s->sort_bytes, s->cand_a, s->cand_b, cap, 0, 64, st));
-            if (!(s->sort_tmp = g_pool.alloc(s->sort_bytes))) return fail(TRACER_ERR_NOMEM, "sort scratch");
+            if (!(s->sort_tmp = t_pool->alloc(s->sort_bytes))) return fail(TRACER_ERR_NOMEM, "sort scratch");
             s->cand_cap = cap;
         }
     }
@@ -581,11 +702,11 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // bundle-cull mode: ordered by (group, Morton code of (p,q)).  Either way a radix sort of (key, pixel) pairs.
     if (s->rkey_npx < n_px) {
         dev_free(s->rkey), dev_free(s->rkey_sorted), dev_free(s->iota);
-        g_pool.release(s->pair_tmp);
+        t_pool->release(s->pair_tmp);
         s->pair_tmp = nullptr;
         if (dev_alloc(&s->rkey, (size_t)n_px) || dev_alloc(&s->rkey_sorted, (size_t)n_px) || dev_alloc(&s->iota, (size_t)n_px)) return TRACER_ERR_NOMEM;
         CK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, s->pair_bytes, s->rkey, s->rkey_sorted, s->iota, s->list, n_px, 0, 64, st));
-        if (!(s->pair_tmp = g_pool.alloc(s->pair_bytes))) return fail(TRACER_ERR_NOMEM, "sort scratch");
+        if (!(s->pair_tmp = t_pool->alloc(s->pair_bytes))) return fail(TRACER_ERR_NOMEM, "sort scratch");
         trk::iota_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(s->iota, n_px);
         CK_CUDA(cudaGetLastError());
         s->rkey_npx = n_px;
@@ -906,7 +1027,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.cnt[0] = s->cursor + b0 * trk::NFACE, sp.cnt[1] = s->cnt_b + b0 * trk::NFACE;
             sp.work = s->work;
             CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int) * WORK_INTS, st));
-            if (int rc = launch_shadow_light(o.exhaustive_strict != 0, sp, (unsigned *)(s->work + trk::SL_MAXCHUNK), st)) return rc;
+            if (int rc = launch_shadow_light(g, o.exhaustive_strict != 0, sp, (unsigned *)(s->work + trk::SL_MAXCHUNK), st)) return rc;
             ++launches;
         }
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
@@ -977,7 +1098,11 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.kernel_launches = launches;
     // shadow sweeps: 6 FFMA per pair, or (6 + 3R) FFMA per R pairs when a thread's R = 8 rays share the q-terms
-    s->stats.flop_primary = flop_primary, s->stats.flop_shadow = cull ? 0.0 : 2.0 * (6 + 3 * 8) / 8;
+    // FP32 flops the sweeps execute per swept pair (all in the FMA pipe; FFMA = 2, FMUL = 1): the three edge rows, plus
+    // the conjunction x'*y'*z' accumulated per pair (FMUL + FFMA = 3).  Shadow sweeps: (6 + 3R) FFMA per R pairs for the
+    // rows when a thread's R = 8 q-sorted rays share one q-term per row.
+    s->stats.flop_primary_edges = flop_primary, s->stats.flop_shadow_edges = cull ? 0.0 : 2.0 * (6 + 3 * 8) / 8;
+    s->stats.flop_primary = cull ? 0.0 : flop_primary + 3.0, s->stats.flop_shadow = cull ? 0.0 : s->stats.flop_shadow_edges + 3.0;
     if (hc.cull_overflow)
         return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow; use the default mode for this scene");
     if (getenv("TRACER_CULL_DIAG"))
@@ -994,6 +1119,7 @@ int tracer_cuda_last_stats(tracer_scene_dev *s, tracer_frame_stats *out) {
 
 int tracer_cuda_render(const tracer_scene_flat *scene, const tracer_camera *cam, int32_t width, int32_t height,
                        const tracer_render_opts *opts, uint8_t *rgb_out) {
+    if (g_multi.n > 1) return tracer_cuda_render_multi(scene, cam, width, height, opts, rgb_out);
     tracer_scene_dev *s = nullptr;
     if (int rc = tracer_cuda_scene_create(scene, &s)) return rc;
     const int rc = tracer_cuda_render_scene(s, cam, width, height, opts, rgb_out);
@@ -1003,7 +1129,8 @@ int tracer_cuda_render(const tracer_scene_flat *scene, const tracer_camera *cam,
 
 int tracer_cuda_assemble_bands(const uint8_t *gathered_dev, uint8_t *frame_dev, int32_t width, int32_t height,
                                int32_t band_rows, int32_t band_count, int32_t rows_per_rank_padded, void *cuda_stream) {
-    if (!g.inited) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    if (!g_cur) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init not called");
+    Ctx &g = *g_cur;
     if (!gathered_dev || !frame_dev || width <= 0 || height <= 0 || band_rows <= 0 || band_count <= 0)
         return fail(TRACER_ERR_INVALID, "bad argument");
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g.stream;
@@ -1012,6 +1139,187 @@ int tracer_cuda_assemble_bands(const uint8_t *gathered_dev, uint8_t *frame_dev, 
     CK_CUDA(cudaGetLastError());
     CK_CUDA(cudaStreamSynchronize(st));
     return TRACER_OK;
+}
+
+
+/* ---- all GPUs of one box behind one call ---------------------------------------------------------------------
+ * one process, a context (stream, pool, scene replica) per GPU, one host thread per GPU while a frame
+ * renders, ONE NCCL communicator set (ncclCommInitAll).  PPM rows are cut into 8-row bands, band b -> GPU b % n;
+ * every GPU quantises its bands straight into its send buffer, the packed bands go to GPU 0 with grouped
+ * ncclSend / ncclRecv over NVLink (this NCCL has no ncclGather), GPU 0 scatters them into PPM order. */
+int tracer_cuda_init_multi(int n_gpus) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(TRACER_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0"));
+    if (n_gpus < 1 || n_gpus > n || n_gpus > MAX_GPUS) return fail(TRACER_ERR_INVALID, "n_gpus out of range (" + std::to_string(n) + " devices visible)");
+    multi_shutdown();
+    for (int d = n_gpus - 1; d >= 0; --d) // device 0 last: it stays the current context
+        if (int rc = tracer_cuda_init(d)) return rc;
+    if (n_gpus > 1) {
+        std::string err;
+        if (!g_nccl.load(err)) return fail(TRACER_ERR_CUDA, err);
+        int devs[MAX_GPUS];
+        for (int d = 0; d < n_gpus; ++d) devs[d] = d;
+        const ncclResult_t r = g_nccl.CommInitAll(g_multi.comms, n_gpus, devs);
+        if (r != ncclSuccess) return fail(TRACER_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+        g_multi.have_comms = true;
+    }
+    g_multi.n = n_gpus;
+    return TRACER_OK;
+}
+
+int tracer_cuda_multi_gpu_count(void) { return g_multi.n; }
+
+void tracer_cuda_scene_destroy_multi(tracer_scene_multi *ms) {
+    if (!ms) return;
+    for (tracer_scene_dev *d : ms->dev) tracer_cuda_scene_destroy(d);
+    delete ms;
+}
+
+int tracer_cuda_scene_create_multi(const tracer_scene_flat *sc, tracer_scene_multi **out) {
+    if (!out) return fail(TRACER_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (g_multi.n < 1) return fail(TRACER_ERR_NO_DEVICE, "tracer_cuda_init_multi not called");
+    auto *ms = new tracer_scene_multi();
+    ms->dev.assign((size_t)g_multi.n, nullptr);
+    std::vector<int> rc((size_t)g_multi.n, 0);
+    std::vector<std::string> err((size_t)g_multi.n);
+    auto work = [&](int d) { // replicate: every GPU uploads over its own PCIe link
+        rc[d] = scene_create_on(g_ctx[d], sc, &ms->dev[d]);
+        if (rc[d]) err[d] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < g_multi.n; ++d) th.emplace_back(work, d);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int d = 0; d < g_multi.n; ++d)
+        if (rc[d]) {
+            const int r = rc[d];
+            const std::string m = "GPU " + std::to_string(d) + ": " + err[d];
+            tracer_cuda_scene_destroy_multi(ms);
+            return fail(r, m);
+        }
+    *out = ms;
+    return TRACER_OK;
+}
+
+int tracer_cuda_render_scene_multi(tracer_scene_multi *ms, const tracer_camera *cam, int32_t W, int32_t H,
+                                   const tracer_render_opts *opts_in, uint8_t *rgb_out) {
+    if (!ms || !cam || !rgb_out) return fail(TRACER_ERR_INVALID, "null argument");
+    const int n = (int)ms->dev.size();
+    if (n != g_multi.n || n < 1) return fail(TRACER_ERR_STATE, "scene was created for a different GPU set");
+    if (n == 1) {
+        const int rc = tracer_cuda_render_scene(ms->dev[0], cam, W, H, opts_in, rgb_out);
+        ms->stats = ms->dev[0]->stats;
+        return rc;
+    }
+    tracer_render_opts o;
+    std::memset(&o, 0, sizeof o);
+    if (opts_in) std::memcpy(&o, opts_in, std::min<size_t>(sizeof o, opts_in->struct_size ? opts_in->struct_size : sizeof o));
+    if (o.band_count > 1) return fail(TRACER_ERR_INVALID, "the multi-GPU call partitions the frame itself: leave band_count at 0");
+    if (o.out_tri || o.out_t || o.out_v || o.out_occ_tri || o.out_rgb) return fail(TRACER_ERR_INVALID, "debug outputs are per-GPU: use tracer_cuda_render_scene with bands");
+    if (W < 2 || H < 2 || (int64_t)W * H > (int64_t)1 << 30) return fail(TRACER_ERR_INVALID, "bad frame size");
+    const int band_rows = o.band_rows > 0 ? o.band_rows : 8;
+    int rows_pad = 0;
+    for (int d = 0; d < n; ++d) rows_pad = std::max(rows_pad, tracer_band_row_count(H, band_rows, d, n));
+    const size_t row_bytes = (size_t)W * 3, pad_bytes = (size_t)rows_pad * row_bytes, frame_bytes = row_bytes * H;
+    // device 0: gather buffer (slot d = GPU d's packed bands; GPU 0 renders straight into slot 0) and the assembled frame
+    Ctx &g0 = g_ctx[0];
+    CK_CUDA(cudaSetDevice(0));
+    t_pool = &g0.pool;
+    if (g_multi.gathered_cap < pad_bytes * n + 64) {
+        dev_free(g_multi.gathered);
+        g_multi.gathered_cap = 0;
+        if (dev_alloc(&g_multi.gathered, pad_bytes * n + 64)) return TRACER_ERR_NOMEM;
+        g_multi.gathered_cap = pad_bytes * n + 64;
+    }
+    if (g_multi.frame_cap < frame_bytes + 64) {
+        dev_free(g_multi.frame);
+        g_multi.frame_cap = 0;
+        if (dev_alloc(&g_multi.frame, frame_bytes + 64)) return TRACER_ERR_NOMEM;
+        g_multi.frame_cap = frame_bytes + 64;
+    }
+    std::vector<int> rc((size_t)n, 0);
+    std::vector<std::string> err((size_t)n);
+    auto work = [&](int d) {
+        Ctx &g = g_ctx[d];
+        uint8_t *dst = g_multi.gathered; // GPU 0
+        if (d > 0) {
+            if (cudaSetDevice(d) != cudaSuccess) { rc[d] = TRACER_ERR_CUDA, err[d] = "cudaSetDevice"; return; }
+            t_pool = &g.pool;
+            if (g_multi.band_cap[d] < pad_bytes + 64) {
+                dev_free(g_multi.band_buf[d]);
+                g_multi.band_cap[d] = 0;
+                if (dev_alloc(&g_multi.band_buf[d], pad_bytes + 64)) { rc[d] = TRACER_ERR_NOMEM, err[d] = g_err; return; }
+                g_multi.band_cap[d] = pad_bytes + 64;
+            }
+            dst = g_multi.band_buf[d];
+        }
+        tracer_render_opts od = o;
+        od.struct_size = sizeof od;
+        od.band_rows = band_rows, od.band_index = d, od.band_count = n;
+        od.rgb_out_is_device = 1, od.cuda_stream = nullptr; // the GPU's own stream: the send below is queued behind the frame
+        rc[d] = tracer_cuda_render_scene(ms->dev[d], cam, W, H, &od, dst);
+        if (rc[d]) err[d] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < n; ++d) th.emplace_back(work, d);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n; ++d)
+        if (rc[d]) return fail(rc[d], "GPU " + std::to_string(d) + ": " + err[d]);
+    // the one exchange step: packed bands -> GPU 0
+    ncclResult_t r = g_nccl.GroupStart();
+    for (int d = 1; d < n && r == ncclSuccess; ++d) {
+        const size_t bytes = (size_t)tracer_band_row_count(H, band_rows, d, n) * row_bytes;
+        if (!bytes) continue;
+        r = g_nccl.Send(g_multi.band_buf[d], bytes, ncclUint8, 0, g_multi.comms[d], g_ctx[d].stream);
+        if (r == ncclSuccess) r = g_nccl.Recv(g_multi.gathered + (size_t)d * pad_bytes, bytes, ncclUint8, d, g_multi.comms[0], g0.stream);
+    }
+    const ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess)
+        return fail(TRACER_ERR_CUDA, std::string("NCCL band gather: ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+    CK_CUDA(cudaSetDevice(0));
+    uint8_t *frame_dst = o.rgb_out_is_device ? rgb_out : g_multi.frame;
+    trk::assemble_bands_kernel<<<g0.n_sms * 8, 256, 0, g0.stream>>>(g_multi.gathered, frame_dst, W, H, band_rows, n, rows_pad);
+    CK_CUDA(cudaGetLastError());
+    if (!o.rgb_out_is_device) CK_CUDA(cudaMemcpyAsync(rgb_out, g_multi.frame, frame_bytes, cudaMemcpyDeviceToHost, g0.stream));
+    for (int d = n - 1; d >= 0; --d) { // the senders' streams too: their buffers are reused by the next frame
+        CK_CUDA(cudaSetDevice(d));
+        CK_CUDA(cudaStreamSynchronize(g_ctx[d].stream));
+    }
+    // whole-frame statistics: counts summed over the GPUs, times of the slowest
+    tracer_frame_stats t{};
+    for (int d = 0; d < n; ++d) {
+        const tracer_frame_stats &x = ms->dev[d]->stats;
+        t.ms_total = std::max(t.ms_total, x.ms_total), t.ms_primary = std::max(t.ms_primary, x.ms_primary);
+        t.ms_shadow = std::max(t.ms_shadow, x.ms_shadow), t.ms_other = std::max(t.ms_other, x.ms_other);
+        t.n_pixels += x.n_pixels, t.n_primary_rays += x.n_primary_rays, t.n_shadow_rays += x.n_shadow_rays;
+        t.tests_primary += x.tests_primary, t.tests_shadow += x.tests_shadow, t.tests_shadow_ref += x.tests_shadow_ref;
+        t.strict_evals += x.strict_evals, t.filter_misses += x.filter_misses, t.kernel_launches += x.kernel_launches;
+        t.n_sms += x.n_sms;
+        t.flop_primary = x.flop_primary, t.flop_shadow = x.flop_shadow;
+        t.flop_primary_edges = x.flop_primary_edges, t.flop_shadow_edges = x.flop_shadow_edges;
+    }
+    t.kernel_launches += 1; // assemble
+    ms->stats = t;
+    return TRACER_OK;
+}
+
+int tracer_cuda_last_stats_multi(tracer_scene_multi *ms, tracer_frame_stats *out) {
+    if (!ms || !out) return fail(TRACER_ERR_INVALID, "null argument");
+    *out = ms->stats;
+    return TRACER_OK;
+}
+
+int tracer_cuda_render_multi(const tracer_scene_flat *scene, const tracer_camera *cam, int32_t width, int32_t height,
+                             const tracer_render_opts *opts, uint8_t *rgb_out) {
+    tracer_scene_multi *ms = nullptr;
+    if (int rc = tracer_cuda_scene_create_multi(scene, &ms)) return rc;
+    const int rc = tracer_cuda_render_scene_multi(ms, cam, width, height, opts, rgb_out);
+    tracer_cuda_scene_destroy_multi(ms);
+    return rc;
 }
 
 }  // extern "C"

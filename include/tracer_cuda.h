@@ -141,10 +141,14 @@ typedef struct tracer_frame_stats {
     int64_t filter_misses;  /* exhaustive_strict only: strict accepts the filter would have lost (must be 0) */
     int32_t kernel_launches;
     int32_t n_sms;
-    double flop_primary;    /* FP32 flops the closest-hit sweep executes per swept pair: 2*(3+3R)/R when the R rays of a
-                               thread share q (no jitter), else 12; 0 in bundle-cull mode                       */
-    double flop_shadow;     /* same for the any-hit sweeps: 2*(6+3R)/R = 7.5 (R = 8 q-sorted rays of a thread share one
-                               q-term per edge row), 12 with TRACER_SHADOW_QBAR=0                              */
+    double flop_primary;    /* FP32 flops the closest-hit sweep executes per swept pair, all in the FMA pipe: edge rows
+                               (below) + 3 (FMUL + FFMA of the conjunction); 0 in bundle-cull mode              */
+    double flop_shadow;     /* same for the any-hit sweeps                                                      */
+    /* of which the three edge rows alone (the rest, 3 per pair, is the conjunction x'*y'*z' += in the FMA pipe):
+     * closest hit 2*(3+3R)/R = 6.75 when the R = 8 rays of a thread share q (no jitter), else 12;
+     * any-hit 2*(6+3R)/R = 7.5 (R = 8 q-sorted rays of a thread share one q-term per edge row) */
+    double flop_primary_edges;
+    double flop_shadow_edges;
 } tracer_frame_stats;
 
 typedef struct tracer_device_info {
@@ -160,7 +164,7 @@ typedef struct tracer_scene_dev tracer_scene_dev; /* opaque: scene resident in H
 
 /* ---- lifetime ------------------------------------------------------------ */
 int tracer_cuda_abi_version(void);
-int tracer_cuda_init(int device_ordinal); /* cudaSetDevice + stream; one device per process */
+int tracer_cuda_init(int device_ordinal); /* cudaSetDevice + stream; makes that GPU the current context */
 void tracer_cuda_shutdown(void);
 const char *tracer_cuda_last_error(void);
 int tracer_cuda_device_info(tracer_device_info *out);
@@ -178,6 +182,27 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *scene);
 int tracer_cuda_render_scene(tracer_scene_dev *scene, const tracer_camera *cam, int32_t width, int32_t height,
                              const tracer_render_opts *opts, uint8_t *rgb_out);
 int tracer_cuda_last_stats(tracer_scene_dev *scene, tracer_frame_stats *out);
+
+/* ---- all GPUs of one box behind one call ------------------------------------
+ * The reference has no multi-device path (its closest analogue is thread-per-row,
+ * src/main.cpp:629-643).  One process; a context, stream and scene replica per GPU; one
+ * host thread per GPU while a frame renders; one NCCL communicator set (ncclCommInitAll).
+ * The frame's PPM rows are cut into bands of opts->band_rows (default 8) rows, band b is
+ * rendered by GPU b % n_gpus, every GPU quantises its bands straight into its send
+ * buffer and the packed bands are gathered on GPU 0 with grouped ncclSend/ncclRecv over
+ * NVLink.  Results are byte-identical to a single-GPU frame (TRACER_RNG_HASH and
+ * TRACER_RNG_EXPLICIT; TRACER_RNG_MT19937 needs the whole frame on one GPU).
+ * After tracer_cuda_init_multi(n > 1) the drop-in tracer_cuda_render() uses all n GPUs. */
+typedef struct tracer_scene_multi tracer_scene_multi; /* opaque: one scene replica per GPU */
+int tracer_cuda_init_multi(int n_gpus);               /* devices 0 .. n_gpus-1 */
+int tracer_cuda_multi_gpu_count(void);                /* 0 before tracer_cuda_init_multi */
+int tracer_cuda_render_multi(const tracer_scene_flat *scene, const tracer_camera *cam, int32_t width, int32_t height,
+                             const tracer_render_opts *opts, uint8_t *rgb_out);
+int tracer_cuda_scene_create_multi(const tracer_scene_flat *scene, tracer_scene_multi **out);
+void tracer_cuda_scene_destroy_multi(tracer_scene_multi *scene);
+int tracer_cuda_render_scene_multi(tracer_scene_multi *scene, const tracer_camera *cam, int32_t width, int32_t height,
+                                   const tracer_render_opts *opts, uint8_t *rgb_out); /* rgb_out: host, or GPU 0 if rgb_out_is_device */
+int tracer_cuda_last_stats_multi(tracer_scene_multi *scene, tracer_frame_stats *out); /* counts summed, times of the slowest GPU */
 
 /* number of PPM rows the band selection (band_rows, band_index, band_count) covers */
 int32_t tracer_band_row_count(int32_t height, int32_t band_rows, int32_t band_index, int32_t band_count);
