@@ -324,22 +324,25 @@ class Renderer:
 
     def trace(self, scene, camera: Camera, width: int, height: int, *, rng_mode=RNG_HASH, seed=1, faceid=None,
               bands=None, exhaustive_strict=False, debug=False, out_device_ptr=None, stream=None,
-              rays_per_thread=0, shadow_chunks=0, samples_per_pixel=0, bundle_cull=False) -> Frame:
+              rays_per_thread=0, shadow_chunks=0, samples_per_pixel=0, bundle_cull=False, out=None) -> Frame:
         """Render; ``scene`` is a Scene (one-shot: upload + render, the drop-in call) or a
         ResidentScene.  ``bands`` = (band_rows, band_index, band_count).  With
-        ``out_device_ptr`` the packed rows are left in HBM at that address."""
+        ``out_device_ptr`` the packed rows are left in HBM at that address; ``out`` is an optional
+        caller-owned uint8 [rows, W, 3] host array (e.g. pinned) to receive them."""
         sc = scene.scene if isinstance(scene, ResidentScene) else scene
         rows = height if bands is None else band_row_count(height, *bands)
         n_px = rows * width
         keep = []
         o, dbg = self._opts(sc, width, height, rng_mode, seed, faceid, bands, exhaustive_strict, debug, n_px, keep,
                             (rays_per_thread, shadow_chunks, samples_per_pixel, int(bundle_cull)))
-        out = None
         if out_device_ptr is not None:
+            out = None
             o.rgb_out_is_device = 1
             dst = C.c_void_p(out_device_ptr)
         else:
-            out = np.zeros((rows, width, 3), np.uint8)
+            if out is None:
+                out = np.zeros((rows, width, 3), np.uint8)
+            assert out.dtype == np.uint8 and out.size == rows * width * 3 and out.flags.c_contiguous
             dst = out.ctypes.data_as(C.c_void_p)
         if stream is not None:
             o.cuda_stream = C.c_void_p(stream)

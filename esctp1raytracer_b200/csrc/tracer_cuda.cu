@@ -371,7 +371,10 @@ extern "C" {
 
 const char *tracer_cuda_last_error(void) { return g_err.c_str(); }
 
-int tracer_cuda_init(int device_ordinal) {
+}  // extern "C"
+
+namespace {
+int init_device(int device_ordinal) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -391,6 +394,14 @@ int tracer_cuda_init(int device_ordinal) {
     g_cur = &g;
     t_pool = &g.pool;
     return TRACER_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tracer_cuda_init(int device_ordinal) {
+    multi_shutdown(); // "use this GPU": ends a multi-GPU set-up, the drop-in call renders on this device again
+    return init_device(device_ordinal);
 }
 
 void tracer_cuda_shutdown(void) {
@@ -1155,7 +1166,7 @@ int tracer_cuda_init_multi(int n_gpus) {
     if (n_gpus < 1 || n_gpus > n || n_gpus > MAX_GPUS) return fail(TRACER_ERR_INVALID, "n_gpus out of range (" + std::to_string(n) + " devices visible)");
     multi_shutdown();
     for (int d = n_gpus - 1; d >= 0; --d) // device 0 last: it stays the current context
-        if (int rc = tracer_cuda_init(d)) return rc;
+        if (int rc = init_device(d)) return rc;
     if (n_gpus > 1) {
         std::string err;
         if (!g_nccl.load(err)) return fail(TRACER_ERR_CUDA, err);

@@ -24,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference"
 RESTATED_SO = os.path.join(HERE, "librestated.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
+REF_RELEASE_SO = os.path.join(HERE, "_ref_release", "libref_oracle.so")  # -O3 -ffast-math: timing only, never parity
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -31,7 +32,7 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(verbose: bool = False) -> None:
     """Compile the restatement, and the reference harness when /root/reference exists."""
-    targets = ["restated"] + (["ref"] if os.path.exists(os.path.join(REF_ROOT, "src", "main.cpp")) else [])
+    targets = ["restated"] + (["ref", "ref_release"] if os.path.exists(os.path.join(REF_ROOT, "src", "main.cpp")) else [])
     r = subprocess.run(["make", "-C", HERE] + targets, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout, r.stderr)
@@ -282,15 +283,22 @@ def ref_available() -> bool:
     return os.path.exists(REF_SO)
 
 
-class RefOracle:
-    """The unmodified reference serial path (oracle/ref_harness.cpp)."""
+def ref_release_available() -> bool:
+    return os.path.exists(REF_RELEASE_SO)
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
+
+class RefOracle:
+    """The unmodified reference serial path (oracle/ref_harness.cpp).  ``release=True`` loads the build with the
+    reference's own Release flags (-O3 -ffast-math, cmake/gcc.cmake:16): a TIMING comparator, not a parity oracle."""
+
+    def __init__(self, release: bool = False):
+        so = REF_RELEASE_SO if release else REF_SO
+        if not os.path.exists(so):
             build()
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO)
-        self.lib = C.CDLL(REF_SO)
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
+        self.release = release
+        self.lib = C.CDLL(so)
         L = self.lib
         L.ref_load_obj.restype = C.c_void_p
         L.ref_load_obj.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
