@@ -154,6 +154,11 @@ def cpu_sample(scene, W, H, n_pixels, threads, seed=42, extras=False):
             return ref, h, out["seconds"], rays
 
         rel = ref_release_available()
+        for r_ in ({False, rel}):  # warm both builds (page-in, thread start) on a few pixels before anything is timed
+            w_ = RefOracle(release=r_)
+            hw_ = w_.from_flat(fs)
+            w_.render_pixels(hw_, W, H, EYE, LOOK, pw[:threads], ph[:threads], fid[:threads], n_threads=threads)
+            w_.free(hw_)
         ref, h, secs, rays = timed(rel)
         kind, build = "reference", ("-O3 -ffast-math (the reference's Release flags)" if rel else "-O3 -ffp-contract=off (strict)")
         if rel:

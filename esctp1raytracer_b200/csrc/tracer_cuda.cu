@@ -620,7 +620,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     Ctx &g = *s->ctx;
     t_pool = &g.pool;
     if (W < 2 || H < 2) return fail(TRACER_ERR_INVALID, "width and height must be >= 2 (the reference divides by W-1, H-1)");
-    if ((int64_t)W * H > (int64_t)1 << 30) return fail(TRACER_ERR_INVALID, "frame too large");
+    // per-pixel planes are indexed with int (3 planes of n_px floats): keep 3 * n_px below 2^31
+    if ((int64_t)W * H > (int64_t)700 * 1000 * 1000) return fail(TRACER_ERR_INVALID, "frame too large (limit 7e8 pixels per call; render bands)");
     tracer_render_opts o;
     std::memset(&o, 0, sizeof o);
     if (opts_in) std::memcpy(&o, opts_in, std::min<size_t>(sizeof o, opts_in->struct_size ? opts_in->struct_size : sizeof o));
@@ -725,6 +726,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // two-phase bundle cull (cull.cuh "block lists"): phase A emits block<<32|triangle into cand_a; the sorted
     // keys land in cand_b, which phase B reads while it emits its ray<<32|triangle candidates into cand_a again.
     // Returns the number of keys, or -1 when the survivor lists would not fit (then the streaming kernels run).
+    // test knob: pretend the bundle-cull candidate buffer holds only this many pairs (exercises the overflow fallback)
+    const char *cand_env = std::getenv("TRACER_CAND_CAP");
+    const unsigned long long em_cap = cand_env ? std::min<unsigned long long>((unsigned long long)std::atoll(cand_env), s->cand_cap) : (unsigned long long)s->cand_cap;
     double flop_primary = 0.0; // executed FP32 flops per swept pair of the closest-hit sweep (default mode)
     const bool two_phase = cull && o.bundle_cull != 2;
     int64_t host_tests_primary = 0, host_tests_shadow = 0; // pairs considered by two-phase sweeps (every block x every triangle)
@@ -739,7 +743,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     int tri_bits = 1;
     while (((int64_t)1 << tri_bits) < s->n_pad) ++tri_bits;
     auto block_lists = [&](cull::L0Params lp, int max_blocks, long long &n_keys) -> int {
-        lp.boxes = s->boxes, lp.keys = s->cand_a, lp.count = s->cand_count, lp.cap = (unsigned long long)s->cand_cap;
+        lp.boxes = s->boxes, lp.keys = s->cand_a, lp.count = s->cand_count, lp.cap = (unsigned long long)s->cand_cap; /* phase-A keys: their own limit (TRACER_L0_CAP) */
         lp.n_tris = s->n_tris, lp.tri_bits = tri_bits, lp.diag = s->counters;
         CK_CUDA(cudaMemsetAsync(s->cand_count, 0, sizeof(unsigned long long), st));
         const dim3 grid((unsigned)((s->n_tris + cull::L0_THREADS - 1) / cull::L0_THREADS), (unsigned)lp.n_groups);
@@ -778,7 +782,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.tiles_x = (W + 127) / 128, p.tiles_y = (n_rows + 31) / 32;
         const int blocks = p.tiles_x * p.tiles_y;
         p.n_slices = blocks >= 12 * g.n_sms ? 1 : std::max(1, std::min((12 * g.n_sms + blocks - 1) / blocks, std::max(1, c_tiles / 8)));
-        p.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
+        p.em = cull::Emitter{s->cand_a, s->cand_count, em_cap};
         p.counters = s->counters, p.work = s->work;
         long long n_keys = -1;
         if (two_phase) {
@@ -800,7 +804,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             trk::primary_cull_kernel<<<std::min(blocks * p.n_slices, 2 * g.n_sms), sweep::THREADS, smem, st>>>(p);
             CK_CUDA(cudaGetLastError());
         }
-        trk::strict_primary_pairs<<<8 * g.n_sms, 256, 0, st>>>(s->cand_a, s->cand_count, (unsigned long long)s->cand_cap, dc, bands,
+        trk::strict_primary_pairs<<<8 * g.n_sms, 256, 0, st>>>(s->cand_a, s->cand_count, em_cap, dc, bands,
                                                                s->tri_verts, s->best, s->counters);
         CK_CUDA(cudaGetLastError());
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
@@ -924,7 +928,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.cells_per_group = 0, sp.n_slices = s->n_slices;
             sp.list = s->list, sp.seg_off = s->seg_off, sp.seg_cnt = s->cursor, sp.blk_off = s->blk_off, sp.px = px;
             sp.counters = s->counters, sp.work = s->work;
-            sp.em = cull::Emitter{s->cand_a, s->cand_count, (unsigned long long)s->cand_cap};
+            sp.em = cull::Emitter{s->cand_a, s->cand_count, em_cap};
             long long n_keys = -1;
             if (two_phase) {
                 const int max_blocks = n_px / rpb + F + 1;
@@ -947,7 +951,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                 trk::shadow_cull_kernel<<<2 * g.n_sms, sweep::THREADS, smem, st>>>(sp);
                 CK_CUDA(cudaGetLastError());
             }
-            trk::strict_shadow_pairs<<<8 * g.n_sms, 256, 0, st>>>(s->cand_a, s->cand_count, (unsigned long long)s->cand_cap, px, n_px,
+            trk::strict_shadow_pairs<<<8 * g.n_sms, 256, 0, st>>>(s->cand_a, s->cand_count, em_cap, px, n_px,
                                                                   s->tri_verts, s->counters);
             CK_CUDA(cudaGetLastError());
             launches += 4;
@@ -1114,8 +1118,14 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // rows when a thread's R = 8 q-sorted rays share one q-term per row.
     s->stats.flop_primary_edges = flop_primary, s->stats.flop_shadow_edges = cull ? 0.0 : 2.0 * (6 + 3 * 8) / 8;
     s->stats.flop_primary = cull ? 0.0 : flop_primary + 3.0, s->stats.flop_shadow = cull ? 0.0 : s->stats.flop_shadow_edges + 3.0;
-    if (hc.cull_overflow)
-        return fail(TRACER_ERR_NOMEM, "bundle-cull: candidate buffer overflow; use the default mode for this scene");
+    if (hc.cull_overflow) {
+        // the optional mode's candidate buffer (24 per ray + slack) was too small for this scene's depth complexity:
+        // the frame is rendered again by the default sweeps, which need no such buffer — same bytes out
+        tracer_render_opts o2 = o;
+        o2.struct_size = sizeof o2;
+        o2.bundle_cull = 0;
+        return tracer_cuda_render_scene(s, cam, W, H, &o2, rgb_out);
+    }
     if (getenv("TRACER_CULL_DIAG"))
         fprintf(stderr, "cull diag (shadow): l0 survivors %llu, tiles with any %llu, fallback tiles %llu, l1 warp-passes %llu, item-tiles %llu\n", hc.cull_l0,
                 hc.cull_tiles_any, hc.cull_tiles_fallback, hc.cull_l1, (unsigned long long)(hc.tests_shadow / 4096 / cull::CTILE));
@@ -1230,7 +1240,7 @@ int tracer_cuda_render_scene_multi(tracer_scene_multi *ms, const tracer_camera *
     if (opts_in) std::memcpy(&o, opts_in, std::min<size_t>(sizeof o, opts_in->struct_size ? opts_in->struct_size : sizeof o));
     if (o.band_count > 1) return fail(TRACER_ERR_INVALID, "the multi-GPU call partitions the frame itself: leave band_count at 0");
     if (o.out_tri || o.out_t || o.out_v || o.out_occ_tri || o.out_rgb) return fail(TRACER_ERR_INVALID, "debug outputs are per-GPU: use tracer_cuda_render_scene with bands");
-    if (W < 2 || H < 2 || (int64_t)W * H > (int64_t)1 << 30) return fail(TRACER_ERR_INVALID, "bad frame size");
+    if (W < 2 || H < 2 || (int64_t)W * H > (int64_t)2000 * 1000 * 1000) return fail(TRACER_ERR_INVALID, "bad frame size");
     const int band_rows = o.band_rows > 0 ? o.band_rows : 8;
     int rows_pad = 0;
     for (int d = 0; d < n; ++d) rows_pad = std::max(rows_pad, tracer_band_row_count(H, band_rows, d, n));

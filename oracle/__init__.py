@@ -24,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference"
 RESTATED_SO = os.path.join(HERE, "librestated.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
+DROPIN_BIN = os.path.join(HERE, "_ref", "ESCViewer2021_cuda")  # reference main.cpp + INTEGRATION.md section 3 patch
 REF_RELEASE_SO = os.path.join(HERE, "_ref_release", "libref_oracle.so")  # -O3 -ffast-math: timing only, never parity
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -32,7 +33,10 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(verbose: bool = False) -> None:
     """Compile the restatement, and the reference harness when /root/reference exists."""
-    targets = ["restated"] + (["ref", "ref_release"] if os.path.exists(os.path.join(REF_ROOT, "src", "main.cpp")) else [])
+    have_ref = os.path.exists(os.path.join(REF_ROOT, "src", "main.cpp"))
+    targets = ["restated"] + (["ref", "ref_release"] if have_ref else [])
+    if have_ref and os.path.exists(os.path.join(HERE, "..", "esctp1raytracer_b200", "libtracer_cuda.so")):
+        targets.append("dropin")  # the reference's main.cpp + the INTEGRATION.md binding, linked with the product library
     r = subprocess.run(["make", "-C", HERE] + targets, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout, r.stderr)

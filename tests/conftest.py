@@ -67,3 +67,22 @@ def ref_oracle():
     if not ref_available():
         pytest.skip("oracle/_ref not built (no /root/reference here)")
     return RefOracle()
+
+
+def write_obj(s, obj_path, mtl_name="scene.mtl"):
+    """Write a flat scene as OBJ + MTL (one `g` + `usemtl` per geometry, floats via repr so that they parse back to the
+    same bits): what the reference's loader (and ours) turns back into the same flat scene."""
+    mtl_path = os.path.join(os.path.dirname(str(obj_path)), mtl_name)
+    with open(mtl_path, "w") as f:
+        for g in range(s.n_geoms):
+            m = [float(x) for x in s.geom_material[g]]
+            f.write(f"newmtl m{g}\nKa {m[0]!r} {m[1]!r} {m[2]!r}\nKd {m[3]!r} {m[4]!r} {m[5]!r}\nKs {m[6]!r} {m[7]!r} {m[8]!r}\n"
+                    f"Ke {m[9]!r} {m[10]!r} {m[11]!r}\nNs {m[12]!r}\n")
+    with open(obj_path, "w") as f:
+        f.write(f"mtllib {mtl_name}\n")
+        for v in s.tri_verts.reshape(-1, 3).tolist():
+            f.write(f"v {v[0]!r} {v[1]!r} {v[2]!r}\n")
+        for g in range(s.n_geoms):
+            f.write(f"g geom{g}\nusemtl m{g}\n")
+            for t in range(s.geom_tri_offset[g], s.geom_tri_offset[g + 1]):
+                f.write(f"f {3 * t + 1} {3 * t + 2} {3 * t + 3}\n")

@@ -53,20 +53,10 @@ def test_cli_gpus_flag_writes_the_same_ppm(tmp_path):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     s = scenes.box_scene()
-    obj, mtl = tmp_path / "box.obj", tmp_path / "box.mtl"
-    with open(mtl, "w") as f:
-        for g in range(s.n_geoms):
-            m = [float(x) for x in s.geom_material[g]]
-            f.write(f"newmtl m{g}\nKa {m[0]!r} {m[1]!r} {m[2]!r}\nKd {m[3]!r} {m[4]!r} {m[5]!r}\nKs {m[6]!r} {m[7]!r} {m[8]!r}\n"
-                    f"Ke {m[9]!r} {m[10]!r} {m[11]!r}\nNs {m[12]!r}\n")
-    with open(obj, "w") as f:
-        f.write("mtllib box.mtl\n")
-        for v in s.tri_verts.reshape(-1, 3).tolist():
-            f.write(f"v {v[0]!r} {v[1]!r} {v[2]!r}\n")
-        for g in range(s.n_geoms):
-            f.write(f"g geom{g}\nusemtl m{g}\n")
-            for t in range(s.geom_tri_offset[g], s.geom_tri_offset[g + 1]):
-                f.write(f"f {3 * t + 1} {3 * t + 2} {3 * t + 3}\n")
+    from conftest import write_obj
+
+    obj = tmp_path / "box.obj"
+    write_obj(s, obj)
     cli = os.path.join(ROOT, "esctp1raytracer_b200", "tracer_cli.bin")
     outs = []
     for k in (1, n):

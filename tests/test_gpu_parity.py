@@ -241,20 +241,10 @@ def test_cli_host_flow_obj_to_ppm(renderer, restated, tmp_path):
     from esctp1raytracer_b200 import Scene, scenes
 
     s = scenes.box_scene()
-    obj, mtl = tmp_path / "box.obj", tmp_path / "box.mtl"
-    with open(mtl, "w") as f:
-        for g in range(s.n_geoms):
-            m = [float(x) for x in s.geom_material[g]]
-            f.write(f"newmtl m{g}\nKa {m[0]!r} {m[1]!r} {m[2]!r}\nKd {m[3]!r} {m[4]!r} {m[5]!r}\nKs {m[6]!r} {m[7]!r} {m[8]!r}\n"
-                    f"Ke {m[9]!r} {m[10]!r} {m[11]!r}\nNs {m[12]!r}\n")
-    with open(obj, "w") as f:
-        f.write("mtllib box.mtl\n")
-        for v in s.tri_verts.reshape(-1, 3).tolist():
-            f.write(f"v {v[0]!r} {v[1]!r} {v[2]!r}\n")
-        for g in range(s.n_geoms):
-            f.write(f"g geom{g}\nusemtl m{g}\n")
-            for t in range(s.geom_tri_offset[g], s.geom_tri_offset[g + 1]):
-                f.write(f"f {3 * t + 1} {3 * t + 2} {3 * t + 3}\n")
+    from conftest import write_obj
+
+    obj = tmp_path / "box.obj"
+    write_obj(s, obj)
     loaded = Scene.load_obj(str(obj))
     assert np.array_equal(bits(loaded.tri_verts), bits(s.tri_verts)) and np.array_equal(loaded.light_geom, s.light_geom)
     assert np.array_equal(bits(loaded.geom_material), bits(s.geom_material))
@@ -441,3 +431,46 @@ def test_shadow_sweeps_with_shared_q_terms_never_miss(renderer, restated):
         has_pow = bool(s.geom_material[:, 6:9].any() or s.sphere_material[:, 6:9].any())
         _check_frame(a, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), has_pow, occ=o.occ_tri)
         assert a.stats["tests_shadow_ref"] == o.n_tests[1]
+
+
+def test_big_light_tables_are_batched_within_a_budget(renderer, restated):
+    """the 6 cube-face filter tables per light vertex used to be allocated for ALL light vertices up
+    front, so an emissive mesh could be refused outright.  They now live in a budgeted number of slots that each light's
+    vertices go through batch by batch (TRACER_TABLE_SLOTS fakes a tiny budget): same frame as with resident tables."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    s = scenes.soup_scene(12000, 12, 3, seed=21, n_spheres=4)
+    W, H = 112, 70
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    a = renderer.trace(renderer.upload(s), cam, W, H, rng_mode=RNG_HASH, seed=6, debug=True)
+    os.environ["TRACER_TABLE_SLOTS"] = "1"
+    try:
+        rs = renderer.upload(s)  # the budget is taken at scene creation
+    finally:
+        del os.environ["TRACER_TABLE_SLOTS"]
+    b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=6, debug=True)
+    _same_frames(a, b)
+    c = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=6, debug=True, bundle_cull=True)  # falls back to the default sweeps
+    _same_frames(a, c)
+    o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=hash_faceids(6, W, H, s.faces_per_light))
+    _check_frame(b, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), False, occ=o.occ_tri)
+
+
+def test_bundle_cull_overflow_rerenders_in_default_mode(renderer):
+    """ADVICE r1 (low): a candidate-buffer overflow in the optional mode used to reject the frame after all the work;
+    now the frame is rendered again by the default sweeps (TRACER_CAND_CAP fakes a tiny buffer)."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, scenes
+
+    s = scenes.soup_scene(20000, 40, 3, seed=6)
+    W, H = 96, 64
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True)
+    os.environ["TRACER_CAND_CAP"] = "1000"
+    try:
+        for mode in (1, 2):
+            b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, bundle_cull=mode)
+            _same_frames(a, b)
+            assert b.stats["flop_primary"] > 0  # the statistics are the default sweeps'
+    finally:
+        del os.environ["TRACER_CAND_CAP"]

@@ -100,4 +100,4 @@ def test_bench_model_workloads_load_the_reference_models():
     assert (sc.n_tris, W, H, sc.n_lights) == (36, 1024, 768, 1) and bench.EYE == (0.0, 1.0, 2.0)
     sc, W, H = bench.make_scene("c3", a)
     assert (sc.n_tris, W, H, sc.n_lights) == (7088, 1920, 1080, 1) and sc.tri_normals is not None
-    assert "reference model" in bench.workload_config("c3", sc, W, H)["workload"]
+    assert "reference model" in bench.workload_config("c3", sc, W, H, 1, "brute")["workload"]
