@@ -63,7 +63,7 @@ class FrameStats(C.Structure):
         ("tests_primary", C.c_int64), ("tests_shadow", C.c_int64), ("tests_shadow_ref", C.c_int64),
         ("strict_evals", C.c_int64), ("filter_misses", C.c_int64), ("kernel_launches", C.c_int32),
         ("n_sms", C.c_int32), ("flop_primary", C.c_double), ("flop_shadow", C.c_double),
-        ("flop_primary_edges", C.c_double), ("flop_shadow_edges", C.c_double),
+        ("flop_primary_edges", C.c_double), ("flop_shadow_edges", C.c_double), ("pipeline_errors", C.c_int64),
     ]
 
     def asdict(self):

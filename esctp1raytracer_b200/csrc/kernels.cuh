@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const _
     sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
     const int tid = threadIdx.x;
     sweep::smem_init(sm);
-    unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0;
+    unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0, n_pipe_err = 0;
     unsigned long long tests = 0;
     const int n_items = p.n_blocks * p.n_slices;
     for (;;) {
@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const _
                 const unsigned c = strict_primary(p, k0, mask, tri, filt);
                 n_strict += c & 0xffffu, n_miss += c >> 16;
                 return 0u;
-            });
+            },
+            &n_pipe_err);
         const int t_lo = min(tile_lo * sweep::TILE, p.n_tris), t_hi = min(tile_hi * sweep::TILE, p.n_tris);
         tests += (unsigned long long)__popc(valid) * (unsigned)(t_hi - t_lo);
         __syncthreads(); // sm.blk is rewritten by the next item
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const _
     atomicAdd(&p.counters->tests_primary, tests);
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
     if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
+    if (EXHAUSTIVE && n_pipe_err) atomicAdd(&p.counters->pipeline_errors, (unsigned long long)n_pipe_err);
 }
 
 // ---------------------------------------------------------------------------------
@@ -651,7 +653,7 @@ __device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float
 template <int RR, bool EXHAUSTIVE>
 __device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowLightParams &p, const int *__restrict__ list_in, int base,
                                             int seg_end, int lo, int hi, const float4 *__restrict__ tab, unsigned &gtile,
-                                            unsigned &n_strict, unsigned &n_miss, unsigned long long &tests) {
+                                            unsigned &n_strict, unsigned &n_miss, unsigned long long &tests, unsigned &n_pipe_err) {
     const int tid = threadIdx.x, n = p.n_px;
     float rp[RR], rq[RR];
     unsigned valid = 0, done = 0;
@@ -678,7 +680,8 @@ __device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowLightPa
             const unsigned c = strict_shadow(p.px, p.tri_verts, list_in, n, e0, seg_end - 1, mask, tri, filt);
             n_strict += (c >> 8) & 0xffu, n_miss += c >> 16;
             return c & 0xffu;
-        });
+        },
+        &n_pipe_err);
     tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
 }
 
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
     __shared__ int s_blk_off[SL_MAXF + 1], s_cblk_off[SL_MAXF + 1], s_scratch[sweep::NT / 32], s_off;
     const int tid = threadIdx.x, F = p.F;
     sweep::smem_init(sm);
-    unsigned gtile = 0, n_strict = 0, n_miss = 0, epoch = 0;
+    unsigned gtile = 0, n_strict = 0, n_miss = 0, epoch = 0, n_pipe_err = 0;
     unsigned long long tests = 0;
     // chunk scheme: equal chunks keep the pairs swept past a ray's occluder lowest and win when the light has many
     // rays; with few rays the per-chunk tails weigh more and boundaries that start fine and coarsen geometrically win
@@ -797,11 +800,11 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
             // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups).
             const int cnt = seg_end - base;
             if (cnt > 4 * sweep::NT)
-                shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
             else if (cnt > 2 * sweep::NT)
-                shadow_item<4, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                shadow_item<4, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
             else
-                shadow_item<2, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests);
+                shadow_item<2, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
             __syncthreads();
         }
         if (c == n_chunks - 1) break; // nothing left to sweep: the lists are not needed compacted
@@ -905,6 +908,7 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
     atomicAdd(&p.counters->tests_shadow, tests);
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
     if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
+    if (EXHAUSTIVE && n_pipe_err) atomicAdd(&p.counters->pipeline_errors, (unsigned long long)n_pipe_err);
 }
 
 // extension: spheres are tested after all triangles, in order, by the rays that found no triangle

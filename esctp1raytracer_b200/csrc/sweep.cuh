@@ -148,6 +148,7 @@ struct Counters {
     unsigned long long tests_primary, tests_shadow, strict_evals, tests_shadow_ref, n_hits, filter_misses;
     unsigned long long cull_l0, cull_l1, cull_tiles_any, cull_tiles_fallback; // bundle-cull diagnostics
     unsigned long long cull_overflow; // bundle-cull: a candidate buffer was too small (the frame is rejected)
+    unsigned long long pipeline_errors; // validation mode: staged tiles that differed from their source (must be 0)
 };
 
 __device__ __forceinline__ void smem_init(Smem &sm) {
@@ -275,7 +276,8 @@ __device__ __forceinline__ unsigned eval_batch_lop3(const float4 *__restrict__ t
 template <int R, int MODE, bool ANYHIT, bool EXHAUSTIVE, class Strict>
 __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi, int n_tris,
                                             const float (&rp)[R], const float (&rq)[R], float qbar, float qdelta, unsigned valid,
-                                            unsigned &done, unsigned &gtile, unsigned &n_tiles_swept, Strict &&strict) {
+                                            unsigned &done, unsigned &gtile, unsigned &n_tiles_swept, Strict &&strict,
+                                            unsigned *n_pipe_err = nullptr) {
     const int tid = threadIdx.x;
     const int n_tiles = tile_hi - tile_lo;
     const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
@@ -291,6 +293,20 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
         const unsigned g = gtile + it;
         const int s = g % STAGES;
         mbar_wait(&sm.full_bar[s], (g / STAGES) & 1u);
+        // Validation mode doubles as the pipeline's own race check (compute-sanitizer is not available on this pool):
+        // every warp compares the staged tile with its source in global memory when the tile arrives AND after it has
+        // used it — a copy that had not landed, or a refill issued while a warp was still reading, shows up here.
+        auto tile_differs = [&]() {
+            unsigned bad = 0;
+            const uint4 *a = reinterpret_cast<const uint4 *>(sm.tile[s]);
+            const uint4 *b = reinterpret_cast<const uint4 *>(src + (size_t)it * TILE * 3);
+            for (int i = tid & 31; i < TILE * 3; i += 32) {
+                const uint4 x = a[i], y = __ldcg(&b[i]);
+                bad |= (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w);
+            }
+            return __any_sync(0xffffffffu, bad != 0);
+        };
+        if (EXHAUSTIVE && n_pipe_err && tile_differs() && (tid & 31) == 0) ++*n_pipe_err;
         // any-hit: a warp whose rays all have their occluder has nothing left to evaluate
         const bool idle = ANYHIT && __all_sync(0xffffffffu, (done | ~valid) == 0xffffffffu);
         if (!idle) {
@@ -328,6 +344,7 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
 #endif
             }
         }
+        if (EXHAUSTIVE && n_pipe_err && tile_differs() && (tid & 31) == 0) ++*n_pipe_err;
         // No block-wide barrier per tile: every warp counts itself out of stage s, and the LAST one refills it.
         // Warps run up to STAGES-1 tiles apart, which absorbs the skew of the (rare, long) strict evaluations
         // instead of stalling every warp behind one.

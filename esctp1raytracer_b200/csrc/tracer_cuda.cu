@@ -1111,6 +1111,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.tests_shadow_ref = (int64_t)hc.tests_shadow_ref;
     s->stats.strict_evals = (int64_t)hc.strict_evals;
     s->stats.filter_misses = (int64_t)hc.filter_misses;
+    s->stats.pipeline_errors = (int64_t)hc.pipeline_errors;
     s->stats.kernel_launches = launches;
     // shadow sweeps: 6 FFMA per pair, or (6 + 3R) FFMA per R pairs when a thread's R = 8 rays share the q-terms
     // FP32 flops the sweeps execute per swept pair (all in the FMA pipe; FFMA = 2, FMUL = 1): the three edge rows, plus
@@ -1319,6 +1320,7 @@ int tracer_cuda_render_scene_multi(tracer_scene_multi *ms, const tracer_camera *
         t.n_pixels += x.n_pixels, t.n_primary_rays += x.n_primary_rays, t.n_shadow_rays += x.n_shadow_rays;
         t.tests_primary += x.tests_primary, t.tests_shadow += x.tests_shadow, t.tests_shadow_ref += x.tests_shadow_ref;
         t.strict_evals += x.strict_evals, t.filter_misses += x.filter_misses, t.kernel_launches += x.kernel_launches;
+        t.pipeline_errors += x.pipeline_errors;
         t.n_sms += x.n_sms;
         t.flop_primary = x.flop_primary, t.flop_shadow = x.flop_shadow;
         t.flop_primary_edges = x.flop_primary_edges, t.flop_shadow_edges = x.flop_shadow_edges;

@@ -149,6 +149,9 @@ typedef struct tracer_frame_stats {
      * any-hit 2*(6+3R)/R = 7.5 (R = 8 q-sorted rays of a thread share one q-term per edge row) */
     double flop_primary_edges;
     double flop_shadow_edges;
+    int64_t pipeline_errors; /* exhaustive_strict only: the sweeps' own race check — staged table tiles (TMA pipeline,
+                                per-warp stage recycling) that differed from their source when a warp started or
+                                finished using them (must be 0) */
 } tracer_frame_stats;
 
 typedef struct tracer_device_info {

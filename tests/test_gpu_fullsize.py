@@ -141,7 +141,7 @@ def test_c4_full_size_oracle_subset_and_filter_soundness(renderer, restated):
     for r in np.random.default_rng(2).choice(n_bands, 4, replace=False):
         b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True, bands=(8, int(r), n_bands),
                            exhaustive_strict=True)
-        assert b.stats["filter_misses"] == 0
+        assert b.stats["filter_misses"] == 0 and b.stats["pipeline_errors"] == 0
         rows = slice(int(r) * 8, int(r) * 8 + 8)
         assert np.array_equal(b.rgb8, a.rgb8[rows])
         assert np.array_equal(b.tri, a.tri.reshape(H, W)[rows].reshape(-1))

@@ -34,7 +34,7 @@ def _to_ppm_order(a, W, H):
 
 
 def _check_frame(out, W, H, tri, t, v, rgb, q, has_pow, occ=None):
-    assert out.stats == {} or out.stats["filter_misses"] == 0
+    assert out.stats == {} or (out.stats["filter_misses"] == 0 and out.stats["pipeline_errors"] == 0)
     assert np.array_equal(out.tri, _to_ppm_order(tri, W, H)), "hit ids differ"
     assert np.array_equal(bits(out.t), bits(_to_ppm_order(t, W, H))), "closest-hit t differs"
     assert np.array_equal(bits(out.v), bits(_to_ppm_order(v, W, H))), "closest-hit v differs"
@@ -82,7 +82,7 @@ def test_exhaustive_strict_mode_agrees_and_filter_never_misses(renderer, name):
     W, H = fr["W"], fr["H"]
     rs = renderer.upload(to_scene(fs))
     a = renderer.trace(rs, _cam(fr), W, H, rng_mode=RNG_EXPLICIT, faceid=fr["faceid"], debug=True, exhaustive_strict=True)
-    assert a.stats["filter_misses"] == 0
+    assert a.stats["filter_misses"] == 0 and a.stats["pipeline_errors"] == 0
     _check_frame(a, W, H, fr["tri"], fr["t"], fr["v"], fr["rgb"], fr["q"], False)
 
 
@@ -134,7 +134,7 @@ def test_coplanar_light_plane_and_eye_plane(renderer, restated):
         out = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True)
         _check_frame(out, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), False, occ=o.occ_tri)
         ex = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, debug=True, exhaustive_strict=True)
-        assert ex.stats["filter_misses"] == 0
+        assert ex.stats["filter_misses"] == 0 and ex.stats["pipeline_errors"] == 0
         assert np.array_equal(ex.rgb8, out.rgb8)
 
 
@@ -147,7 +147,7 @@ def test_soup_exhaustive_no_filter_misses(renderer):
     rs = renderer.upload(s)
     a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True)
     b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=3, debug=True, exhaustive_strict=True)
-    assert b.stats["filter_misses"] == 0
+    assert b.stats["filter_misses"] == 0 and b.stats["pipeline_errors"] == 0
     assert np.array_equal(a.rgb8, b.rgb8) and np.array_equal(a.occ_tri, b.occ_tri) and np.array_equal(a.tri, b.tri)
     assert a.stats["strict_evals"] < b.stats["strict_evals"] / 20
 
@@ -425,7 +425,7 @@ def test_shadow_sweeps_with_shared_q_terms_never_miss(renderer, restated):
         rs = renderer.upload(s)
         a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=7, debug=True, shadow_chunks=chunks)
         b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=7, debug=True, shadow_chunks=chunks, exhaustive_strict=True)
-        assert b.stats["filter_misses"] == 0
+        assert b.stats["filter_misses"] == 0 and b.stats["pipeline_errors"] == 0
         _same_frames(a, b)
         o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=hash_faceids(7, W, H, s.faces_per_light))
         has_pow = bool(s.geom_material[:, 6:9].any() or s.sphere_material[:, 6:9].any())

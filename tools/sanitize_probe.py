@@ -23,5 +23,7 @@ for name, kw in (("default", {}), ("default chunks=24", dict(shadow_chunks=24)),
     if name != "4 spp":
         ref = out.rgb8 if ref is None else ref
         assert np.array_equal(out.rgb8, ref), name
-    print(name, "launches", out.stats["kernel_launches"], "strict", out.stats["strict_evals"], "misses", out.stats["filter_misses"], flush=True)
+    print(name, "launches", out.stats["kernel_launches"], "strict", out.stats["strict_evals"], "filter misses", out.stats["filter_misses"],
+          "pipeline errors", out.stats["pipeline_errors"], flush=True)
+    assert out.stats["filter_misses"] == 0 and out.stats["pipeline_errors"] == 0
 print("OK")
