@@ -42,7 +42,8 @@ for mode, sizes in (("cull", args.cull), ("brute", args.brute)):
         s = scenes.soup_scene(n, min(1000, max(8, n // 100)), 1, seed=42)
         rs = r.upload(s)
         kw = dict(rank=rank, world=world, seed=42, bundle_cull=(mode == "cull"), samples_per_pixel=args.spp)
-        frame, st = tdist.render_frame(r, rs, cam, W, H, **kw)  # warm-up: builds the tables, sizes the workspace
+        # warm-up at 1 spp (1/16 of the cost): builds the filter tables, sizes the workspace, loads the kernels
+        tdist.render_frame(r, rs, cam, W, H, **dict(kw, samples_per_pixel=1))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
