@@ -323,9 +323,11 @@ def main():
         def upload(sc):
             return multi.upload(sc)
 
-        def render(rs, cull):
-            fr = multi.trace(rs, cam, W, H, seed=seed, bundle_cull=cull, samples_per_pixel=spp)
-            return torch.from_numpy(fr.rgb8), fr.stats
+        dev_frame = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda:0")
+
+        def render(rs, cull):  # like the torch path, `value` leaves the assembled frame in HBM on GPU 0
+            fr = multi.trace(rs, cam, W, H, seed=seed, bundle_cull=cull, samples_per_pixel=spp, out_device_ptr=dev_frame.data_ptr())
+            return dev_frame, fr.stats
     else:
         renderer = Renderer(local_rank)
 
@@ -436,7 +438,7 @@ def main():
         elif native:
             def e2e_step():
                 fr = multi.trace(pin, cam, W, H, seed=seed, bundle_cull=main_cull, samples_per_pixel=spp)
-                host_frame.numpy()[...] = fr.rgb8
+                host_frame.numpy()[...] = fr.rgb8  # (MultiRenderer returns its own host array)
             path = "tracer_cuda_render_multi(host scene, ...): per-GPU upload + render + NCCL gather + read-back in one C call"
         else:
             def e2e_step():

@@ -241,7 +241,8 @@ class MultiRenderer:
         return _MultiScene(self, scene, h)
 
     def trace(self, scene, camera: "Camera", width: int, height: int, *, rng_mode=RNG_HASH, seed=1, faceid=None,
-              samples_per_pixel=0, bundle_cull=False, band_rows=0) -> "Frame":
+              samples_per_pixel=0, bundle_cull=False, band_rows=0, out_device_ptr=None) -> "Frame":
+        """``out_device_ptr``: leave the assembled frame in HBM on GPU 0 at that address instead of copying it to the host."""
         sc = scene.scene if isinstance(scene, _MultiScene) else scene
         o = _lib.RenderOpts()
         o.struct_size = C.sizeof(_lib.RenderOpts)
@@ -251,18 +252,20 @@ class MultiRenderer:
             keep = np.ascontiguousarray(faceid, np.int32)
             o.faceid = _ptr(keep, C.c_int32)
         o.samples_per_pixel, o.bundle_cull, o.band_rows = samples_per_pixel, int(bundle_cull), band_rows
-        out = np.zeros((height, width, 3), np.uint8)
+        if out_device_ptr is not None:
+            out, dst, o.rgb_out_is_device = None, C.c_void_p(out_device_ptr), 1
+        else:
+            out = np.empty((height, width, 3), np.uint8)
+            dst = out.ctypes.data_as(C.c_void_p)
         stats = {}
         if isinstance(scene, _MultiScene):
-            _lib.check(self.lib.tracer_cuda_render_scene_multi(scene.handle, C.byref(camera.c), width, height, C.byref(o),
-                                                               out.ctypes.data_as(C.c_void_p)))
+            _lib.check(self.lib.tracer_cuda_render_scene_multi(scene.handle, C.byref(camera.c), width, height, C.byref(o), dst))
             st = _lib.FrameStats()
             _lib.check(self.lib.tracer_cuda_last_stats_multi(scene.handle, C.byref(st)))
             stats = st.asdict()
         else:
             cs = sc.c_struct()
-            _lib.check(self.lib.tracer_cuda_render_multi(C.byref(cs), C.byref(camera.c), width, height, C.byref(o),
-                                                         out.ctypes.data_as(C.c_void_p)))
+            _lib.check(self.lib.tracer_cuda_render_multi(C.byref(cs), C.byref(camera.c), width, height, C.byref(o), dst))
         return Frame(rgb8=out, stats=stats)
 
 

@@ -772,40 +772,47 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
         if (total_blocks == 0) break; // every shadow ray of this light already has its occluder (same on every CTA)
         const int total_cblocks = cta_group_prefix(cnt_in, F, CBLK, s_cblk_off, s_scratch);
         const int tile_lo = bounds[c], tile_hi = bounds[c + 1], n_tiles = tile_hi - tile_lo;
-        // enough (block, slice) items to keep every CTA busy to the end of the chunk, >= 4 tiles per slice
+        // (ray block, triangle slice) items, slices of >= 2 tiles.  Items are BLOCK-major (consecutive items = consecutive
+        // slices of one ray block) and handed out in runs whose length shrinks as the chunk drains (guided self-scheduling):
+        // long runs while there is plenty of work (one ray set-up per run), single 2-tile slices at the end, so the
+        // chunk's tail — every CTA waits at the grid barrier for the last item — is one small slice long.  This is what
+        // the 8-GPU band shares need: their chunks are only ~1 ms long.
         const int want = p.items_per_cta * (int)gridDim.x;
-        const int n_slices = max(1, min(total_blocks >= want ? 1 : (want + total_blocks - 1) / total_blocks, max(1, n_tiles / 4)));
+        const int n_slices = max(1, min(total_blocks >= want ? 1 : (want + total_blocks - 1) / total_blocks, max(1, n_tiles / 2)));
         const int n_items = total_blocks * n_slices;
         // ---- A: sweep --------------------------------------------------------------------------------------
         for (;;) {
             if (tid == 0) {
-                const int it = atomicAdd(&p.work[c], 1);
-                int j = 0, b = -1, sl = 0;
-                if (it < n_items) {
-                    sl = it / total_blocks, b = it - sl * total_blocks; // slice-major
-                    j = group_of_block(s_blk_off, F, b);
-                }
-                sm.blk = b, sm.seg = j, sm.slice = sl;
+                const int seen = *(volatile int *)&p.work[c];
+                const int g = max(1, min((n_items - seen) / (2 * (int)gridDim.x), n_slices));
+                const int it = atomicAdd(&p.work[c], g);
+                sm.blk = it < n_items ? it : -1, sm.seg = min(it + g, n_items);
             }
             __syncthreads();
-            const int blk = sm.blk, j = sm.seg, slice = sm.slice;
-            if (blk < 0) break;
-            const int lo = tile_lo + (int)((long long)n_tiles * slice / n_slices);
-            const int hi = tile_lo + (int)((long long)n_tiles * (slice + 1) / n_slices);
-            const int seg_begin = p.seg_off[j], seg_end = seg_begin + cnt_in[j];
-            const int base = seg_begin + (blk - s_blk_off[j]) * (sweep::NT * R);
-            const int face = j % NFACE;
-            const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
-            // The last block of a ray group is rarely full.  A block with at most NT*RR rays is swept with RR rays per
-            // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups).
-            const int cnt = seg_end - base;
-            if (cnt > 4 * sweep::NT)
-                shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
-            else if (cnt > 2 * sweep::NT)
-                shadow_item<4, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
-            else
-                shadow_item<2, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
-            __syncthreads();
+            int it = sm.blk;
+            const int it_end = sm.seg;
+            if (it < 0) break;
+            while (it < it_end) { // (uniform) one run per ray block touched
+                const int blk = it / n_slices, sl0 = it - blk * n_slices, sl1 = min(n_slices, sl0 + (it_end - it));
+                it += sl1 - sl0;
+                const int j = group_of_block(s_blk_off, F, blk);
+                const int lo = tile_lo + (int)((long long)n_tiles * sl0 / n_slices);
+                const int hi = tile_lo + (int)((long long)n_tiles * sl1 / n_slices);
+                const int seg_begin = p.seg_off[j], seg_end = seg_begin + cnt_in[j];
+                const int base = seg_begin + (blk - s_blk_off[j]) * (sweep::NT * R);
+                const int face = j % NFACE;
+                const float4 *tab = face == NFACE - 1 ? p.allcand : p.tables + (size_t)((j / NFACE) * 6 + face) * p.table_stride;
+                // The last block of a ray group is rarely full.  A block with at most NT*RR rays is swept with RR rays per
+                // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups).
+                const int cnt = seg_end - base;
+                if (cnt > 4 * sweep::NT)
+                    shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
+                else if (cnt > 2 * sweep::NT)
+                    shadow_item<4, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
+                else
+                    shadow_item<2, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
+                __syncthreads(); // every warp is out of the tile pipeline before the next run re-arms it
+            }
         }
         if (c == n_chunks - 1) break; // nothing left to sweep: the lists are not needed compacted
         grid_barrier(bar, epoch);

@@ -165,6 +165,7 @@ struct tracer_scene_dev {
     void *pair_tmp = nullptr;
     int rkey_npx = 0;
     size_t cand_cap = 0, sort_bytes = 0;
+    int cull_grow = 1; // candidate buffers hold 24 * cull_grow pairs per ray (grown after an overflow)
     void *sort_tmp = nullptr;
     int *seg_count = nullptr, *seg_off = nullptr, *blk_off = nullptr, *cursor = nullptr, *cnt_b = nullptr, *work = nullptr,
         *n_slices = nullptr;
@@ -699,7 +700,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // (the optional mode keeps every light vertex's tables resident; a light too big for that renders in the default mode)
     const bool cull = s->tables_resident && (o.bundle_cull == 3 ? est_default_ms > 6.0 : o.bundle_cull != 0);
     if (cull) { // candidate buffers: 24 per ray + slack (a few per ray are typical), sorted with a radix sort
-        const size_t cap = (size_t)n_px * 24 + ((size_t)1 << 22);
+        const size_t cap = (size_t)n_px * 24 * (size_t)s->cull_grow + ((size_t)1 << 22);
         if (cap > s->cand_cap) {
             dev_free(s->cand_a), dev_free(s->cand_b), dev_free(s->cand_count);
             t_pool->release(s->sort_tmp);
@@ -1120,11 +1121,18 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.flop_primary_edges = flop_primary, s->stats.flop_shadow_edges = cull ? 0.0 : 2.0 * (6 + 3 * 8) / 8;
     s->stats.flop_primary = cull ? 0.0 : flop_primary + 3.0, s->stats.flop_shadow = cull ? 0.0 : s->stats.flop_shadow_edges + 3.0;
     if (hc.cull_overflow) {
-        // the optional mode's candidate buffer (24 per ray + slack) was too small for this scene's depth complexity:
-        // the frame is rendered again by the default sweeps, which need no such buffer — same bytes out
+        // the optional mode's candidate buffer (24 per ray + slack) was too small for this scene's depth complexity: render
+        // the frame again with a 4x larger one while that fits comfortably, else by the default sweeps, which need no such
+        // buffer — same bytes out either way
         tracer_render_opts o2 = o;
         o2.struct_size = sizeof o2;
-        o2.bundle_cull = 0;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t next_bytes = ((size_t)n_px * 24 * (size_t)s->cull_grow * 4 + ((size_t)1 << 22)) * sizeof(unsigned long long) * 3;
+        if (!std::getenv("TRACER_CAND_CAP") && s->cull_grow < 64 && next_bytes < free_b / 2 + s->cand_cap * 24)
+            s->cull_grow *= 4;
+        else
+            o2.bundle_cull = 0;
         return tracer_cuda_render_scene(s, cam, W, H, &o2, rgb_out);
     }
     if (getenv("TRACER_CULL_DIAG"))

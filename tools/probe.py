@@ -25,9 +25,10 @@ for n, W, H, L in cases:
     look = (0, 1, 6) if os.environ.get('PROBE_AWAY') else (0, 1, 0)
     cam = Camera.for_frame((0, 1, 3), look, W, H)
     rs = r.upload(s)
+    bands = tuple(int(x) for x in os.environ['PROBE_BANDS'].split(',')) if os.environ.get('PROBE_BANDS') else None  # e.g. 8,0,8
     for it in range(3):
         t0 = time.time()
-        out = r.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=1, rays_per_thread=int(os.environ.get('TRACER_RAYS', '0')),
+        out = r.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=1, bands=bands, rays_per_thread=int(os.environ.get('TRACER_RAYS', '0')),
                       shadow_chunks=int(os.environ.get('TRACER_CHUNKS', '0')), bundle_cull=bool(os.environ.get('TRACER_CULL')))
         wall = time.time() - t0
     st = out.stats
