@@ -592,6 +592,7 @@ __global__ void iota_kernel(int *a, int n) {
 // so the pairs actually swept track the reference's own early-exit count (main.cpp:324) and the host is not in
 // the loop at all: block offsets, slice counts, the chunk scheme and the early stop ("every ray has its occluder")
 // are decided on the device.  Round 1 ran A/B/C as 4 launches per chunk with host read-backs in between.
+constexpr int SHADOW_R = 12;    // rays per thread of a full shadow-ray block (blocks of NT * SHADOW_R consecutive list entries)
 constexpr int SL_MAXF = 1022;   // ray groups per launch (the host batches bigger lights: 146 vertices x NFACE)
 constexpr int SL_MAXCHUNK = 64;
 constexpr int CBLK = 1024;      // list entries per compaction block
@@ -605,6 +606,7 @@ struct ShadowLightParams {
     int bounds[2][SL_MAXCHUNK + 1]; // chunk boundaries in tiles
     long long many_rays;
     int items_per_cta;            // (ray block, slice) items wanted per resident CTA
+    int min_tiles;                // smallest slice, in tiles
     const float *tri_verts;
     int *list[2];                 // ping-pong ray lists, [0] = the sorted input
     const int *seg_off;           // [F+1] segment starts of this launch's groups (absolute list positions)
@@ -621,7 +623,7 @@ struct ShadowLightParams {
 // (occlusion(), main.cpp:314-329): the first accepted face in order ends the ray and leaves t = t2 behind (the
 // multi-light carry).  Origin, direction and length stay in the pixel state and are fetched on demand: only a
 // few rays per work item ever get here.  Ray r of the thread is list entry min(e0 + r, e_last).
-// Returns newly occluded rays | evaluations << 8 | filter misses << 16.
+// Returns newly occluded rays (bits 0-15) | evaluations << 16 | filter misses << 24.
 __device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float *__restrict__ tri_verts, const int *__restrict__ list_in,
                                                int n_px, int e0, int e_last, unsigned mask, int tri, unsigned filt) {
     const float *q = tri_verts + 9 * (size_t)tri;
@@ -637,11 +639,11 @@ __device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float
         const f3 o = strict::mk(px.ro[k], px.ro[n + k], px.ro[2 * n + k]);
         const f3 d = strict::mk(px.rd[k], px.rd[n + k], px.rd[2 * n + k]);
         float t = px.rt[k], v = 0.f; // the ray has no occluder yet, so t is its initial length (main.cpp:764)
-        ret += 1u << 8;
+        ret += 1u << 16;
         if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
             atomicMin(&px.best_occ[k], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(t));
             ret |= 1u << r;
-            if (!((filt >> r) & 1u)) ret += 1u << 16;
+            if (!((filt >> r) & 1u)) ret += 1u << 24;
         }
     }
     return ret;
@@ -678,8 +680,8 @@ __device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowLightPa
     sweep::sweep_table<RR, sweep::MODE_QBAR, true, EXHAUSTIVE>(
         sm, tab, lo, hi, p.n_tris, rp, rq, qbar, qdelta, valid, done, gtile, swept, [&](unsigned mask, int tri, unsigned filt) {
             const unsigned c = strict_shadow(p.px, p.tri_verts, list_in, n, e0, seg_end - 1, mask, tri, filt);
-            n_strict += (c >> 8) & 0xffu, n_miss += c >> 16;
-            return c & 0xffu;
+            n_strict += (c >> 16) & 0xffu, n_miss += c >> 24;
+            return c & 0xffffu;
         },
         &n_pipe_err);
     tests += (unsigned long long)swept * sweep::TILE * __popc(valid);
@@ -741,7 +743,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &epoch) {
         __threadfence();
         atomicAdd(bar, 1u);
         const unsigned want = epoch * gridDim.x;
-        while (*(volatile unsigned *)bar < want) __nanosleep(64);
+        while (*(volatile unsigned *)bar < want) __nanosleep(20);
         __threadfence();
     }
     __syncthreads();
@@ -750,7 +752,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &epoch) {
 template <bool EXHAUSTIVE>
 __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(const __grid_constant__ ShadowLightParams p, unsigned *bar) {
     static_assert(CBLK % sweep::NT == 0, "compaction block must be a multiple of the CTA size");
-    constexpr int R = 8, CPT = CBLK / sweep::NT; // rays per thread of a full ray block; list entries per thread of a compaction block
+    constexpr int R = SHADOW_R, CPT = CBLK / sweep::NT; // rays per thread of a full ray block; list entries per thread of a compaction block
     extern __shared__ __align__(128) unsigned char smem_raw[];
     sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
     __shared__ int s_blk_off[SL_MAXF + 1], s_cblk_off[SL_MAXF + 1], s_scratch[sweep::NT / 32], s_off;
@@ -772,13 +774,13 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
         if (total_blocks == 0) break; // every shadow ray of this light already has its occluder (same on every CTA)
         const int total_cblocks = cta_group_prefix(cnt_in, F, CBLK, s_cblk_off, s_scratch);
         const int tile_lo = bounds[c], tile_hi = bounds[c + 1], n_tiles = tile_hi - tile_lo;
-        // (ray block, triangle slice) items, slices of >= 2 tiles.  Items are BLOCK-major (consecutive items = consecutive
+        // (ray block, triangle slice) items, slices of >= min_tiles tiles.  Items are BLOCK-major (consecutive items = consecutive
         // slices of one ray block) and handed out in runs whose length shrinks as the chunk drains (guided self-scheduling):
-        // long runs while there is plenty of work (one ray set-up per run), single 2-tile slices at the end, so the
+        // long runs while there is plenty of work (one ray set-up per run), single smallest slices at the end, so the
         // chunk's tail — every CTA waits at the grid barrier for the last item — is one small slice long.  This is what
         // the 8-GPU band shares need: their chunks are only ~1 ms long.
         const int want = p.items_per_cta * (int)gridDim.x;
-        const int n_slices = max(1, min(total_blocks >= want ? 1 : (want + total_blocks - 1) / total_blocks, max(1, n_tiles / 2)));
+        const int n_slices = max(1, min(total_blocks >= want ? 1 : (want + total_blocks - 1) / total_blocks, max(1, n_tiles / p.min_tiles)));
         const int n_items = total_blocks * n_slices;
         // ---- A: sweep --------------------------------------------------------------------------------------
         for (;;) {
@@ -805,7 +807,9 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
                 // The last block of a ray group is rarely full.  A block with at most NT*RR rays is swept with RR rays per
                 // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups).
                 const int cnt = seg_end - base;
-                if (cnt > 4 * sweep::NT)
+                if (cnt > 8 * sweep::NT)
+                    shadow_item<12, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
+                else if (cnt > 4 * sweep::NT)
                     shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
                 else if (cnt > 2 * sweep::NT)
                     shadow_item<4, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);

@@ -81,7 +81,7 @@
 #define SWEEP_NT 256
 #endif
 #ifndef SWEEP_MINB
-#define SWEEP_MINB 3
+#define SWEEP_MINB 2
 #endif
 #ifndef SWEEP_STAGES
 #define SWEEP_STAGES 4
@@ -189,51 +189,63 @@ __device__ __forceinline__ float qterm_qbar(const float4 row, float qbar, float 
 // Everything runs in the FMA pipe (measured on B200, tools/sweep_mb3.cu: a scalar FMA-pipe instruction costs ~1.3
 // issue cycles, a LOP3/SHF/FMNMX on the half-rate ALU pipe ~2, and the two do not overlap in this loop):
 //   x' = sat(p*A_u + q_u)   y' = sat(p*A_v + q_v)   z' = sat(p*A_w + q_w)      3 FFMA.SAT per pair
-//   acc += (x' * y') * z'                                                        1 FMUL + 1 FFMA per pair
+//   acc += (x' * y') * z'                                                        1 FMUL + 1 FFMA per pair (packed: below)
 // A candidate pair contributes exactly 1, any other pair something in [0,1), so after GROUP triangles
 // "sum of the accumulators >= 1" is a necessary condition for the group to hold a candidate.  Straight-line FFMA /
 // FMUL / LDS.128 stream, no branch per triangle.  Returns bit g set = triangles [g*GROUP, (g+1)*GROUP) may hold one.
-constexpr int GROUP = 4; // triangles per accumulator group
-constexpr int NACC = 4;  // independent accumulators (dependent FFMA chains) per group
+// The conjunction runs on ray PAIRS in packed form (FMUL2 + FFMA2, fma.rn.f32x2): on this part a packed instruction
+// costs ~2.2 issue cycles for two FMAs against ~2.6 for two scalar ones; the saturating row evaluations stay scalar
+// (fma.sat has no f32x2 form).  Measured (tools/sweep_mb3.cu, shared q): scalar conjunction 5.05 Tpairs/s at R = 8,
+// packed 5.41 at R = 8 and 5.71 at R = 12.
+template <int R>
+struct Batch {
+    static_assert(R % 2 == 0, "rays are evaluated in pairs");
+    static constexpr int GROUP = R >= 12 ? 4 : 8;                   // triangles per accumulator group
+    static constexpr int NACC = R >= 12 ? 3 : (R >= 4 ? 2 : 1);     // independent packed accumulators (FFMA2 chains) per group
+    static constexpr int NGROUPS = BATCH / GROUP;
+};
 
 template <int R, int MODE>
 __device__ __forceinline__ unsigned eval_batch(const float4 *__restrict__ tp, const float (&rp)[R], const float (&rq)[R], float qbar,
                                                float qdelta) {
-    constexpr int NA = R < NACC ? R : NACC;
+    constexpr int GROUP = Batch<R>::GROUP, NA = Batch<R>::NACC;
     unsigned cand = 0;
 #pragma unroll
     for (int g = 0; g < BATCH / GROUP; ++g) {
-        float acc[NA];
+        float2 acc[NA];
 #pragma unroll
-        for (int a = 0; a < NA; ++a) acc[a] = 0.f;
+        for (int a = 0; a < NA; ++a) acc[a] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int kk = 0; kk < GROUP; ++kk) {
             const int k = g * GROUP + kk;
             const float4 rb = tp[3 * k], rc = tp[3 * k + 1], rd = tp[3 * k + 2];
             if (MODE == MODE_OWNQ) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float x = __saturatef(fmaf(rp[r], rb.x, fmaf(rq[r], rb.y, rb.z)));
-                    const float y = __saturatef(fmaf(rp[r], rc.x, fmaf(rq[r], rc.y, rc.z)));
-                    const float z = __saturatef(fmaf(rp[r], rd.x, fmaf(rq[r], rd.y, rd.z)));
-                    acc[r % NA] = fmaf(__fmul_rn(x, y), z, acc[r % NA]);
+                for (int r = 0; r < R; r += 2) {
+                    const float2 x = make_float2(__saturatef(fmaf(rp[r], rb.x, fmaf(rq[r], rb.y, rb.z))),
+                                                 __saturatef(fmaf(rp[r + 1], rb.x, fmaf(rq[r + 1], rb.y, rb.z))));
+                    const float2 y = make_float2(__saturatef(fmaf(rp[r], rc.x, fmaf(rq[r], rc.y, rc.z))),
+                                                 __saturatef(fmaf(rp[r + 1], rc.x, fmaf(rq[r + 1], rc.y, rc.z))));
+                    const float2 z = make_float2(__saturatef(fmaf(rp[r], rd.x, fmaf(rq[r], rd.y, rd.z))),
+                                                 __saturatef(fmaf(rp[r + 1], rd.x, fmaf(rq[r + 1], rd.y, rd.z))));
+                    acc[(r / 2) % NA] = __ffma2_rn(__fmul2_rn(x, y), z, acc[(r / 2) % NA]);
                 }
             } else {
                 const float qx = MODE == MODE_QBAR ? qterm_qbar(rb, qbar, qdelta) : fmaf(rq[0], rb.y, rb.z);
                 const float qy = MODE == MODE_QBAR ? qterm_qbar(rc, qbar, qdelta) : fmaf(rq[0], rc.y, rc.z);
                 const float qz = MODE == MODE_QBAR ? qterm_qbar(rd, qbar, qdelta) : fmaf(rq[0], rd.y, rd.z);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float x = __saturatef(fmaf(rp[r], rb.x, qx));
-                    const float y = __saturatef(fmaf(rp[r], rc.x, qy));
-                    const float z = __saturatef(fmaf(rp[r], rd.x, qz));
-                    acc[r % NA] = fmaf(__fmul_rn(x, y), z, acc[r % NA]);
+                for (int r = 0; r < R; r += 2) {
+                    const float2 x = make_float2(__saturatef(fmaf(rp[r], rb.x, qx)), __saturatef(fmaf(rp[r + 1], rb.x, qx)));
+                    const float2 y = make_float2(__saturatef(fmaf(rp[r], rc.x, qy)), __saturatef(fmaf(rp[r + 1], rc.x, qy)));
+                    const float2 z = make_float2(__saturatef(fmaf(rp[r], rd.x, qz)), __saturatef(fmaf(rp[r + 1], rd.x, qz)));
+                    acc[(r / 2) % NA] = __ffma2_rn(__fmul2_rn(x, y), z, acc[(r / 2) % NA]);
                 }
             }
         }
-        float sum = acc[0];
+        float sum = 0.f;
 #pragma unroll
-        for (int a = 1; a < NA; ++a) sum += acc[a];
+        for (int a = 0; a < NA; ++a) sum += acc[a].x + acc[a].y;
         if (sum >= 1.f) cand |= 1u << g;
     }
     return cand;
@@ -318,6 +330,7 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
 #ifdef SWEEP_NO_STRICT // development microbenchmark only (tools/sweep_mb2.cu): timing without the strict path
                 if (cand) ++done;
 #else
+                constexpr int GROUP = Batch<R>::GROUP;
                 if (EXHAUSTIVE) cand = (1u << (BATCH / GROUP)) - 1u;
                 while (cand) {
                     // rare: a group of GROUP triangles may hold a candidate.  Rebuild the per-ray candidate mask of each

@@ -308,6 +308,7 @@ int launch_shadow_light(Ctx &g, bool ex, const trk::ShadowLightParams &p, unsign
     return ex ? launch_shadow_light_t<true>(g, p, bar, st) : launch_shadow_light_t<false>(g, p, bar, st);
 }
 int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+    if (R == 12) return ex ? launch_primary_t<12, true>(p, grid, st) : launch_primary_t<12, false>(p, grid, st);
     if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
     if (R == 4) return ex ? launch_primary_t<4, true>(p, grid, st) : launch_primary_t<4, false>(p, grid, st);
     return ex ? launch_primary_t<2, true>(p, grid, st) : launch_primary_t<2, false>(p, grid, st);
@@ -334,10 +335,10 @@ Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int ext
         return (int)((n_rays + (int64_t)sweep::NT * R - 1) / ((int64_t)sweep::NT * R)) + extra_blocks;
     };
     Decomp d{2, blocks_for(2), 1};
-    if (forced_R == 2 || forced_R == 4 || forced_R == 8) {
+    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == 12) {
         d.R = forced_R, d.n_blocks = blocks_for(forced_R);
     } else {
-        for (int R : {8, 4, 2}) {
+        for (int R : {12, 8, 4, 2}) {
             d.R = R, d.n_blocks = blocks_for(R);
             if ((int64_t)d.n_blocks * slices_possible >= 4 * (int64_t)n_sms) break;
         }
@@ -992,27 +993,34 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             s->allcand_built = true, ++launches;
         }
         // Triangle chunks: after each one the still-unoccluded rays are compacted (early exit, main.cpp:324).  Equal chunks
-        // keep the pairs swept past a ray's occluder lowest (x1.12 at 32 chunks) and win when a light has many shadow
-        // rays; with few rays (small frames, one band share of a multi-GPU frame) the per-chunk tails weigh more and
-        // boundaries that start fine (1/64 of the triangles: most occluded rays find their occluder early) and coarsen
-        // geometrically win (12 chunks, x1.19).  The kernel picks the scheme from the live-ray count it finds.
-        // opts.shadow_chunks asks for that many equal chunks.
+        // keep the pairs swept past a ray's occluder lowest (x1.056 at 64 chunks; x1.11 at 32) and win when a light has many
+        // shadow rays; with few rays (small frames, one band share of a multi-GPU frame) a chunk's fixed cost (three grid
+        // barriers, the compaction passes, the sweep's tail: ~0.1 ms) weighs more, and 20 chunks that start fine (1/64 of the
+        // triangles: most occluded rays find their occluder early) and coarsen win (x1.10).  The kernel picks the scheme from
+        // the live-ray count it finds.  opts.shadow_chunks asks for that many equal chunks.
         trk::ShadowLightParams sp{};
         {
-            const int nc = std::min({n_tiles, trk::SL_MAXCHUNK, o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(32, n_tiles / 8))});
+            const int nc = std::min({n_tiles, trk::SL_MAXCHUNK, o.shadow_chunks > 0 ? o.shadow_chunks : std::max(1, std::min(64, n_tiles / 8))});
             sp.n_chunks[1] = nc;
             for (int c = 0; c <= nc; ++c) sp.bounds[1][c] = (int)((int64_t)n_tiles * c / nc);
             if (o.shadow_chunks > 0 || n_tiles < 64) {
                 sp.n_chunks[0] = nc;
                 std::memcpy(sp.bounds[0], sp.bounds[1], sizeof sp.bounds[0]);
             } else {
-                const int fr[] = {0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
-                sp.n_chunks[0] = 12;
-                for (int c = 0; c <= 12; ++c) sp.bounds[0][c] = (int)((int64_t)n_tiles * fr[c] / 64);
+                std::vector<int> fr{0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64};
+                int den = 64;
+                if (const char *e = std::getenv("TRACER_GEO")) { // development knob: "den,f1,f2,...,den"
+                    fr.assign(1, 0);
+                    den = std::atoi(e);
+                    for (const char *q = std::strchr(e, ','); q; q = std::strchr(q + 1, ',')) fr.push_back(std::atoi(q + 1));
+                }
+                sp.n_chunks[0] = (int)fr.size() - 1;
+                for (size_t c = 0; c < fr.size(); ++c) sp.bounds[0][c] = (int)((int64_t)n_tiles * fr[c] / den);
             }
         }
         sp.many_rays = (long long)1 << 20;
         sp.items_per_cta = items_per_cta();
+        sp.min_tiles = std::getenv("TRACER_MIN_TILES") ? std::max(1, std::atoi(std::getenv("TRACER_MIN_TILES"))) : 1;
         sp.allcand = s->allcand_table, sp.table_stride = s->table_stride;
         sp.n_tris = s->n_tris, sp.n_tiles = n_tiles, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
         sp.list[0] = s->list, sp.list[1] = s->list_b;
@@ -1118,7 +1126,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // FP32 flops the sweeps execute per swept pair (all in the FMA pipe; FFMA = 2, FMUL = 1): the three edge rows, plus
     // the conjunction x'*y'*z' accumulated per pair (FMUL + FFMA = 3).  Shadow sweeps: (6 + 3R) FFMA per R pairs for the
     // rows when a thread's R = 8 q-sorted rays share one q-term per row.
-    s->stats.flop_primary_edges = flop_primary, s->stats.flop_shadow_edges = cull ? 0.0 : 2.0 * (6 + 3 * 8) / 8;
+    s->stats.flop_primary_edges = flop_primary, s->stats.flop_shadow_edges = cull ? 0.0 : 2.0 * (6 + 3 * trk::SHADOW_R) / trk::SHADOW_R;
     s->stats.flop_primary = cull ? 0.0 : flop_primary + 3.0, s->stats.flop_shadow = cull ? 0.0 : s->stats.flop_shadow_edges + 3.0;
     if (hc.cull_overflow) {
         // the optional mode's candidate buffer (24 per ray + slack) was too small for this scene's depth complexity: render

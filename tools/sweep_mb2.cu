@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(NTH, MINBLK) k_prod(const float4 *table, int n
 #pragma unroll
         for (int r = 0; r < R; ++r) rp[r] = seed * (tid + 1) * (r + 1 + blk), rq[r] = seed * (tid + 7) * 3;
         unsigned done = 0;
-        sweep_table<R, MODE, ANYHIT, false>(sm, table, 0, n_tiles, n_tiles * TILE, rp, rq, rq[0], 1e-6f, 0xffu >> (8 - R), done, gtile, n_swept,
+        sweep_table<R, MODE, ANYHIT, false>(sm, table, 0, n_tiles, n_tiles * TILE, rp, rq, rq[0], 1e-6f, (1u << R) - 1u, done, gtile, n_swept,
                                             [&](unsigned, int, unsigned) { return 0u; });
         acc += done;
         __syncthreads();
@@ -176,6 +176,12 @@ int main() {
         cudaMemcpy(table, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
         cudaMalloc(&work, 4);
         printf("-- production data path (TMA tile pipeline, per-warp stage recycling), %d tiles per item\n", n_tiles);
+        bench_prod<12, MODE_SHAREDQ, false, 256, 2>(table, n_tiles, work, out, 2);
+        bench_prod<12, MODE_SHAREDQ, false, 256, 2>(table, n_tiles, work, out, 8);
+        bench_prod<8, MODE_SHAREDQ, false, 256, 2>(table, n_tiles, work, out, 2);
+        bench_prod<12, MODE_QBAR, true, 256, 2>(table, n_tiles, work, out, 2);
+        bench_prod<8, MODE_QBAR, true, 256, 2>(table, n_tiles, work, out, 2);
+        bench_prod<12, MODE_OWNQ, false, 256, 2>(table, n_tiles, work, out, 2);
         bench_prod<8, MODE_SHAREDQ, false, 512, 1>(table, n_tiles, work, out, 2);
         bench_prod<8, MODE_SHAREDQ, false, 512, 2>(table, n_tiles, work, out, 2);
         bench_prod<8, MODE_SHAREDQ, false, 256, 3>(table, n_tiles, work, out, 2);
