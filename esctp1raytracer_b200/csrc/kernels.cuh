@@ -103,11 +103,15 @@ struct TableParam {
 };
 
 // K: the margin for unit directions; K2u: the second margin (same units); returns the scaled float row
-__device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K, double K2u) {
+// row3: the same row before the second margin and the scaling, in FP64: a pair the reference could accept satisfies
+// p*row3[0] + q*row3[1] + row3[2] >= 0 in exact arithmetic (input of the span rows, span_rows below)
+__device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K, double K2u, double *row3) {
     const double A = tp.U[0] * vx + tp.U[1] * vy + tp.U[2] * vz;
     const double B = tp.V[0] * vx + tp.V[1] * vy + tp.V[2] * vz;
     const double K1 = K2u * tp.dmax;
-    const double C = tp.W[0] * vx + tp.W[1] * vy + tp.W[2] * vz + K * tp.dmax * 1.0001 + K1; // first margin + K2
+    const double C0 = tp.W[0] * vx + tp.W[1] * vy + tp.W[2] * vz + K * tp.dmax * 1.0001; // first margin
+    row3[0] = A, row3[1] = B, row3[2] = C0;
+    const double C = C0 + K1; // + K2
     // S = 2^k >= 1 / (0.9 K2).  |row| / K2 is bounded by ~1/(8 eps) by construction, so the scaled row stays far inside
     // the float range; should that ever fail (or K2 be 0) the row becomes "always candidate": the strict path decides.
     const double mag = fmax(fabs(A), fmax(fabs(B), fabs(C)));
@@ -120,15 +124,96 @@ __device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, d
     return make_float4((float)A * Sf, (float)B * Sf, (float)C * Sf, 0.f);
 }
 
+// SPAN rows (sweep.cuh, 4.): the three exact rows  p*A_i + q*B_i + C_i >= 0  as two lower and two upper bounds of p.
+//   A_i > 0:  p >= q*beta + gamma     A_i < 0:  p <= q*beta + gamma      beta = -B_i/A_i, gamma = -C_i/A_i
+// stored in row units with the +1 of the saturating test:  lower (-S*beta, 1 - S*gamma + M),  upper (S*beta, 1 + S*gamma + M).
+// M covers the float evaluation of the bound (coefficients rounded to float, one or two FFMA roundings, |q| <= QMAX):
+// M = 8 eps (QMAX S|beta| + S|gamma| + 1), so that a pair satisfying the exact row reaches >= 1 and saturates to exactly 1.
+// A row whose A is tiny against its other terms (|A| < 1e-9 (PMAX|A| + QMAX|B| + |C|)) barely depends on p: it is replaced
+// by (A', B, C + PMAX(|A'| + |A|)) with |A'| = that threshold, which is weaker for every |p| <= PMAX, and may take either
+// sign, i.e. fill a lower or an upper slot.  Three bounds on the same side (a triangle whose cone reaches around the
+// parametrisation plane: only for triangles that span tens of degrees as seen from O) keep the two that lose the least
+// area of the (p,q) box; dropping a bound only loosens the filter.  Rows that are not finite make the triangle "always
+// candidate" (the strict path decides).
+constexpr double SPAN_PMAX = 1.0625, SPAN_QMAX = 1.0625; // |p|, |q| of every ray swept in span form (image plane: [0,1]; cube faces: [-1,1])
+
+struct SpanBound {
+    double beta, gamma;
+};
+__device__ __forceinline__ void span_rows(const double (&rows)[3][3], float4 &lo, float4 &hi) {
+    const double S = (double)sweep::SPAN_S, eps = (double)TRC_EPS;
+    const float OPEN = sweep::SPAN_OPEN;
+    lo = make_float4(0.f, OPEN, 0.f, OPEN), hi = make_float4(0.f, OPEN, 0.f, OPEN); // no bound at all: always candidate
+    SpanBound L[3], U[3];
+    int nl = 0, nu = 0;
+    double flexB[3], flexC[3], flexA[3]; // rows that barely depend on p: B, widened C, |A'|
+    int nf = 0;
+    for (int i = 0; i < 3; ++i) {
+        const double A = rows[i][0], B = rows[i][1], C = rows[i][2];
+        const double mag = SPAN_PMAX * fabs(A) + SPAN_QMAX * fabs(B) + fabs(C);
+        if (!(mag < 1e30)) return;  // inf / NaN: always candidate
+        if (mag == 0.0) continue;   // 0 >= 0: no bound
+        const double amin = 1e-9 * mag;
+        if (fabs(A) < amin) {
+            flexA[nf] = amin, flexB[nf] = B, flexC[nf] = C + SPAN_PMAX * (amin + fabs(A)), ++nf;
+        } else if (A > 0.0) {
+            L[nl].beta = -B / A, L[nl].gamma = -C / A, ++nl;
+        } else {
+            U[nu].beta = -B / A, U[nu].gamma = -C / A, ++nu;
+        }
+    }
+    for (int i = 0; i < nf; ++i) { // A' = +|A'| is a lower bound, A' = -|A'| an upper one: take the side with room
+        if (nl <= nu) L[nl].beta = -flexB[i] / flexA[i], L[nl].gamma = -flexC[i] / flexA[i], ++nl;
+        else U[nu].beta = flexB[i] / flexA[i], U[nu].gamma = flexC[i] / flexA[i], ++nu;
+    }
+    // three bounds on one side: drop the one whose removal adds the least area inside the box (sampled in q)
+    auto drop_one = [&](SpanBound *b, int &n, bool lower) {
+        if (n < 3) return;
+        double loss[3] = {0, 0, 0};
+        for (int sidx = 0; sidx < 17; ++sidx) {
+            const double q = -SPAN_QMAX + 2.0 * SPAN_QMAX * sidx / 16.0;
+            double c[3];
+            for (int i = 0; i < 3; ++i) c[i] = fmin(SPAN_PMAX, fmax(-SPAN_PMAX, q * b[i].beta + b[i].gamma));
+            for (int j = 0; j < 3; ++j) {
+                const double o1 = c[(j + 1) % 3], o2 = c[(j + 2) % 3];
+                if (lower) loss[j] += fmax(0.0, c[j] - fmax(o1, o2)); // lower bounds: the binding one is the maximum
+                else loss[j] += fmax(0.0, fmin(o1, o2) - c[j]);
+            }
+        }
+        int j = 0;
+        if (loss[1] < loss[j]) j = 1;
+        if (loss[2] < loss[j]) j = 2;
+        b[j] = b[2];
+        n = 2;
+    };
+    drop_one(L, nl, true), drop_one(U, nu, false);
+    float *lof = &lo.x, *hif = &hi.x;
+    for (int i = 0; i < nl; ++i) {
+        const double M = 8.0 * eps * (SPAN_QMAX * S * fabs(L[i].beta) + S * fabs(L[i].gamma) + 1.0);
+        const double b = -S * L[i].beta, c = 1.0 - S * L[i].gamma + M;
+        if (!(fabs(b) < 1e30) || !(fabs(c) < 1e30)) continue; // cannot be represented: leave the bound open
+        lof[2 * i] = (float)b, lof[2 * i + 1] = (float)c;
+    }
+    for (int i = 0; i < nu; ++i) {
+        const double M = 8.0 * eps * (SPAN_QMAX * S * fabs(U[i].beta) + S * fabs(U[i].gamma) + 1.0);
+        const double b = S * U[i].beta, c = 1.0 + S * U[i].gamma + M;
+        if (!(fabs(b) < 1e30) || !(fabs(c) < 1e30)) continue;
+        hif[2 * i] = (float)b, hif[2 * i + 1] = (float)c;
+    }
+}
+
+// table: the 48-byte three-row table (MODE_OWNQ sweeps, bundle-cull mode) or null; span: the 32-byte span table or null
 __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tris, int n_pad, const TableParam tp,
-                                   float4 *__restrict__ table) {
+                                   float4 *__restrict__ table, float4 *__restrict__ span) {
     const double ox = tp.o[0], oy = tp.o[1], oz = tp.o[2], lmax = tp.lmax;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
-    float4 rb, rc, rd;
+    float4 rb, rc, rd, slo, shi;
     if (i >= n_tris) { // padding rows: never candidate
         rb = rc = rd = make_float4(0.f, 0.f, -1.f, 0.f);
+        slo = make_float4(0.f, -sweep::SPAN_OPEN, 0.f, -sweep::SPAN_OPEN), shi = make_float4(0.f, sweep::SPAN_OPEN, 0.f, sweep::SPAN_OPEN);
     } else {
+        double rows[3][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}}; // exact rows behind rb, rc, rd (always true unless set)
         const float *p = tri_verts + 9 * (size_t)i;
         const double v0x = p[0], v0y = p[1], v0z = p[2];
         const double e1x = (double)p[3] - v0x, e1y = (double)p[4] - v0y, e1z = (double)p[5] - v0z;
@@ -170,8 +255,8 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
                     if (kappa < 1.0) {
                         // second margin: a fraction of the slab's own width, never below the evaluation noise of a unit row
                         const double k2 = fmax(kappa / 8.0, 16.0 * eps);
-                        rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37, k2);
-                        rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37, k2);
+                        rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37, k2, rows[0]);
+                        rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37, k2, rows[1]);
                     }
                 }
             }
@@ -179,26 +264,36 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
             const double s = tprime > 0 ? 1.0 : -1.0;
             // round K up a little so the float row never under-states it
             const double Kd = K * 1.0000002 + 1e-37;
-            rb = project_row(tp, s * Bx, s * By, s * Bz, Kd, Kd);
-            rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd, Kd);
-            rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd, Kd);
+            rb = project_row(tp, s * Bx, s * By, s * Bz, Kd, Kd, rows[0]);
+            rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd, Kd, rows[1]);
+            rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd, Kd, rows[2]);
         }
         // rb.w (bundle-cull mode only): a lower bound of the distance from O to any point X of the triangle,
         // |X - O| >= |V - O| - |X - V| >= max(la, lb, lc) - emax, less a slack far above the float noise of the
         // reference's own t2.  A shadow ray that ends at O and is shorter than this cannot hit the triangle.
         if (lmax > 0.0) rb.w = (float)fmax(0.0, (fmax(la, fmax(lb, lc)) - emax - 1e-4 * reach) * 0.999999);
+        if (span) span_rows(rows, slo, shi);
     }
-    table[3 * (size_t)i] = rb;
-    table[3 * (size_t)i + 1] = rc;
-    table[3 * (size_t)i + 2] = rd;
+    if (table) {
+        table[3 * (size_t)i] = rb;
+        table[3 * (size_t)i + 1] = rc;
+        table[3 * (size_t)i + 2] = rd;
+    }
+    if (span) {
+        span[2 * (size_t)i] = slo;
+        span[2 * (size_t)i + 1] = shi;
+    }
 }
 
 // every row a candidate: the group of rays whose assumptions failed (never observed in practice)
-__global__ void build_allcand_table(int n_tris, int n_pad, float4 *__restrict__ table) {
+__global__ void build_allcand_table(int n_tris, int n_pad, float4 *__restrict__ table, float4 *__restrict__ span) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     const float4 r = make_float4(0.f, 0.f, i < n_tris ? 1.f : -1.f, 0.f);
     table[3 * (size_t)i] = table[3 * (size_t)i + 1] = table[3 * (size_t)i + 2] = r;
+    const float lo = i < n_tris ? sweep::SPAN_OPEN : -sweep::SPAN_OPEN;
+    span[2 * (size_t)i] = make_float4(0.f, lo, 0.f, lo);
+    span[2 * (size_t)i + 1] = make_float4(0.f, sweep::SPAN_OPEN, 0.f, sweep::SPAN_OPEN);
 }
 
 // ---------------------------------------------------------------------------------
@@ -215,7 +310,7 @@ constexpr unsigned long long KEY_NONE = 0xffffffffffffffffull;
 struct PrimaryParams {
     Cam cam;
     Bands bands;
-    const float4 *table; // eye table
+    const float4 *table; // eye table: span rows when the rays of a thread share q, three-row table with jittered samples
     int n_tiles, n_tris;
     const float *tri_verts;
     unsigned long long *best; // [n_px] merged closest-hit keys over triangles, KEY_NONE = miss
@@ -592,7 +687,7 @@ __global__ void iota_kernel(int *a, int n) {
 // so the pairs actually swept track the reference's own early-exit count (main.cpp:324) and the host is not in
 // the loop at all: block offsets, slice counts, the chunk scheme and the early stop ("every ray has its occluder")
 // are decided on the device.  Round 1 ran A/B/C as 4 launches per chunk with host read-backs in between.
-constexpr int SHADOW_R = 12;    // rays per thread of a full shadow-ray block (blocks of NT * SHADOW_R consecutive list entries)
+constexpr int SHADOW_R = 16;    // rays per thread of a full shadow-ray block (blocks of NT * SHADOW_R consecutive list entries)
 constexpr int SL_MAXF = 1022;   // ray groups per launch (the host batches bigger lights: 146 vertices x NFACE)
 constexpr int SL_MAXCHUNK = 64;
 constexpr int CBLK = 1024;      // list entries per compaction block
@@ -808,7 +903,7 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
                 // thread instead of dragging empty lanes through every triangle (late chunks have few rays in many groups).
                 const int cnt = seg_end - base;
                 if (cnt > 8 * sweep::NT)
-                    shadow_item<12, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
+                    shadow_item<SHADOW_R, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
                 else if (cnt > 4 * sweep::NT)
                     shadow_item<8, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
                 else if (cnt > 2 * sweep::NT)

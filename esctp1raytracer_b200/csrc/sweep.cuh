@@ -96,9 +96,18 @@ constexpr int THREADS = 512;       // threads per CTA of the bundle-cull kernels
 constexpr int NT = SWEEP_NT;       // threads per CTA of the default sweeps
 constexpr int MINB = SWEEP_MINB;   // CTAs per SM of the default sweeps
 constexpr float CK = 64.f;         // safety factor of the filter margins (units of FLT_EPSILON)
-constexpr uint32_t TILE_BYTES = TILE * 3 * sizeof(float4);
+constexpr uint32_t TILE_BYTES = TILE * 3 * sizeof(float4); // 48-byte rows (MODE_OWNQ, bundle-cull mode, tools/)
+constexpr float SPAN_S = 65536.f;  // span rows: row units per unit of p (a power of two: p * SPAN_S is exact)
+constexpr float SPAN_OPEN = 1e30f; // span rows: an unused bound
 
+// MODE_OWNQ sweeps the 48-byte three-row table (every ray its own q: jittered primary rays); MODE_SHAREDQ and MODE_QBAR
+// sweep the 32-byte SPAN table (4. below)
 enum { MODE_OWNQ = 0, MODE_SHAREDQ = 1, MODE_QBAR = 2 };
+template <int MODE>
+struct Rows {
+    static constexpr int N = MODE == MODE_OWNQ ? 3 : 2;                // float4 per triangle
+    static constexpr uint32_t BYTES = TILE * N * sizeof(float4);      // per staged tile
+};
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+; sm_100a here) -------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,7 +210,7 @@ template <int R>
 struct Batch {
     static_assert(R % 2 == 0, "rays are evaluated in pairs");
     static constexpr int GROUP = R >= 12 ? 4 : 8;                   // triangles per accumulator group
-    static constexpr int NACC = R >= 12 ? 3 : (R >= 4 ? 2 : 1);     // independent packed accumulators (FFMA2 chains) per group
+    static constexpr int NACC = R >= 16 ? 4 : R >= 12 ? 3 : (R >= 4 ? 2 : 1); // independent packed accumulators (FFMA2 chains) per group
     static constexpr int NGROUPS = BATCH / GROUP;
 };
 
@@ -251,6 +260,66 @@ __device__ __forceinline__ unsigned eval_batch(const float4 *__restrict__ tp, co
     return cand;
 }
 
+// ---- SPAN form -------------------------------------------------------------------------------------------------------
+// For rays that share q the three affine rows p*A_i + (q*B_i + C_i) >= 0 are half-lines in p: p >= c_i(q) where A_i > 0,
+// p <= c_i(q) where A_i < 0, with c_i(q) = q*beta_i + gamma_i, beta = -B/A, gamma = -C/A (divided once per (origin,
+// triangle) in FP64, kernels.cuh: build_origin_table).  A triangle in front of the parametrisation plane has two lower
+// bounds and one upper bound or the reverse, so the 32-byte span row holds two of each, already in row units and with the
+// +1 of the saturating test folded in:
+//     lo = (Bl1, Cl1, Bl2, Cl2):  a_i = q*Bl_i + Cl_i = 1 - S*(c_i(q) - margin)      ax = min(a_1, a_2)
+//     hi = (Bu1, Cu1, Bu2, Cu2):  b_i = q*Bu_i + Cu_i = 1 + S*(c_i(q) + margin)      ay = min(b_1, b_2)
+// and a pair is a candidate iff  x = sat(S*p + ax)  and  y = sat(ay - S*p)  are both exactly 1.  Per thread and triangle:
+// 4 FFMA + 2 FMNMX (8 FFMA in MODE_QBAR, which adds |B|*qdelta to every bound); per PAIR: 2 FADD.SAT + half a packed
+// FFMA2 (acc += x*y), against 3 FFMA.SAT + FMUL2/2 + FFMA2/2 of the three-row form.  Measured (tools/sweep_mb4.cu, B200):
+// 8.9 Tpairs/s at 16 rays per thread, 9.3 at 24, against 5.7 for the three-row loop at 12.
+__device__ __forceinline__ void span_terms(const float4 lo, const float4 hi, float q, float &ax, float &ay) {
+    ax = fminf(fmaf(q, lo.x, lo.y), fmaf(q, lo.z, lo.w));
+    ay = fminf(fmaf(q, hi.x, hi.y), fmaf(q, hi.z, hi.w));
+}
+__device__ __forceinline__ void span_terms_qbar(const float4 lo, const float4 hi, float qbar, float qdelta, float &ax, float &ay) {
+    ax = fminf(fmaf(fabsf(lo.x), qdelta, fmaf(qbar, lo.x, lo.y)), fmaf(fabsf(lo.z), qdelta, fmaf(qbar, lo.z, lo.w)));
+    ay = fminf(fmaf(fabsf(hi.x), qdelta, fmaf(qbar, hi.x, hi.y)), fmaf(fabsf(hi.z), qdelta, fmaf(qbar, hi.z, hi.w)));
+}
+// per-ray test of the (rare) candidate path: ps = p * SPAN_S, the ray's own q
+__device__ __forceinline__ bool span_pass(const float4 lo, const float4 hi, float ps, float q) {
+    float ax, ay;
+    span_terms(lo, hi, q, ax, ay);
+    return fminf(ps + ax, ay - ps) >= 1.f;
+}
+
+// BATCH triangles of a staged span tile against the R rays of this thread (ps[r] = p_r * SPAN_S).  A candidate pair
+// contributes exactly 1 to its accumulator, any other pair something in [0,1).  Returns bit g set = triangles
+// [g*GROUP, (g+1)*GROUP) may hold a candidate.
+template <int R, int MODE>
+__device__ __forceinline__ unsigned eval_span(const float4 *__restrict__ tp, const float (&ps)[R], float q, float qdelta) {
+    constexpr int GROUP = Batch<R>::GROUP, NA = Batch<R>::NACC;
+    unsigned cand = 0;
+#pragma unroll
+    for (int g = 0; g < BATCH / GROUP; ++g) {
+        float2 acc[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) acc[a] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int kk = 0; kk < GROUP; ++kk) {
+            const int k = g * GROUP + kk;
+            float ax, ay;
+            if (MODE == MODE_QBAR) span_terms_qbar(tp[2 * k], tp[2 * k + 1], q, qdelta, ax, ay);
+            else span_terms(tp[2 * k], tp[2 * k + 1], q, ax, ay);
+#pragma unroll
+            for (int r = 0; r < R; r += 2) {
+                const float2 x = make_float2(__saturatef(ps[r] + ax), __saturatef(ps[r + 1] + ax));
+                const float2 y = make_float2(__saturatef(ay - ps[r]), __saturatef(ay - ps[r + 1]));
+                acc[(r / 2) % NA] = __ffma2_rn(x, y, acc[(r / 2) % NA]);
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) sum += acc[a].x + acc[a].y;
+        if (sum >= 1.f) cand |= 1u << g;
+    }
+    return cand;
+}
+
 // The LOP3 form of the same loop (round 1; kept for tools/sweep_mb3.cu): sign bits OR-ed per ray, AND-ed over rays,
 // shifted into a bit register.  Returns bit (BATCH-1-k) CLEAR = some ray of this thread may hit triangle k.
 template <int R, int MODE, int UNROLL>
@@ -290,17 +359,24 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
                                             const float (&rp)[R], const float (&rq)[R], float qbar, float qdelta, unsigned valid,
                                             unsigned &done, unsigned &gtile, unsigned &n_tiles_swept, Strict &&strict,
                                             unsigned *n_pipe_err = nullptr) {
+    constexpr int ROWS = Rows<MODE>::N;
+    constexpr uint32_t BYTES = Rows<MODE>::BYTES;
+    constexpr bool SPAN = MODE != MODE_OWNQ;
     const int tid = threadIdx.x;
     const int n_tiles = tile_hi - tile_lo;
-    const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * 3;
+    const float4 *__restrict__ src = table + (size_t)tile_lo * TILE * ROWS;
     if (tid == 0) {
         const int first = n_tiles < STAGES ? n_tiles : STAGES;
         for (int i = 0; i < first; ++i) {
             const unsigned g = gtile + i;
-            mbar_expect_tx(&sm.full_bar[g % STAGES], TILE_BYTES);
-            tma_load_1d(sm.tile[g % STAGES], src + (size_t)i * TILE * 3, TILE_BYTES, &sm.full_bar[g % STAGES]);
+            mbar_expect_tx(&sm.full_bar[g % STAGES], BYTES);
+            tma_load_1d(sm.tile[g % STAGES], src + (size_t)i * TILE * ROWS, BYTES, &sm.full_bar[g % STAGES]);
         }
     }
+    float ps[R]; // span form: the rays' p in row units (exact: SPAN_S is a power of two)
+#pragma unroll
+    for (int r = 0; r < R; ++r) ps[r] = rp[r] * SPAN_S;
+    const float qhot = MODE == MODE_QBAR ? qbar : rq[0];
     for (int it = 0; it < n_tiles; ++it) {
         const unsigned g = gtile + it;
         const int s = g % STAGES;
@@ -311,8 +387,8 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
         auto tile_differs = [&]() {
             unsigned bad = 0;
             const uint4 *a = reinterpret_cast<const uint4 *>(sm.tile[s]);
-            const uint4 *b = reinterpret_cast<const uint4 *>(src + (size_t)it * TILE * 3);
-            for (int i = tid & 31; i < TILE * 3; i += 32) {
+            const uint4 *b = reinterpret_cast<const uint4 *>(src + (size_t)it * TILE * ROWS);
+            for (int i = tid & 31; i < TILE * ROWS; i += 32) {
                 const uint4 x = a[i], y = __ldcg(&b[i]);
                 bad |= (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w);
             }
@@ -326,11 +402,16 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
             const float4 *__restrict__ tp = sm.tile[s];
 #pragma unroll 1
             for (int b0 = 0; b0 < TILE; b0 += BATCH) {
-                unsigned cand = eval_batch<R, MODE>(tp + 3 * b0, rp, rq, qbar, qdelta);
+                unsigned cand;
+                if (SPAN) cand = eval_span<R, MODE>(tp + ROWS * b0, ps, qhot, qdelta);
+                else cand = eval_batch<R, MODE>(tp + ROWS * b0, rp, rq, qbar, qdelta);
 #ifdef SWEEP_NO_STRICT // development microbenchmark only (tools/sweep_mb2.cu): timing without the strict path
                 if (cand) ++done;
 #else
                 constexpr int GROUP = Batch<R>::GROUP;
+                // validation mode: every group goes to the strict path; the hot loop's own verdict is kept so that an
+                // accepted pair whose group it would have skipped counts as a filter miss too
+                const unsigned cand_hot = cand;
                 if (EXHAUSTIVE) cand = (1u << (BATCH / GROUP)) - 1u;
                 while (cand) {
                     // rare: a group of GROUP triangles may hold a candidate.  Rebuild the per-ray candidate mask of each
@@ -342,10 +423,17 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
                     for (int kk = 0; kk < GROUP; ++kk) {
                         const int k = b0 + gq * GROUP + kk;
                         const int tri = (tile_lo + it) * TILE + k;
-                        const float4 rb = lds128_opaque(&tp[3 * k]), rc = lds128_opaque(&tp[3 * k + 1]), rd = lds128_opaque(&tp[3 * k + 2]);
                         unsigned filt = 0;
+                        if (SPAN) {
+                            const float4 lo = lds128_opaque(&tp[2 * k]), hi = lds128_opaque(&tp[2 * k + 1]);
 #pragma unroll
-                        for (int r = 0; r < R; ++r) filt |= (unsigned)edge_pass(rb, rc, rd, rp[r], rq[r]) << r;
+                            for (int r = 0; r < R; ++r) filt |= (unsigned)span_pass(lo, hi, ps[r], rq[r]) << r;
+                        } else {
+                            const float4 rb = lds128_opaque(&tp[3 * k]), rc = lds128_opaque(&tp[3 * k + 1]), rd = lds128_opaque(&tp[3 * k + 2]);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) filt |= (unsigned)edge_pass(rb, rc, rd, rp[r], rq[r]) << r;
+                        }
+                        if (EXHAUSTIVE && !((cand_hot >> gq) & 1u)) filt = 0;
                         const unsigned live = valid & ~done;
                         const unsigned mask = EXHAUSTIVE ? live : (filt & live);
                         if (mask && tri < n_tris) {
@@ -368,8 +456,8 @@ __device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__
                 sm.consumed[s] = 0;
                 __threadfence_block();
                 if (it + STAGES < n_tiles) {
-                    mbar_expect_tx(&sm.full_bar[s], TILE_BYTES);
-                    tma_load_1d(sm.tile[s], src + (size_t)(it + STAGES) * TILE * 3, TILE_BYTES, &sm.full_bar[s]);
+                    mbar_expect_tx(&sm.full_bar[s], BYTES);
+                    tma_load_1d(sm.tile[s], src + (size_t)(it + STAGES) * TILE * ROWS, BYTES, &sm.full_bar[s]);
                 }
             }
         }

@@ -140,12 +140,13 @@ struct tracer_scene_dev {
     std::vector<int> h_light_vbase, h_light_F;
     std::vector<float> h_light_verts;
     double bb_lo[3], bb_hi[3];
-    float4 *eye_table = nullptr, *light_tables = nullptr, *allcand_table = nullptr;
+    float4 *eye_table = nullptr, *light_tables = nullptr, *allcand_table = nullptr; // 48-byte three-row tables
+    float4 *eye_span = nullptr, *light_spans = nullptr, *allcand_span = nullptr;    // 32-byte span tables (same slots)
     std::vector<double> table_lmax; // per (light vertex, cube face): reach bound it was built for, < 0 = not built
     int table_slots = 1;            // light vertices whose 6 face tables fit at once (and per persistent-kernel launch)
     bool tables_resident = true;    // every light vertex has its own slot: tables are kept across lights and frames
     bool allcand_built = false;
-    size_t table_stride = 0; // float4 per table
+    size_t table_stride = 0, span_stride = 0; // float4 per table
     // per-frame workspace
     int ws_npx = 0, ws_L = 0;
     int *hit_tri = nullptr, *rj = nullptr, *list = nullptr, *list_b = nullptr, *faceid = nullptr, *dbg_occ = nullptr;
@@ -212,11 +213,6 @@ int launch_primary_q(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     trk::primary_kernel<R, EX, SQ><<<grid, sweep::NT, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
-}
-template <int R, bool EX>
-int launch_primary_t(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
-    // rays of one thread share q unless the sample positions are jittered (extension)
-    return p.bands.spp_n > 1 ? launch_primary_q<R, EX, false>(p, grid, st) : launch_primary_q<R, EX, true>(p, grid, st);
 }
 int scene_create_on(Ctx &g, const tracer_scene_flat *sc, tracer_scene_dev **out);
 
@@ -308,10 +304,17 @@ int launch_shadow_light(Ctx &g, bool ex, const trk::ShadowLightParams &p, unsign
     return ex ? launch_shadow_light_t<true>(g, p, bar, st) : launch_shadow_light_t<false>(g, p, bar, st);
 }
 int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
-    if (R == 12) return ex ? launch_primary_t<12, true>(p, grid, st) : launch_primary_t<12, false>(p, grid, st);
-    if (R == 8) return ex ? launch_primary_t<8, true>(p, grid, st) : launch_primary_t<8, false>(p, grid, st);
-    if (R == 4) return ex ? launch_primary_t<4, true>(p, grid, st) : launch_primary_t<4, false>(p, grid, st);
-    return ex ? launch_primary_t<2, true>(p, grid, st) : launch_primary_t<2, false>(p, grid, st);
+    if (p.bands.spp_n > 1) { // jittered samples (extension): every ray its own q, three-row table
+        if (R == 12) return ex ? launch_primary_q<12, true, false>(p, grid, st) : launch_primary_q<12, false, false>(p, grid, st);
+        if (R == 8) return ex ? launch_primary_q<8, true, false>(p, grid, st) : launch_primary_q<8, false, false>(p, grid, st);
+        if (R == 4) return ex ? launch_primary_q<4, true, false>(p, grid, st) : launch_primary_q<4, false, false>(p, grid, st);
+        return ex ? launch_primary_q<2, true, false>(p, grid, st) : launch_primary_q<2, false, false>(p, grid, st);
+    }
+    if (R == 24) return ex ? launch_primary_q<24, true, true>(p, grid, st) : launch_primary_q<24, false, true>(p, grid, st);
+    if (R == 16) return ex ? launch_primary_q<16, true, true>(p, grid, st) : launch_primary_q<16, false, true>(p, grid, st);
+    if (R == 8) return ex ? launch_primary_q<8, true, true>(p, grid, st) : launch_primary_q<8, false, true>(p, grid, st);
+    if (R == 4) return ex ? launch_primary_q<4, true, true>(p, grid, st) : launch_primary_q<4, false, true>(p, grid, st);
+    return ex ? launch_primary_q<2, true, true>(p, grid, st) : launch_primary_q<2, false, true>(p, grid, st);
 }
 // Work decomposition of a sweep: R rays per thread (8 preferred: best amortisation of the row loads) and
 // n_slices triangle slices, chosen so that ray blocks x slices keeps every SM busy for several items.
@@ -329,16 +332,18 @@ int items_per_cta() {
     return forced > 0 ? forced : 24;
 }
 
-Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks) {
+Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks, bool own_q) {
     const int slices_possible = std::max(1, n_tiles / 4); // at least 4 tiles per slice
     auto blocks_for = [&](int R) {
         return (int)((n_rays + (int64_t)sweep::NT * R - 1) / ((int64_t)sweep::NT * R)) + extra_blocks;
     };
     Decomp d{2, blocks_for(2), 1};
-    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == 12) {
+    // span form (rays of a thread share q): 24, 16, 8, 4 or 2 rays per thread; three-row form (own q): 12, 8, 4 or 2
+    const int big = own_q ? 12 : 24, mid = own_q ? 8 : 16;
+    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == mid || forced_R == big) {
         d.R = forced_R, d.n_blocks = blocks_for(forced_R);
     } else {
-        for (int R : {12, 8, 4, 2}) {
+        for (int R : {big, mid, 8, 4, 2}) {
             d.R = R, d.n_blocks = blocks_for(R);
             if ((int64_t)d.n_blocks * slices_possible >= 4 * (int64_t)n_sms) break;
         }
@@ -349,9 +354,11 @@ Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int ext
     return d;
 }
 
-int build_table(const tracer_scene_dev *s, const trk::TableParam &tp, float4 *table, cudaStream_t st) {
-    const int th = 256;
-    trk::build_origin_table<<<(s->n_pad + th - 1) / th, th, 0, st>>>(s->tri_verts, s->n_tris, s->n_pad, tp, table);
+// both forms of the filter table of one origin: the 48-byte rows (jittered primary rays, bundle-cull mode) and the
+// 32-byte span rows (default sweeps)
+int build_table(const tracer_scene_dev *s, const trk::TableParam &tp, float4 *table, float4 *span, cudaStream_t st) {
+    const int th = 128;
+    trk::build_origin_table<<<(s->n_pad + th - 1) / th, th, 0, st>>>(s->tri_verts, s->n_tris, s->n_pad, tp, table, span);
     CK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -445,6 +452,7 @@ void tracer_cuda_scene_destroy(tracer_scene_dev *s) {
     dev_free(s->tri_verts), dev_free(s->tri_normals), dev_free(s->geom_material), dev_free(s->sphere_material);
     dev_free(s->tri_geom), dev_free(s->geom_has_normals), dev_free(s->spheres), dev_free(s->light_vbase);
     dev_free(s->light_verts), dev_free(s->eye_table), dev_free(s->light_tables), dev_free(s->allcand_table);
+    dev_free(s->eye_span), dev_free(s->light_spans), dev_free(s->allcand_span);
     dev_free(s->hit_tri), dev_free(s->rj), dev_free(s->best), dev_free(s->best_occ), dev_free(s->list), dev_free(s->list_b);
     dev_free(s->faceid), dev_free(s->dbg_occ), dev_free(s->cnt_b), dev_free(s->accum_total);
     dev_free(s->hit_t), dev_free(s->hit_v), dev_free(s->carry), dev_free(s->nrm), dev_free(s->accum);
@@ -493,7 +501,7 @@ int scene_create_on(Ctx &g, const tracer_scene_flat *sc, tracer_scene_dev **out)
     s->ctx = &g;
     s->n_geoms = G, s->n_tris = N, s->n_lights = sc->n_lights, s->n_spheres = sc->n_spheres;
     s->n_pad = std::max(1, (N + cull::CTILE - 1) / cull::CTILE) * cull::CTILE; // multiple of both tile sizes
-    s->table_stride = (size_t)s->n_pad * 3;
+    s->table_stride = (size_t)s->n_pad * 3, s->span_stride = (size_t)s->n_pad * 2;
 #define TRY(x)                         \
     do {                               \
         int rc_ = (x);                 \
@@ -577,7 +585,7 @@ int scene_create_on(Ctx &g, const tracer_scene_flat *sc, tracer_scene_dev **out)
         // small next to the O(rays x N) sweep it serves).  The reference renders any light size, and so does this.
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const size_t per_vertex = 6 * s->table_stride * sizeof(float4);
+        const size_t per_vertex = 6 * (s->table_stride + s->span_stride) * sizeof(float4);
         const size_t budget = free_b / 2;
         const char *cap_env = std::getenv("TRACER_TABLE_SLOTS"); // test knob: pretend only this many vertices fit
         size_t fit = std::max<size_t>(1, budget / per_vertex);
@@ -588,6 +596,9 @@ int scene_create_on(Ctx &g, const tracer_scene_flat *sc, tracer_scene_dev **out)
     TRY(dev_alloc(&s->eye_table, s->table_stride));
     TRY(dev_alloc(&s->light_tables, s->table_stride * 6 * (size_t)std::max(1, s->tables_resident ? s->V : s->table_slots)));
     TRY(dev_alloc(&s->allcand_table, s->table_stride));
+    TRY(dev_alloc(&s->eye_span, s->span_stride));
+    TRY(dev_alloc(&s->light_spans, s->span_stride * 6 * (size_t)std::max(1, s->tables_resident ? s->V : s->table_slots)));
+    TRY(dev_alloc(&s->allcand_span, s->span_stride));
     s->table_lmax.assign((size_t)6 * s->V, -1.0);
     const size_t n_groups = (size_t)s->maxF * trk::NFACE;
     TRY(dev_alloc(&s->seg_count, n_groups + 1));
@@ -688,7 +699,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             tp.dmax = std::max(tp.dmax, std::sqrt(n2));
         }
         tp.lmax = 0.0;
-        if (int rc = build_table(s, tp, s->eye_table, st)) return rc;
+        if (int rc = build_table(s, tp, s->eye_table, s->eye_span, st)) return rc;
         ++launches;
     }
     CK_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(sweep::Counters), st));
@@ -814,9 +825,10 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         CK_CUDA(cudaGetLastError());
         launches += 3;
     } else {
-        const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0);
+        const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0, bands.spp_n > 1);
         trk::PrimaryParams p{};
-        p.cam = dc, p.bands = bands, p.table = s->eye_table, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
+        // rays of one thread share q unless the sample positions are jittered (extension): span table, else three-row table
+        p.cam = dc, p.bands = bands, p.table = bands.spp_n > 1 ? s->eye_table : s->eye_span, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
         p.tri_verts = s->tri_verts;
         p.best = s->best, p.counters = s->counters, p.work = s->work;
         p.n_rows = n_rows, p.n_blocks = 0; // ray blocks = screen tiles of (TX R) x (512 / TX) pixels: least edge waste wins
@@ -830,7 +842,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         if (p.n_blocks < want_items) // same sizing rule as pick_decomp, on the real block count
             p.n_slices = std::max(1, std::min((want_items + p.n_blocks - 1) / p.n_blocks, std::max(1, n_tiles / 4)));
         const int grid = std::min(p.n_blocks * p.n_slices, sweep::MINB * g.n_sms);
-        flop_primary = bands.spp_n > 1 ? 12.0 : 2.0 * (3 + 3 * d.R) / d.R;
+        // executed FP32 flops per pair: span form 2 FADD + 1 FFMA per pair and 4 FFMA per thread and triangle; three-row
+        // form with every ray its own q: 6 FFMA.SAT + FMUL + FFMA
+        flop_primary = bands.spp_n > 1 ? 15.0 : 4.0 + 8.0 / d.R;
         if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, p, grid, st)) return rc;
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
                                                                         s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
@@ -869,7 +883,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             const int face = gi % trk::NFACE, vtx = s->h_light_vbase[k] + gi / trk::NFACE;
             if (face == trk::NFACE - 1) {
                 if (!s->allcand_built) {
-                    trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table);
+                    trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table, s->allcand_span);
                     CK_CUDA(cudaGetLastError());
                     s->allcand_built = true, ++launches;
                 }
@@ -880,7 +894,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             if (built >= need) continue;
             built = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
             const trk::TableParam tp = face_param(&s->h_light_verts[3 * (size_t)vtx], face, built);
-            if (int rc = build_table(s, tp, s->light_tables + ((size_t)vtx * 6 + face) * s->table_stride, st)) return rc;
+            if (int rc = build_table(s, tp, s->light_tables + ((size_t)vtx * 6 + face) * s->table_stride,
+                                     s->light_spans + ((size_t)vtx * 6 + face) * s->span_stride, st))
+                return rc;
             ++launches;
         }
         return 0;
@@ -988,7 +1004,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         CK_CUDA(cudaMemsetAsync(s->best_occ, 0xff, sizeof(unsigned long long) * (size_t)n_px, st));
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k], st));
         if (!s->allcand_built) {
-            trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table);
+            trk::build_allcand_table<<<(s->n_pad + 255) / 256, 256, 0, st>>>(s->n_tris, s->n_pad, s->allcand_table, s->allcand_span);
             CK_CUDA(cudaGetLastError());
             s->allcand_built = true, ++launches;
         }
@@ -1021,7 +1037,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         sp.many_rays = (long long)1 << 20;
         sp.items_per_cta = items_per_cta();
         sp.min_tiles = std::getenv("TRACER_MIN_TILES") ? std::max(1, std::atoi(std::getenv("TRACER_MIN_TILES"))) : 1;
-        sp.allcand = s->allcand_table, sp.table_stride = s->table_stride;
+        sp.allcand = s->allcand_span, sp.table_stride = s->span_stride; // the default sweeps read the span tables
         sp.n_tris = s->n_tris, sp.n_tiles = n_tiles, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
         sp.list[0] = s->list, sp.list[1] = s->list_b;
         sp.blk_cnt = s->blk_cnt, sp.px = px, sp.spheres = s->spheres, sp.n_spheres = s->n_spheres;
@@ -1042,10 +1058,12 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
                         built = need * 1.5; // head-room so that camera moves rarely trigger a rebuild
                     }
                     const trk::TableParam tp = face_param(&s->h_light_verts[3 * (size_t)(vb + v)], face, need * 1.5);
-                    if (int rc = build_table(s, tp, s->light_tables + (slot * 6 + face) * s->table_stride, st)) return rc;
+                    if (int rc = build_table(s, tp, s->light_tables + (slot * 6 + face) * s->table_stride,
+                                             s->light_spans + (slot * 6 + face) * s->span_stride, st))
+                        return rc;
                     ++launches;
                 }
-            sp.tables = s->light_tables + (s->tables_resident ? (size_t)(vb + b0) : 0) * 6 * s->table_stride;
+            sp.tables = s->light_spans + (s->tables_resident ? (size_t)(vb + b0) : 0) * 6 * s->span_stride;
             sp.F = (b1 - b0) * trk::NFACE;
             sp.seg_off = s->seg_off + b0 * trk::NFACE;
             sp.cnt[0] = s->cursor + b0 * trk::NFACE, sp.cnt[1] = s->cnt_b + b0 * trk::NFACE;
@@ -1126,8 +1144,10 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // FP32 flops the sweeps execute per swept pair (all in the FMA pipe; FFMA = 2, FMUL = 1): the three edge rows, plus
     // the conjunction x'*y'*z' accumulated per pair (FMUL + FFMA = 3).  Shadow sweeps: (6 + 3R) FFMA per R pairs for the
     // rows when a thread's R = 8 q-sorted rays share one q-term per row.
-    s->stats.flop_primary_edges = flop_primary, s->stats.flop_shadow_edges = cull ? 0.0 : 2.0 * (6 + 3 * trk::SHADOW_R) / trk::SHADOW_R;
-    s->stats.flop_primary = cull ? 0.0 : flop_primary + 3.0, s->stats.flop_shadow = cull ? 0.0 : s->stats.flop_shadow_edges + 3.0;
+    s->stats.flop_primary = cull ? 0.0 : flop_primary, s->stats.flop_shadow = cull ? 0.0 : 4.0 + 16.0 / trk::SHADOW_R;
+    // of which multiply-adds that evaluate bounds (the rest is the two saturating adds and the accumulate of each pair)
+    s->stats.flop_primary_edges = cull ? 0.0 : (bands.spp_n > 1 ? 12.0 : flop_primary - 4.0);
+    s->stats.flop_shadow_edges = cull ? 0.0 : 16.0 / trk::SHADOW_R;
     if (hc.cull_overflow) {
         // the optional mode's candidate buffer (24 per ray + slack) was too small for this scene's depth complexity: render
         // the frame again with a 4x larger one while that fits comfortably, else by the default sweeps, which need no such

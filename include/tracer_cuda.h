@@ -110,7 +110,8 @@ typedef struct tracer_render_opts {
 
     int32_t exhaustive_strict; /* debug: bypass the conservative filter, strict-test every pair */
     int32_t samples_per_pixel; /* extension (parity unpinned): 0/1 = reference; n*n stratified jitter */
-    int32_t rays_per_thread;   /* tuning: 0 = auto, else 2, 4, 8 or 12 rays per thread in the closest-hit sweep */
+    int32_t rays_per_thread;   /* tuning: 0 = auto, else 2, 4, 8, 16 or 24 rays per thread in the closest-hit sweep
+                                  (2, 4, 8 or 12 with jittered samples) */
     int32_t shadow_chunks;     /* tuning: 0 = auto; triangle chunks between shadow-ray compactions */
     int32_t bundle_cull;       /* OPTIONAL mode: hierarchical (bundle box -> warp box -> ray) evaluation of the same
                                   conservative filter; identical results.  1 = two-phase (dense block-box pass, then
@@ -141,12 +142,14 @@ typedef struct tracer_frame_stats {
     int64_t filter_misses;  /* exhaustive_strict only: strict accepts the filter would have lost (must be 0) */
     int32_t kernel_launches;
     int32_t n_sms;
-    double flop_primary;    /* FP32 flops the closest-hit sweep executes per swept pair, all in the FMA pipe: edge rows
-                               (below) + 3 (FMUL + FFMA of the conjunction); 0 in bundle-cull mode              */
-    double flop_shadow;     /* same for the any-hit sweeps                                                      */
-    /* of which the three edge rows alone (the rest, 3 per pair, is the conjunction x'*y'*z' += in the FMA pipe):
-     * closest hit 2*(3+3R)/R = 6.75 when the R = 8 rays of a thread share q (no jitter), else 12;
-     * any-hit 2*(6+3R)/R = 7.5 (R = 8 q-sorted rays of a thread share one q-term per edge row) */
+    double flop_primary;    /* FP32 flops the closest-hit sweep executes per swept pair, all in the FMA pipe (FFMA = 2,
+                               FADD = FMUL = 1).  Span form (no jitter: the R rays of a thread share q): per pair two
+                               saturating adds and one multiply-add, per thread and triangle 4 FFMA: 4 + 8/R.  Jittered
+                               samples (three-row form, every ray its own q): 6 FFMA + FMUL + FFMA = 15.
+                               0 in bundle-cull mode                                                              */
+    double flop_shadow;     /* same for the any-hit sweeps (span form, R = 16 q-sorted rays share one q-term per bound:
+                               8 FFMA per thread and triangle): 4 + 16/R                                          */
+    /* of which the multiply-adds that evaluate the bounds / edge rows (the rest is each pair's conjunction) */
     double flop_primary_edges;
     double flop_shadow_edges;
     int64_t pipeline_errors; /* exhaustive_strict only: the sweeps' own race check — staged table tiles (TMA pipeline,
