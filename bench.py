@@ -469,16 +469,22 @@ def main():
         swept_pairs = tot["tests_primary"] + tot["tests_shadow"]
         sweep_s = max(sweep_ms_max * 1e-3, 1e-12)
         alg_flop = flop_primary * tot["tests_primary"] + flop_shadow * tot["tests_shadow_ref"]
-        alg_flop_edges = flop_primary_e * tot["tests_primary"] + flop_shadow_e * tot["tests_shadow_ref"]
+        # FMA-pipe view: every FADD / FMUL / FFMA is one lane-operation of the pipe whose peak is peak_tflops / 2 lane-ops
+        # per second (an FFMA counts two flops, a saturating FADD one, yet both hold a lane for one cycle); a packed FFMA2
+        # is two.  Span form: 2 FADD.SAT + half an FFMA2 per pair + the bound FFMAs per thread = 3 + (flop - 4) / 2;
+        # three-row form with own q (jittered samples): 6 FFMA.SAT + FMUL + FFMA = 8
+        def lane_ops(flop):
+            return 8.0 if flop >= 15.0 else (3.0 + (flop - 4.0) / 2.0 if flop > 0 else 0.0)
+        alg_lane_ops = lane_ops(flop_primary) * tot["tests_primary"] + lane_ops(flop_shadow) * tot["tests_shadow_ref"]
         swept_flop = flop_primary * tot["tests_primary"] + flop_shadow * tot["tests_shadow"]
         achieved = alg_flop / n_gpus / sweep_s / 1e12  # per GPU
-        achieved_edges = alg_flop_edges / n_gpus / sweep_s / 1e12
+        achieved_lane = alg_lane_ops / n_gpus / sweep_s / 1e12  # T lane-ops/s per GPU
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             pass
-        prim_bytes = 48.0 * scene.n_tris * (1 + scene.n_lights * 2) + 36.0 * scene.n_tris
+        prim_bytes = 32.0 * scene.n_tris * (1 + scene.n_lights * 2) + 36.0 * scene.n_tris
         hbm_gbs = (prim_bytes + 3.0 * W * H / n_gpus) * args.steps / (ms * 1e-3) / 1e9
         traffic = traffic_detail = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
         for tf in ("r02_traffic.json", "r01_traffic.json"):
@@ -512,16 +518,23 @@ def main():
                                "(variants 0, 3) and packed FFMA2 chains (variant 1); MEASURED_PEAKS.json has no FP32 figure",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "peak_variants_tflops": peaks,
                 "peak_scalar_ffma": max(peaks[0], peaks[3]), "frac_of_scalar_ffma_peak": achieved / max(peaks[0], peaks[3]),
-                "flop_per_pair": {"primary": flop_primary, "shadow": flop_shadow, "primary_edge_rows_only": flop_primary_e,
-                                  "shadow_edge_rows_only": flop_shadow_e,
-                                  "note": "FP32 flops the sweeps execute per (ray, triangle) pair, all in the FMA pipe (FFMA = 2, FMUL = 1).  Edge "
-                                          "rows: three 2-D affine rows = 6 FFMA = 12 when each ray evaluates its own; both sweeps compute the "
-                                          "q-term of each row once per thread: closest hit (3 + 3*8) FFMA / 8 pairs = 6.75 (8 rays of one image "
-                                          "row share q exactly), shadow (6 + 3*8) / 8 = 7.5 (8 consecutive rays of the q-sorted list: mean q plus "
-                                          "|B| * spread, still a necessary condition).  Conjunction: the rows are saturating (fma.sat, pre-scaled "
-                                          "so that a possible hit gives exactly 1), acc += (x'*y')*z' = FMUL + FFMA = 3 flops per pair; there is "
-                                          "no integer/ALU-pipe instruction per pair (round 1 used LOP3 sign tests)"},
-                "achieved_edge_rows_only": achieved_edges, "frac_edge_rows_only": achieved_edges / peak_tflops,
+                "flop_per_pair": {"primary": flop_primary, "shadow": flop_shadow, "primary_bounds_only": flop_primary_e,
+                                  "shadow_bounds_only": flop_shadow_e,
+                                  "note": "FP32 flops the sweeps execute per (ray, triangle) pair, all in the FMA pipe (FFMA = 2, FADD = 1).  "
+                                          "Span form (csrc/sweep.cuh): for rays that share q the three affine edge rows of a triangle are "
+                                          "two lower and two upper bounds of p; per thread and triangle 4 FFMA + 2 FMNMX evaluate them "
+                                          "(closest hit: R = 24 pixels of one image row share q exactly; shadow: 8 FFMA, R = 16 q-sorted rays "
+                                          "share mean q + |B| * spread, still a necessary condition); per PAIR x = sat(S p + ax), "
+                                          "y = sat(ay - S p) (2 FADD.SAT = 2 flops) and acc += x*y (half a packed FFMA2 = 2 flops): "
+                                          "4 + 8/R resp. 4 + 16/R flops.  No integer/ALU-pipe instruction per pair.  Because half of the "
+                                          "per-pair instructions are adds (1 flop per lane-cycle instead of 2) the flop fraction under-states "
+                                          "how busy the FMA pipe is: see fma_pipe"},
+                "fma_pipe": {"lane_ops_per_pair": {"primary": lane_ops(flop_primary), "shadow": lane_ops(flop_shadow)},
+                             "achieved_tlaneops": achieved_lane, "peak_tlaneops": peak_tflops / 2.0, "frac": achieved_lane / (peak_tflops / 2.0),
+                             "frac_of_nominal": achieved_lane / (nominal / 2.0),
+                             "note": "FMA-pipe lane-operations (FADD, FMUL, FFMA = 1 each, packed FFMA2 = 2) of the algorithmic pairs per "
+                                     "second against the measured peak in the same unit (peak TFLOP/s / 2): the issue-slot view of the "
+                                     "same kernel time"},
                 "algorithmic_pairs_per_step": alg_pairs / args.steps,
                 "swept_pairs_per_step": swept_pairs / args.steps, "sweep_ms_per_step": sweep_ms_max / args.steps,
                 "executed_tflops": swept_flop / n_gpus / sweep_s / 1e12,
@@ -532,10 +545,11 @@ def main():
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / n_gpus / sweep_s / 1e12,
                 "ceiling_note": "the loop is FMA-pipe issue bound: on this part a scalar FMA-pipe instruction costs ~1.3 issue cycles (own "
                                 "microbenchmark: scalar FFMA chains peak at 0.745 per cycle and scheduler = peak_scalar_ffma; only packed FFMA2 "
-                                "reaches 0.92), independent of occupancy (tools/sweep_mb2.cu: 256-1024 threads x 1-6 CTAs/SM all within 2 %); "
-                                "per pair the loop issues 3 FFMA.SAT + FMUL + FFMA + (q-terms, 3 LDS.128)/8 (profiles/r02_*)",
+                                "reaches 0.92), independent of occupancy; per pair the loop issues 2 FADD.SAT + FFMA2/2, per thread and "
+                                "triangle 4 (shadow: 8) FFMA + 2 FMNMX + 2 LDS.128 (tools/sweep_mb4.cu: 9.3 Tpairs/s at R = 24, "
+                                "8.2 at R = 16 with shared mean q; profiles/r02_*)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
-                        "streams": "filter tables (48 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
+                        "streams": "span tables (32 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},
             },
             "cpu_baseline": cpu, "optional_bundle_cull_mode": cull_extra,
             "rays_per_step": rays / args.steps, "strict_evals_per_step": tot["strict_evals"] / args.steps,
