@@ -14,11 +14,11 @@ synthetic 1M-triangle + 1k-sphere scene at 3840x2160, 4 lights ("c4").  Other wo
 `e2e`    : N = 1: the literal drop-in call tracer_cuda_render(scene, camera, W, H, opts, rgb_out) with HOST buffers
            every step — pinned host scene -> HBM, filter-table build, render, packed frame -> pinned host.
            N > 1: per rank scene upload + render + band gather, rank 0 reads the assembled frame back.
-`roofline`: FP32-FMA bound (no tensor cores on this path).  achieved = FP32 flops the sweeps execute per
-           (ray, triangle) pair (all in the FMA pipe, reported by the library: edge rows + the conjunction
-           accumulate) x ALGORITHMIC pairs (P*N primary + the reference's own in-order count for shadow rays)
-           / sweep-kernel time; peak = our own FFMA microbenchmark measured in the same process
-           (MEASURED_PEAKS.json has no FP32 number); nominal peak and the edge-rows-only figure printed beside it.
+`roofline`: FP32-FMA bound (no tensor cores on this path).  achieved = FP32 flops the sweeps' formulation needs per
+           (ray, triangle) pair (all in the FMA pipe, reported by the library: span form 4 + 8/R) x ALGORITHMIC pairs
+           (P*N primary + the reference's own in-order count for shadow rays) / sweep-kernel time; peak = our own FFMA
+           microbenchmark measured in the same process (MEASURED_PEAKS.json has no FP32 number).  Beside it: the nominal
+           peak, the ceiling of this instruction mix, the as-issued flop count and the FMA-pipe lane-op utilisation.
 `cpu_baseline`: the UNMODIFIED reference compiled from /root/reference (kind "reference"; oracle/_ref_release =
            its own Release flags -O3 -ffast-math for timing, oracle/_ref = strict build beside it) or the plain-C
            port, on a bounded pixel sample of the same workload; plus serial-1-core, the reference's --thread scheme,
@@ -479,6 +479,13 @@ def main():
         swept_flop = flop_primary * tot["tests_primary"] + flop_shadow * tot["tests_shadow"]
         achieved = alg_flop / n_gpus / sweep_s / 1e12  # per GPU
         achieved_lane = alg_lane_ops / n_gpus / sweep_s / 1e12  # T lane-ops/s per GPU
+        # As issued: ptxas folds the exact power-of-two scaling of p into each saturating add (FFMA.SAT R, p, 65536, ax,
+        # profiles/r02_l_sass_primary_span_hot_loop.txt), so the SASS executes two FFMA where the formulation needs two
+        # FADD: +2 flops per pair on the span form.  Reported beside the fraction, never as it.
+        def issued(flop):
+            return flop if flop >= 15.0 or flop <= 0 else flop + 2.0
+        issued_flop = issued(flop_primary) * tot["tests_primary"] + issued(flop_shadow) * tot["tests_shadow_ref"]
+        achieved_issued = issued_flop / n_gpus / sweep_s / 1e12
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -529,6 +536,14 @@ def main():
                                           "4 + 8/R resp. 4 + 16/R flops.  No integer/ALU-pipe instruction per pair.  Because half of the "
                                           "per-pair instructions are adds (1 flop per lane-cycle instead of 2) the flop fraction under-states "
                                           "how busy the FMA pipe is: see fma_pipe"},
+                "mix_ceiling_frac": alg_flop / (2.0 * alg_lane_ops) if alg_lane_ops else None,
+                "mix_ceiling_note": "the fraction this instruction mix would reach with every FMA-pipe lane-cycle used: saturating adds "
+                                    "count 1 flop per lane-cycle, multiply-adds 2 (SURVEY 8d asks for this ceiling beside every fraction)",
+                "as_issued": {"flop_per_pair": {"primary": issued(flop_primary), "shadow": issued(flop_shadow)},
+                              "tflops": achieved_issued, "frac": achieved_issued / peak_tflops, "frac_of_nominal": achieved_issued / nominal,
+                              "note": "NOT roofline.frac: the SASS issues each saturating add as FFMA.SAT with an immediate scale "
+                                      "(R = sat(p * 65536 + ax); the product is exact), i.e. the FMA pipe executes 6 + 8/R flops per pair; "
+                                      "roofline.frac counts the 4 + 8/R the formulation needs"},
                 "fma_pipe": {"lane_ops_per_pair": {"primary": lane_ops(flop_primary), "shadow": lane_ops(flop_shadow)},
                              "achieved_tlaneops": achieved_lane, "peak_tlaneops": peak_tflops / 2.0, "frac": achieved_lane / (peak_tflops / 2.0),
                              "frac_of_nominal": achieved_lane / (nominal / 2.0),

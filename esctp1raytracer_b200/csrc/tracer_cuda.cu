@@ -310,6 +310,7 @@ int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaSt
         if (R == 4) return ex ? launch_primary_q<4, true, false>(p, grid, st) : launch_primary_q<4, false, false>(p, grid, st);
         return ex ? launch_primary_q<2, true, false>(p, grid, st) : launch_primary_q<2, false, false>(p, grid, st);
     }
+    if (R == 32) return ex ? launch_primary_q<32, true, true>(p, grid, st) : launch_primary_q<32, false, true>(p, grid, st);
     if (R == 24) return ex ? launch_primary_q<24, true, true>(p, grid, st) : launch_primary_q<24, false, true>(p, grid, st);
     if (R == 16) return ex ? launch_primary_q<16, true, true>(p, grid, st) : launch_primary_q<16, false, true>(p, grid, st);
     if (R == 8) return ex ? launch_primary_q<8, true, true>(p, grid, st) : launch_primary_q<8, false, true>(p, grid, st);
@@ -329,7 +330,7 @@ int items_per_cta() {
         const char *e = std::getenv("TRACER_ITEMS_PER_CTA");
         return e ? std::atoi(e) : 0;
     }();
-    return forced > 0 ? forced : 24;
+    return forced > 0 ? forced : 48;
 }
 
 Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks, bool own_q) {
@@ -338,9 +339,10 @@ Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int ext
         return (int)((n_rays + (int64_t)sweep::NT * R - 1) / ((int64_t)sweep::NT * R)) + extra_blocks;
     };
     Decomp d{2, blocks_for(2), 1};
-    // span form (rays of a thread share q): 24, 16, 8, 4 or 2 rays per thread; three-row form (own q): 12, 8, 4 or 2
-    const int big = own_q ? 12 : 24, mid = own_q ? 8 : 16;
-    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == mid || forced_R == big) {
+    // span form (rays of a thread share q): 32, 16, 8, 4 or 2 rays per thread (24 on request); three-row form (own q): 12, 8, 4 or 2
+    // (C4 closest-hit sweep on one B200: 997 ms at 16, 944 at 24, 905 at 32)
+    const int big = own_q ? 12 : 32, mid = own_q ? 8 : 16;
+    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == mid || forced_R == big || (!own_q && forced_R == 24)) {
         d.R = forced_R, d.n_blocks = blocks_for(forced_R);
     } else {
         for (int R : {big, mid, 8, 4, 2}) {

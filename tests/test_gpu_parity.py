@@ -474,3 +474,55 @@ def test_bundle_cull_overflow_rerenders_in_default_mode(renderer):
             assert b.stats["flop_primary"] > 0  # the statistics are the default sweeps'
     finally:
         del os.environ["TRACER_CAND_CAP"]
+
+
+def test_span_sweeps_every_rays_per_thread_variant(renderer, restated):
+    """The default sweeps evaluate the filter in SPAN form (two lower + two upper bounds of p per triangle, sweep.cuh).
+    Every rays-per-thread instantiation of the closest-hit sweep (2..32; screen tiles of different shapes) must give the
+    oracle's frame, and exhaustive mode — which also checks the hot loop's own group verdicts — must find no accept the
+    filter would have lost."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    s = scenes.soup_scene(12000, 12, 3, seed=21, edge=(0.02, 0.4))
+    W, H = 300, 70  # wider than one 256-pixel tile row of the 32-ray variant, ragged at both edges
+    cam = Camera.for_frame((0, 1, 3), (0, 1, 0), W, H)
+    rs = renderer.upload(s)
+    o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=hash_faceids(9, W, H, s.faces_per_light))
+    for R in (0, 2, 4, 8, 16, 24, 32):
+        a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=9, debug=True, rays_per_thread=R)
+        _check_frame(a, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), False, occ=o.occ_tri)
+        b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=9, debug=True, rays_per_thread=R, exhaustive_strict=True)
+        assert b.stats["filter_misses"] == 0 and b.stats["pipeline_errors"] == 0, R
+        _same_frames(a, b)
+
+
+def test_span_rows_with_huge_and_degenerate_triangles(renderer, restated):
+    """Span rows divide each edge row by its p-coefficient.  Stress what that could break: triangles that span tens of
+    degrees as seen from the eye and from the lights (cones that reach around the parametrisation plane: three bounds on
+    one side, one is dropped), edges parallel to the p axis (coefficient ~ 0), zero-area and needle triangles, triangles
+    through the eye's plane.  Frames equal the oracle; exhaustive mode finds no filter miss."""
+    from esctp1raytracer_b200 import RNG_HASH, Camera, hash_faceids, scenes
+
+    rng = np.random.default_rng(5)
+    s = scenes.soup_scene(200, 6, 2, seed=31, edge=(0.2, 1.5))  # big triangles all around the eye and the lights
+    v = s.tri_verts.reshape(-1, 3, 3).copy()  # triangles 0-3: floor and wall, 4-7: the two lights (left alone)
+    for i in range(8, 40):  # axis-aligned edges: rows whose p- or q-coefficient vanishes
+        v[i, 1] = v[i, 0] + np.array([rng.uniform(0.2, 2.0), 0.0, 0.0], np.float32)
+        v[i, 2] = v[i, 0] + np.array([0.0, rng.uniform(0.2, 2.0), 0.0], np.float32)
+    for i in range(40, 60):  # needles and zero-area triangles
+        v[i, 1] = v[i, 0] + np.float32(1e-6) * rng.normal(size=3).astype(np.float32)
+        v[i, 2] = v[i, 0] + (v[i, 1] - v[i, 0]) * np.float32(2.0) if i % 2 else v[i, 0]
+    for i in range(60, 90):  # through the plane of the eye (z = 3): the cone wraps around the image plane
+        v[i, 0, 2], v[i, 1, 2], v[i, 2, 2] = 2.0, 4.5, 3.0
+    s.tri_verts = np.ascontiguousarray(v, np.float32)
+    for (W, H, eye, look) in ((160, 90, (0, 1, 3), (0, 1, 0)), (97, 61, (0.3, 0.8, 0.5), (0.1, 1.0, -1.0))):
+        cam = Camera.for_frame(eye, look, W, H)
+        rs = renderer.upload(s)
+        a = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=2, debug=True)
+        b = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=2, debug=True, exhaustive_strict=True)
+        assert b.stats["filter_misses"] == 0 and b.stats["pipeline_errors"] == 0
+        _same_frames(a, b)
+        o = restated.render(to_flat(s), cam.as_array(), W, H, faceid=hash_faceids(2, W, H, s.faces_per_light))
+        _check_frame(a, W, H, o.tri, o.t, o.v, o.rgb, o.rgb8.reshape(-1, 3), False, occ=o.occ_tri)
+        # the filter must still filter
+        assert a.stats["strict_evals"] < 0.5 * b.stats["strict_evals"]
