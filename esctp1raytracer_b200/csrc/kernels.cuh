@@ -310,7 +310,7 @@ constexpr unsigned long long KEY_NONE = 0xffffffffffffffffull;
 struct PrimaryParams {
     Cam cam;
     Bands bands;
-    const float4 *table; // eye table: span rows when the rays of a thread share q, three-row table with jittered samples
+    const float4 *table; // eye table: span rows (MODE_SHAREDQ, MODE_QBAR) or the three-row table (MODE_OWNQ)
     int n_tiles, n_tris;
     const float *tri_verts;
     unsigned long long *best; // [n_px] merged closest-hit keys over triangles, KEY_NONE = miss
@@ -351,11 +351,14 @@ __device__ __noinline__ unsigned strict_primary(const PrimaryParams &p, int k0, 
 }
 
 // Ray block = screen tile, each thread holding R horizontally consecutive pixels of ONE image row.  Without
-// jitter those R rays share the filter parameter q (SHAREDQ), so the inner term B*q + C of every edge function is
-// computed once per thread and triangle instead of once per ray: 3 + 3R FFMA per triangle instead of 6R (the
-// values — and therefore the filter's decisions — are bit-identical, the compiler merely sees one q).
-template <int R, bool EXHAUSTIVE, bool SHAREDQ>
+// jitter those R rays share the filter parameter q exactly (MODE_SHAREDQ): the four bounds of a triangle's span row are
+// evaluated once per thread and triangle.  With jittered samples (extension) the rays of a thread are the same sample
+// of R pixels of one image row: their q lie inside one stratum, 1/(spp_n (H-1)) wide, and the bounds are evaluated at
+// the thread's mean q plus |B| x spread (MODE_QBAR, as the shadow sweeps do); the candidate path uses each ray's own q.
+// MODE_OWNQ (three-row table, every ray its own q) remains for frames too small for the span rows' |p|,|q| range.
+template <int R, bool EXHAUSTIVE, int MODE>
 __global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const __grid_constant__ PrimaryParams p) {
+    constexpr bool SHAREDQ = MODE == sweep::MODE_SHAREDQ;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -393,8 +396,17 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const _
         }
         const int k0 = ly * W + x0; // valid rays are pixels k0 + r
         unsigned done = 0;
-        sweep::sweep_table<R, SHAREDQ ? sweep::MODE_SHAREDQ : sweep::MODE_OWNQ, false, EXHAUSTIVE>(
-            sm, p.table, tile_lo, tile_hi, p.n_tris, rp, rq, 0.f, 0.f, valid, done, gtile, n_swept,
+        float qbar = 0.f, qdelta = 0.f;
+        if (MODE == sweep::MODE_QBAR) { // (rays past the frame's edge are duplicates of edge pixels: all R values count)
+            float qmin = rq[0], qmax = rq[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) qmin = fminf(qmin, rq[r]), qmax = fmaxf(qmax, rq[r]);
+            qbar = 0.5f * (qmin + qmax);
+            // >= max |q_r - qbar| with room for the roundings of this line and of the one extra FFMA per bound
+            qdelta = fmaxf(qmax - qbar, qbar - qmin) * 1.0001f + 2.4e-7f * (fabsf(qbar) + 1.f);
+        }
+        sweep::sweep_table<R, MODE, false, EXHAUSTIVE>(
+            sm, p.table, tile_lo, tile_hi, p.n_tris, rp, rq, qbar, qdelta, valid, done, gtile, n_swept,
             [&](unsigned mask, int tri, unsigned filt) {
                 const unsigned c = strict_primary(p, k0, mask, tri, filt);
                 n_strict += c & 0xffffu, n_miss += c >> 16;

@@ -206,11 +206,11 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
     return 0;
 }
 
-template <int R, bool EX, bool SQ>
+template <int R, bool EX, int MODE>
 int launch_primary_q(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
     const size_t smem = sizeof(sweep::Smem);
-    CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trk::primary_kernel<R, EX, SQ><<<grid, sweep::NT, smem, st>>>(p);
+    CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trk::primary_kernel<R, EX, MODE><<<grid, sweep::NT, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -303,19 +303,27 @@ int launch_shadow_light_t(Ctx &g, const trk::ShadowLightParams &p, unsigned *bar
 int launch_shadow_light(Ctx &g, bool ex, const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
     return ex ? launch_shadow_light_t<true>(g, p, bar, st) : launch_shadow_light_t<false>(g, p, bar, st);
 }
-int launch_primary(int R, bool ex, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
-    if (p.bands.spp_n > 1) { // jittered samples (extension): every ray its own q, three-row table
-        if (R == 12) return ex ? launch_primary_q<12, true, false>(p, grid, st) : launch_primary_q<12, false, false>(p, grid, st);
-        if (R == 8) return ex ? launch_primary_q<8, true, false>(p, grid, st) : launch_primary_q<8, false, false>(p, grid, st);
-        if (R == 4) return ex ? launch_primary_q<4, true, false>(p, grid, st) : launch_primary_q<4, false, false>(p, grid, st);
-        return ex ? launch_primary_q<2, true, false>(p, grid, st) : launch_primary_q<2, false, false>(p, grid, st);
+// qmode: sweep::MODE_SHAREDQ (no jitter), MODE_QBAR (jittered samples, span table) or MODE_OWNQ (jittered, three-row table)
+int launch_primary(int R, bool ex, int qmode, const trk::PrimaryParams &p, int grid, cudaStream_t st) {
+    constexpr int OQ = sweep::MODE_OWNQ, SQ = sweep::MODE_SHAREDQ, QB = sweep::MODE_QBAR;
+    if (qmode == OQ) { // every ray its own q, three-row table
+        if (R == 12) return ex ? launch_primary_q<12, true, OQ>(p, grid, st) : launch_primary_q<12, false, OQ>(p, grid, st);
+        if (R == 8) return ex ? launch_primary_q<8, true, OQ>(p, grid, st) : launch_primary_q<8, false, OQ>(p, grid, st);
+        if (R == 4) return ex ? launch_primary_q<4, true, OQ>(p, grid, st) : launch_primary_q<4, false, OQ>(p, grid, st);
+        return ex ? launch_primary_q<2, true, OQ>(p, grid, st) : launch_primary_q<2, false, OQ>(p, grid, st);
     }
-    if (R == 32) return ex ? launch_primary_q<32, true, true>(p, grid, st) : launch_primary_q<32, false, true>(p, grid, st);
-    if (R == 24) return ex ? launch_primary_q<24, true, true>(p, grid, st) : launch_primary_q<24, false, true>(p, grid, st);
-    if (R == 16) return ex ? launch_primary_q<16, true, true>(p, grid, st) : launch_primary_q<16, false, true>(p, grid, st);
-    if (R == 8) return ex ? launch_primary_q<8, true, true>(p, grid, st) : launch_primary_q<8, false, true>(p, grid, st);
-    if (R == 4) return ex ? launch_primary_q<4, true, true>(p, grid, st) : launch_primary_q<4, false, true>(p, grid, st);
-    return ex ? launch_primary_q<2, true, true>(p, grid, st) : launch_primary_q<2, false, true>(p, grid, st);
+    if (qmode == QB) {
+        if (R == 16) return ex ? launch_primary_q<16, true, QB>(p, grid, st) : launch_primary_q<16, false, QB>(p, grid, st);
+        if (R == 8) return ex ? launch_primary_q<8, true, QB>(p, grid, st) : launch_primary_q<8, false, QB>(p, grid, st);
+        if (R == 4) return ex ? launch_primary_q<4, true, QB>(p, grid, st) : launch_primary_q<4, false, QB>(p, grid, st);
+        return ex ? launch_primary_q<2, true, QB>(p, grid, st) : launch_primary_q<2, false, QB>(p, grid, st);
+    }
+    if (R == 32) return ex ? launch_primary_q<32, true, SQ>(p, grid, st) : launch_primary_q<32, false, SQ>(p, grid, st);
+    if (R == 24) return ex ? launch_primary_q<24, true, SQ>(p, grid, st) : launch_primary_q<24, false, SQ>(p, grid, st);
+    if (R == 16) return ex ? launch_primary_q<16, true, SQ>(p, grid, st) : launch_primary_q<16, false, SQ>(p, grid, st);
+    if (R == 8) return ex ? launch_primary_q<8, true, SQ>(p, grid, st) : launch_primary_q<8, false, SQ>(p, grid, st);
+    if (R == 4) return ex ? launch_primary_q<4, true, SQ>(p, grid, st) : launch_primary_q<4, false, SQ>(p, grid, st);
+    return ex ? launch_primary_q<2, true, SQ>(p, grid, st) : launch_primary_q<2, false, SQ>(p, grid, st);
 }
 // Work decomposition of a sweep: R rays per thread (8 preferred: best amortisation of the row loads) and
 // n_slices triangle slices, chosen so that ray blocks x slices keeps every SM busy for several items.
@@ -333,16 +341,18 @@ int items_per_cta() {
     return forced > 0 ? forced : 48;
 }
 
-Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks, bool own_q) {
+Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks, int qmode) {
     const int slices_possible = std::max(1, n_tiles / 4); // at least 4 tiles per slice
     auto blocks_for = [&](int R) {
         return (int)((n_rays + (int64_t)sweep::NT * R - 1) / ((int64_t)sweep::NT * R)) + extra_blocks;
     };
     Decomp d{2, blocks_for(2), 1};
-    // span form (rays of a thread share q): 32, 16, 8, 4 or 2 rays per thread (24 on request); three-row form (own q): 12, 8, 4 or 2
+    // rays per thread: span form with one exact q (no jitter) 32, 16, 8, 4 or 2 (24 on request); span form with a shared
+    // mean q (jittered samples) 16, 8, 4 or 2; three-row form (own q) 12, 8, 4 or 2
     // (C4 closest-hit sweep on one B200: 997 ms at 16, 944 at 24, 905 at 32)
-    const int big = own_q ? 12 : 32, mid = own_q ? 8 : 16;
-    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == mid || forced_R == big || (!own_q && forced_R == 24)) {
+    const bool own_q = qmode == sweep::MODE_OWNQ;
+    const int big = own_q ? 12 : (qmode == sweep::MODE_QBAR ? 16 : 32), mid = own_q ? 8 : 16;
+    if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == mid || forced_R == big || (qmode == sweep::MODE_SHAREDQ && forced_R == 24)) {
         d.R = forced_R, d.n_blocks = blocks_for(forced_R);
     } else {
         for (int R : {big, mid, 8, 4, 2}) {
@@ -827,10 +837,12 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         CK_CUDA(cudaGetLastError());
         launches += 3;
     } else {
-        const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0, bands.spp_n > 1);
+        // no jitter: the rays of a thread share q exactly; jittered samples (extension): they share a mean q (span table)
+        // unless the frame is so small that a jittered (s,t) can leave the span rows' |p|,|q| <= 1.0625 range
+        const int qmode = bands.spp_n <= 1 ? sweep::MODE_SHAREDQ : (W >= 16 && H >= 16 ? sweep::MODE_QBAR : sweep::MODE_OWNQ);
+        const Decomp d = pick_decomp(n_px, n_tiles, g.n_sms, o.rays_per_thread, 0, qmode);
         trk::PrimaryParams p{};
-        // rays of one thread share q unless the sample positions are jittered (extension): span table, else three-row table
-        p.cam = dc, p.bands = bands, p.table = bands.spp_n > 1 ? s->eye_table : s->eye_span, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
+        p.cam = dc, p.bands = bands, p.table = qmode == sweep::MODE_OWNQ ? s->eye_table : s->eye_span, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
         p.tri_verts = s->tri_verts;
         p.best = s->best, p.counters = s->counters, p.work = s->work;
         p.n_rows = n_rows, p.n_blocks = 0; // ray blocks = screen tiles of (TX R) x (512 / TX) pixels: least edge waste wins
@@ -846,8 +858,8 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         const int grid = std::min(p.n_blocks * p.n_slices, sweep::MINB * g.n_sms);
         // executed FP32 flops per pair: span form 2 FADD + 1 FFMA per pair and 4 FFMA per thread and triangle; three-row
         // form with every ray its own q: 6 FFMA.SAT + FMUL + FFMA
-        flop_primary = bands.spp_n > 1 ? 15.0 : 4.0 + 8.0 / d.R;
-        if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, p, grid, st)) return rc;
+        flop_primary = qmode == sweep::MODE_OWNQ ? 15.0 : 4.0 + (qmode == sweep::MODE_QBAR ? 16.0 : 8.0) / d.R;
+        if (int rc = launch_primary(d.R, o.exhaustive_strict != 0, qmode, p, grid, st)) return rc;
         trk::resolve_primary_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(dc, bands, s->best, s->tri_verts, s->n_tris, s->spheres,
                                                                         s->n_spheres, s->hit_tri, s->hit_t, s->hit_v);
         CK_CUDA(cudaGetLastError());
@@ -1148,7 +1160,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     // rows when a thread's R = 8 q-sorted rays share one q-term per row.
     s->stats.flop_primary = cull ? 0.0 : flop_primary, s->stats.flop_shadow = cull ? 0.0 : 4.0 + 16.0 / trk::SHADOW_R;
     // of which multiply-adds that evaluate bounds (the rest is the two saturating adds and the accumulate of each pair)
-    s->stats.flop_primary_edges = cull ? 0.0 : (bands.spp_n > 1 ? 12.0 : flop_primary - 4.0);
+    s->stats.flop_primary_edges = cull ? 0.0 : (flop_primary >= 15.0 ? 12.0 : flop_primary - 4.0);
     s->stats.flop_shadow_edges = cull ? 0.0 : 16.0 / trk::SHADOW_R;
     if (hc.cull_overflow) {
         // the optional mode's candidate buffer (24 per ray + slack) was too small for this scene's depth complexity: render

@@ -283,6 +283,21 @@ def test_multisample_jitter_extension(renderer, restated):
         assert np.array_equal(bits(out.rgb), bits(_to_ppm_order(rgb, W, H)))
         assert np.array_equal(out.rgb8, rgb8)
         assert out.stats["n_primary_rays"] == W * H * spp
+        # jittered rays of a thread share a MEAN q in the span sweep (mean q + |B| * spread): still a necessary condition
+        ex = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, samples_per_pixel=spp, debug=True, exhaustive_strict=True)
+        assert ex.stats["filter_misses"] == 0 and ex.stats["pipeline_errors"] == 0
+        assert np.array_equal(bits(out.rgb), bits(ex.rgb)) and np.array_equal(out.rgb8, ex.rgb8)
+        for R in (2, 4, 8, 16):
+            o2 = renderer.trace(rs, cam, W, H, rng_mode=RNG_HASH, seed=seed, samples_per_pixel=spp, debug=True, rays_per_thread=R)
+            assert np.array_equal(bits(out.rgb), bits(o2.rgb)), R
+    # frames too small for the span rows' parameter range keep the three-row sweep (every ray its own q)
+    Ws, Hs = 12, 9
+    cams = Camera.for_frame((0, 1, 3), (0, 1, 0), Ws, Hs)
+    rgb, rgb8 = restated.render_spp(to_flat(s), cams.as_array(), Ws, Hs, seed, 2)
+    out = renderer.trace(rs, cams, Ws, Hs, rng_mode=RNG_HASH, seed=seed, samples_per_pixel=4, debug=True)
+    assert np.array_equal(bits(out.rgb), bits(_to_ppm_order(rgb, Ws, Hs))) and np.array_equal(out.rgb8, rgb8)
+    ex = renderer.trace(rs, cams, Ws, Hs, rng_mode=RNG_HASH, seed=seed, samples_per_pixel=4, debug=True, exhaustive_strict=True)
+    assert ex.stats["filter_misses"] == 0 and np.array_equal(out.rgb8, ex.rgb8)
     with pytest.raises(TracerError):
         renderer.trace(rs, cam, W, H, samples_per_pixel=5)  # not a square
 
