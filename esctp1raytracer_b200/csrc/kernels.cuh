@@ -1,6 +1,6 @@
 // kernels.cuh — device kernels of the render path (see sweep.cuh for the sweeps).
 //
-//   build_origin_table   per (point O, triangle): the 48-byte filter row
+//   build_origin_table   per (point O, triangle): the 32-byte span row and the 48-byte three-row filter row
 //   primary_kernel       raygen (camera.h:31-34) + closest hit (main.cpp:176-192)
 //   light_step_kernel    per pixel, per light: finish light k-1 (main.cpp:772-788),
 //                        set up the shadow ray of light k (main.cpp:740-770)

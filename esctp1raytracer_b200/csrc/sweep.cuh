@@ -3,9 +3,8 @@
 //
 // What the reference does per (ray, triangle) pair: full Moller-Trumbore with
 // a double-precision divide (ray_triangle.h:7-57, ~52 flop).  What this kernel
-// does per pair: at most 6 FFMA + 1.5 LOP3 (3.4-3.75 FFMA when the rays of a
-// thread share the q-term of each row, see 3.).  The saving comes from these
-// observations.
+// does per pair: two saturating adds and half a packed multiply-add (4.), plus
+// 4-8 FFMA per thread and triangle.  The saving comes from these observations.
 //
 //  1. Every sweep is a bundle of rays through ONE common point.  Primary rays
 //     all start at the eye (camera.h:31-34).  A shadow ray runs from the hit
@@ -18,15 +17,12 @@
 //     w' = det-u'-v' = d.(e2 x e1 - a x e2 - e1 x a),  and the side of the
 //     plane O lies on, s = sign(e2.(e1 x a)), is a per-triangle constant.
 //     A line through O can only hit the triangle if s*u', s*v', s*w' >= 0.
-//     The three vectors (pre-multiplied by s) plus a safety margin K are
-//     tabulated once per (O, triangle).
 //
 //  1b. Directions through one point have two degrees of freedom.  Each ray group
 //     uses a parametrisation d' = p*U + q*V + W (the image plane for primary
 //     rays: U,V,W = horizontal, vertical, llc-origin and (p,q) = the reference's
 //     own (s,t); a cube face around a light vertex for shadow rays), so each
-//     edge function becomes AFFINE in (p,q):  u'(p,q) = p*(U.B) + q*(V.B) + (W.B + K|d'|max)
-//     = 2 FFMA.  The table row is 3 x (A,B,C,-) = 48 bytes per (O, group, triangle).
+//     edge function becomes AFFINE in (p,q):  u'(p,q) = p*(U.B) + q*(V.B) + (W.B + K|d'|max).
 //
 //  2. The test above is used as a CONSERVATIVE FILTER only: K bounds every
 //     rounding difference between this evaluation and the reference's own
@@ -41,29 +37,35 @@
 //                                                   minimum of (t, index): t2 >= t rejects)
 //        occluder     key = index << 32  | t2 bits (occlusion() returns the lowest index)
 //     so the sweep keeps NO per-ray state in shared memory: a CTA's shared
-//     memory is the table-tile pipeline only (48 KB), and two 512-thread CTAs
-//     (32 warps) fit on an SM.
+//     memory is the table-tile pipeline only.
 //
-//  3. The R rays of a thread can share the q-term B*q + C of every row.  Closest-hit
-//     ray blocks are screen tiles in which a thread holds R consecutive pixels of one
-//     image row: same q, the compiler merges the R identical inner FFMAs (MODE_SHAREDQ).
-//     Shadow-ray lists are sorted by q, a thread takes R consecutive rays and uses
-//     qbar*B + |B|*qdelta + C with qdelta >= max|q_r - qbar|, which is >= every ray's own
-//     term, so the test stays a necessary condition (MODE_QBAR).
+//  3. The R rays of a thread share q.  Closest-hit ray blocks are screen tiles in which a
+//     thread holds R consecutive pixels of one image row: same q exactly (MODE_SHAREDQ).
+//     Shadow-ray lists are sorted by q, a thread takes R consecutive rays and evaluates the
+//     q-dependent terms at qbar with |B|*qdelta added, qdelta >= max|q_r - qbar|, which is
+//     >= every ray's own term, so the test stays a necessary condition (MODE_QBAR; also used
+//     for jittered primary samples, whose q lie inside one stratum).
 //
-// Mapping to the SM (choices measured with tools/sweep_mb2.cu):
-//  * rows stream HBM/L2 -> shared memory in 12 KB tiles via TMA 1-D bulk copies
+//  4. SPAN form.  For rays that share q, the three affine rows are half-lines in p: with
+//     beta = -B/A, gamma = -C/A (divided once per (origin, triangle) in FP64) row i says
+//     p >= q*beta_i + gamma_i where A_i > 0 and p <= q*beta_i + gamma_i where A_i < 0.  A
+//     triangle has two lower bounds and one upper bound or the reverse, so the table row is
+//     two lower + two upper bounds = 32 bytes, the thread evaluates the four at its q and keeps
+//     the binding ones (4 FFMA + 2 FMNMX), and each PAIR is a two-sided span test (below).
+//     MODE_OWNQ (every ray its own q) keeps the 48-byte three-row table: 3 x (A,B,C,-).
+//
+// Mapping to the SM (choices measured with tools/sweep_mb2-4.cu):
+//  * rows stream HBM/L2 -> shared memory in tiles of 256 triangles via TMA 1-D bulk copies
 //    (cp.async.bulk + mbarrier complete_tx, UBLKCP in SASS), STAGES deep;
-//  * every lane of every warp reads the SAME row at the same time, so the three
-//    LDS.128 per triangle are pure broadcasts, amortised over R rays per thread
-//    held in registers (R = 8: 27-30 FFMA per 3 loads);
-//  * "all three >= 0" is decided IN THE FMA PIPE: rows are pre-scaled so that a pair the
-//    reference could accept saturates to exactly 1 on each row (fma.sat is free), the three
-//    are multiplied and accumulated: 3 FFMA.SAT + FMUL + FFMA per pair, no integer op.  The
-//    round-1 form (sign bits through LOP3 on the half-rate ALU pipe) measured 63 issue cycles
-//    per warp and triangle (8 rays per thread) against 59 for this one, and its FMA pipe was
-//    idle 55 % of the time; this loop runs at ~0.78 FMA-pipe instructions per cycle and
-//    scheduler, the scalar-FFMA issue ceiling of the part (own microbenchmark: 0.745);
+//  * every lane of every warp reads the SAME row at the same time, so the two LDS.128 per
+//    triangle are pure broadcasts, amortised over R rays per thread held in registers
+//    (R = 32 closest hit, 16 any-hit);
+//  * the conjunction is decided IN THE FMA PIPE: bounds carry the +1 of a saturating test, so
+//    x = sat(S*p + ax) and y = sat(ay - S*p) are both exactly 1 for a pair the reference could
+//    accept, and acc += x*y runs on ray pairs as one packed FFMA2: 2 FFMA.SAT-slot instructions
+//    + half an FFMA2 per pair, no integer op.  History on this part (cycles per pair, closest hit):
+//    round 1 sign bits through LOP3 on the half-rate ALU pipe 7.9, three saturating rows with a
+//    product accumulate 6.8, span form 4.0;
 //  * the inner loop has NO per-triangle branch: an accumulator group of 4 triangles is
 //    tested once; candidates (a few per ray per sweep) are then re-evaluated one by one;
 //  * NO block-wide barrier per tile in either sweep: every warp counts itself out of a
@@ -194,7 +196,7 @@ __device__ __forceinline__ float qterm_qbar(const float4 row, float qbar, float 
     return fmaf(fabsf(row.y), qdelta, fmaf(qbar, row.y, row.z));
 }
 
-// ---- the hot loop: BATCH triangles of a staged tile against the R rays of this thread ---------------
+// ---- three-row form (MODE_OWNQ; also tools/sweep_mb2,3.cu): BATCH triangles of a staged tile against the R rays of this thread ---
 // Everything runs in the FMA pipe (measured on B200, tools/sweep_mb3.cu: a scalar FMA-pipe instruction costs ~1.3
 // issue cycles, a LOP3/SHF/FMNMX on the half-rate ALU pipe ~2, and the two do not overlap in this loop):
 //   x' = sat(p*A_u + q_u)   y' = sat(p*A_v + q_v)   z' = sat(p*A_w + q_w)      3 FFMA.SAT per pair
@@ -271,7 +273,7 @@ __device__ __forceinline__ unsigned eval_batch(const float4 *__restrict__ tp, co
 // and a pair is a candidate iff  x = sat(S*p + ax)  and  y = sat(ay - S*p)  are both exactly 1.  Per thread and triangle:
 // 4 FFMA + 2 FMNMX (8 FFMA in MODE_QBAR, which adds |B|*qdelta to every bound); per PAIR: 2 FADD.SAT + half a packed
 // FFMA2 (acc += x*y), against 3 FFMA.SAT + FMUL2/2 + FFMA2/2 of the three-row form.  Measured (tools/sweep_mb4.cu, B200):
-// 8.9 Tpairs/s at 16 rays per thread, 9.3 at 24, against 5.7 for the three-row loop at 12.
+// 8.9 Tpairs/s at 16 rays per thread, 9.3 at 24, 9.5 at 32, against 5.7 for the three-row loop at 12.
 __device__ __forceinline__ void span_terms(const float4 lo, const float4 hi, float q, float &ax, float &ay) {
     ax = fminf(fmaf(q, lo.x, lo.y), fmaf(q, lo.z, lo.w));
     ay = fminf(fmaf(q, hi.x, hi.y), fmaf(q, hi.z, hi.w));
