@@ -140,7 +140,7 @@ constexpr double SPAN_PMAX = 1.0625, SPAN_QMAX = 1.0625; // |p|, |q| of every ra
 struct SpanBound {
     double beta, gamma;
 };
-__device__ __forceinline__ void span_rows(const double (&rows)[3][3], float4 &lo, float4 &hi) {
+__host__ __device__ __forceinline__ void span_rows(const double (&rows)[3][3], float4 &lo, float4 &hi) {
     const double S = (double)sweep::SPAN_S, eps = (double)TRC_EPS;
     const float OPEN = sweep::SPAN_OPEN;
     lo = make_float4(0.f, OPEN, 0.f, OPEN), hi = make_float4(0.f, OPEN, 0.f, OPEN); // no bound at all: always candidate

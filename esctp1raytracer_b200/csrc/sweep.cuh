@@ -274,16 +274,16 @@ __device__ __forceinline__ unsigned eval_batch(const float4 *__restrict__ tp, co
 // 4 FFMA + 2 FMNMX (8 FFMA in MODE_QBAR, which adds |B|*qdelta to every bound); per PAIR: 2 FADD.SAT + half a packed
 // FFMA2 (acc += x*y), against 3 FFMA.SAT + FMUL2/2 + FFMA2/2 of the three-row form.  Measured (tools/sweep_mb4.cu, B200):
 // 8.9 Tpairs/s at 16 rays per thread, 9.3 at 24, 9.5 at 32, against 5.7 for the three-row loop at 12.
-__device__ __forceinline__ void span_terms(const float4 lo, const float4 hi, float q, float &ax, float &ay) {
+__host__ __device__ __forceinline__ void span_terms(const float4 lo, const float4 hi, float q, float &ax, float &ay) {
     ax = fminf(fmaf(q, lo.x, lo.y), fmaf(q, lo.z, lo.w));
     ay = fminf(fmaf(q, hi.x, hi.y), fmaf(q, hi.z, hi.w));
 }
-__device__ __forceinline__ void span_terms_qbar(const float4 lo, const float4 hi, float qbar, float qdelta, float &ax, float &ay) {
+__host__ __device__ __forceinline__ void span_terms_qbar(const float4 lo, const float4 hi, float qbar, float qdelta, float &ax, float &ay) {
     ax = fminf(fmaf(fabsf(lo.x), qdelta, fmaf(qbar, lo.x, lo.y)), fmaf(fabsf(lo.z), qdelta, fmaf(qbar, lo.z, lo.w)));
     ay = fminf(fmaf(fabsf(hi.x), qdelta, fmaf(qbar, hi.x, hi.y)), fmaf(fabsf(hi.z), qdelta, fmaf(qbar, hi.z, hi.w)));
 }
 // per-ray test of the (rare) candidate path: ps = p * SPAN_S, the ray's own q
-__device__ __forceinline__ bool span_pass(const float4 lo, const float4 hi, float ps, float q) {
+__host__ __device__ __forceinline__ bool span_pass(const float4 lo, const float4 hi, float ps, float q) {
     float ax, ay;
     span_terms(lo, hi, q, ax, ay);
     return fminf(ps + ax, ay - ps) >= 1.f;

@@ -19,6 +19,25 @@
 
 #include "kernels.cuh"
 
+// Internal (tests only, no GPU needed): the span-row construction of build_origin_table and the sweeps' per-ray span
+// test, compiled for the host from the same source.  rows9 = three exact rows (A, B, C); row8 = lo.xyzw, hi.xyzw.
+extern "C" void tracer__span_rows(const double *rows9, float *row8) {
+    double rows[3][3];
+    for (int i = 0; i < 9; ++i) rows[i / 3][i % 3] = rows9[i];
+    float4 lo, hi;
+    trk::span_rows(rows, lo, hi);
+    row8[0] = lo.x, row8[1] = lo.y, row8[2] = lo.z, row8[3] = lo.w, row8[4] = hi.x, row8[5] = hi.y, row8[6] = hi.z, row8[7] = hi.w;
+}
+// qdelta < 0: the ray's own q (candidate path); else the hot loop's shared-q form (q = qbar, bounds widened by |B| qdelta)
+extern "C" int tracer__span_pass(const float *row8, float p, float q, float qdelta) {
+    const float4 lo = make_float4(row8[0], row8[1], row8[2], row8[3]), hi = make_float4(row8[4], row8[5], row8[6], row8[7]);
+    const float ps = p * sweep::SPAN_S;
+    if (qdelta < 0.f) return sweep::span_pass(lo, hi, ps, q) ? 1 : 0;
+    float ax, ay;
+    sweep::span_terms_qbar(lo, hi, q, qdelta, ax, ay);
+    return fminf(ps + ax, ay - ps) >= 1.f ? 1 : 0;
+}
+
 extern "C" int tracer__mt19937_scan(uint32_t seed, int32_t n_lights, const int32_t *faces_per_light, int64_t n_px,
                                     const uint8_t *hit_scan, int32_t *faceid_scan);
 
