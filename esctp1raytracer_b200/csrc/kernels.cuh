@@ -360,7 +360,8 @@ template <int R, bool EXHAUSTIVE, int MODE>
 __global__ void __launch_bounds__(sweep::NT, sweep::MINB) primary_kernel(const __grid_constant__ PrimaryParams p) {
     constexpr bool SHAREDQ = MODE == sweep::MODE_SHAREDQ;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
+    using Smem = sweep::SmemT<sweep::Rows<MODE>::N>;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
     sweep::smem_init(sm);
     unsigned gtile = 0, n_strict = 0, n_swept = 0, n_miss = 0, n_pipe_err = 0;
@@ -760,7 +761,7 @@ __device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float
 // (and compaction keeps it so); a thread takes RR CONSECUTIVE rays, whose q differ by ~1e-6, and evaluates them
 // with one q-term per edge row (sweep::MODE_QBAR).
 template <int RR, bool EXHAUSTIVE>
-__device__ __forceinline__ void shadow_item(sweep::Smem &sm, const ShadowLightParams &p, const int *__restrict__ list_in, int base,
+__device__ __forceinline__ void shadow_item(sweep::SmemT<2> &sm, const ShadowLightParams &p, const int *__restrict__ list_in, int base,
                                             int seg_end, int lo, int hi, const float4 *__restrict__ tab, unsigned &gtile,
                                             unsigned &n_strict, unsigned &n_miss, unsigned long long &tests, unsigned &n_pipe_err) {
     const int tid = threadIdx.x, n = p.n_px;
@@ -861,12 +862,14 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
     static_assert(CBLK % sweep::NT == 0, "compaction block must be a multiple of the CTA size");
     constexpr int R = SHADOW_R, CPT = CBLK / sweep::NT; // rays per thread of a full ray block; list entries per thread of a compaction block
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    sweep::Smem &sm = *reinterpret_cast<sweep::Smem *>(smem_raw);
+    sweep::SmemT<2> &sm = *reinterpret_cast<sweep::SmemT<2> *>(smem_raw); // the any-hit sweeps read span tables only
     __shared__ int s_blk_off[SL_MAXF + 1], s_cblk_off[SL_MAXF + 1], s_scratch[sweep::NT / 32], s_off;
     const int tid = threadIdx.x, F = p.F;
     sweep::smem_init(sm);
     unsigned gtile = 0, n_strict = 0, n_miss = 0, epoch = 0, n_pipe_err = 0;
     unsigned long long tests = 0;
+    long long c_items = 0, c_bar = 0, c_comp = 0, n_it = 0, n_run = 0; // time split (thread 0)
+    const long long c_begin = clock64();
     // chunk scheme: equal chunks keep the pairs swept past a ray's occluder lowest and win when the light has many
     // rays; with few rays the per-chunk tails weigh more and boundaries that start fine and coarsen geometrically win
     const long long live0 = cta_group_prefix(p.cnt[0], F, 1, s_blk_off, s_scratch);
@@ -901,7 +904,10 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
             int it = sm.blk;
             const int it_end = sm.seg;
             if (it < 0) break;
+            const long long c_run = clock64();
+            ++n_run;
             while (it < it_end) { // (uniform) one run per ray block touched
+                ++n_it;
                 const int blk = it / n_slices, sl0 = it - blk * n_slices, sl1 = min(n_slices, sl0 + (it_end - it));
                 it += sl1 - sl0;
                 const int j = group_of_block(s_blk_off, F, blk);
@@ -924,9 +930,12 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
                     shadow_item<2, EXHAUSTIVE>(sm, p, list_in, base, seg_end, lo, hi, tab, gtile, n_strict, n_miss, tests, n_pipe_err);
                 __syncthreads(); // every warp is out of the tile pipeline before the next run re-arms it
             }
+            c_items += clock64() - c_run;
         }
         if (c == n_chunks - 1) break; // nothing left to sweep: the lists are not needed compacted
+        long long c0 = clock64();
         grid_barrier(bar, epoch);
+        c_bar += clock64() - c0, c0 = clock64();
         // ---- B: survivors per compaction block ------------------------------------------------------------------
         for (int cb = blockIdx.x; cb < total_cblocks; cb += gridDim.x) {
             const int j = group_of_block(s_cblk_off, F, cb), bx = cb - s_cblk_off[j];
@@ -947,7 +956,9 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
                 p.blk_cnt[cb] = t;
             }
         }
+        c_comp += clock64() - c0, c0 = clock64();
         grid_barrier(bar, epoch);
+        c_bar += clock64() - c0, c0 = clock64();
         // ---- C: write the survivors in list order ---------------------------------------------------------------
         for (int cb = blockIdx.x; cb < total_cblocks; cb += gridDim.x) {
             const int j = group_of_block(s_cblk_off, F, cb), bx = cb - s_cblk_off[j];
@@ -999,7 +1010,9 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
         // groups without entries keep a zero count
         for (int j = blockIdx.x * sweep::NT + tid; j < F; j += gridDim.x * sweep::NT)
             if (cnt_in[j] == 0) cnt_out[j] = 0;
+        c_comp += clock64() - c0, c0 = clock64();
         grid_barrier(bar, epoch);
+        c_bar += clock64() - c0;
         cur ^= 1;
     }
     // ---- extension: spheres come after all triangles in the object order --------------------------------------------
@@ -1027,6 +1040,11 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
     atomicAdd(&p.counters->strict_evals, (unsigned long long)n_strict);
     if (EXHAUSTIVE) atomicAdd(&p.counters->filter_misses, (unsigned long long)n_miss);
     if (EXHAUSTIVE && n_pipe_err) atomicAdd(&p.counters->pipeline_errors, (unsigned long long)n_pipe_err);
+    if (tid == 0) {
+        atomicAdd(&p.counters->cyc_items, (unsigned long long)c_items), atomicAdd(&p.counters->cyc_barrier, (unsigned long long)c_bar);
+        atomicAdd(&p.counters->cyc_compact, (unsigned long long)c_comp), atomicAdd(&p.counters->cyc_total, (unsigned long long)(clock64() - c_begin));
+        atomicAdd(&p.counters->n_items, (unsigned long long)n_it), atomicAdd(&p.counters->n_runs, (unsigned long long)n_run);
+    }
 }
 
 // extension: spheres are tested after all triangles, in order, by the rays that found no triangle

@@ -80,10 +80,10 @@
 #include "strict_math.cuh"
 
 #ifndef SWEEP_NT
-#define SWEEP_NT 256
+#define SWEEP_NT 128
 #endif
 #ifndef SWEEP_MINB
-#define SWEEP_MINB 2
+#define SWEEP_MINB 4
 #endif
 #ifndef SWEEP_STAGES
 #define SWEEP_STAGES 4
@@ -148,21 +148,27 @@ __device__ __forceinline__ float4 lds128_opaque(const float4 *p) {
 }
 
 // ---- shared memory of one sweep CTA: the table-tile pipeline and nothing else -------------------
-struct __align__(128) Smem {
-    float4 tile[STAGES][TILE * 3];
+template <int ROWS> // float4 per triangle of the table the kernel sweeps: 2 (span rows) or 3 (three-row table)
+struct __align__(128) SmemT {
+    float4 tile[STAGES][TILE * ROWS];
     uint64_t full_bar[STAGES];
     int consumed[STAGES]; // warps that have finished the tile in this stage
     int blk, seg, slice;  // the work item the CTA is on
 };
+using Smem = SmemT<3>;
 
 struct Counters {
     unsigned long long tests_primary, tests_shadow, strict_evals, tests_shadow_ref, n_hits, filter_misses;
     unsigned long long cull_l0, cull_l1, cull_tiles_any, cull_tiles_fallback; // bundle-cull diagnostics
     unsigned long long cull_overflow; // bundle-cull: a candidate buffer was too small (the frame is rejected)
     unsigned long long pipeline_errors; // validation mode: staged tiles that differed from their source (must be 0)
+    // shadow_light_kernel time split, SM cycles summed over CTAs (thread 0's clock; TRACER_SHADOW_DIAG prints them):
+    // inside work items, waiting at grid barriers, compaction passes, everything else (work-queue pops, prefix sums)
+    unsigned long long cyc_items, cyc_barrier, cyc_compact, cyc_total, n_items, n_runs;
 };
 
-__device__ __forceinline__ void smem_init(Smem &sm) {
+template <int ROWS>
+__device__ __forceinline__ void smem_init(SmemT<ROWS> &sm) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full_bar[s], 1), sm.consumed[s] = 0;
         fence_barrier_init();
@@ -357,7 +363,7 @@ __device__ __forceinline__ unsigned eval_batch_lop3(const float4 *__restrict__ t
 // strict(mask, tri, filt) -> newly done rays: the reference's own test on the surviving pairs (kernels.cuh);
 //        mask = rays to test, filt = rays the filter passed (differs from mask only in EXHAUSTIVE validation mode)
 template <int R, int MODE, bool ANYHIT, bool EXHAUSTIVE, class Strict>
-__device__ __forceinline__ void sweep_table(Smem &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi, int n_tris,
+__device__ __forceinline__ void sweep_table(SmemT<Rows<MODE>::N> &sm, const float4 *__restrict__ table, int tile_lo, int tile_hi, int n_tris,
                                             const float (&rp)[R], const float (&rq)[R], float qbar, float qdelta, unsigned valid,
                                             unsigned &done, unsigned &gtile, unsigned &n_tiles_swept, Strict &&strict,
                                             unsigned *n_pipe_err = nullptr) {

@@ -227,7 +227,7 @@ int ensure_workspace(tracer_scene_dev *s, int n_px, bool want_dbg_occ) {
 
 template <int R, bool EX, int MODE>
 int launch_primary_q(const trk::PrimaryParams &p, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(sweep::Smem);
+    const size_t smem = sizeof(sweep::SmemT<sweep::Rows<MODE>::N>);
     CK_CUDA(cudaFuncSetAttribute(trk::primary_kernel<R, EX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trk::primary_kernel<R, EX, MODE><<<grid, sweep::NT, smem, st>>>(p);
     CK_CUDA(cudaGetLastError());
@@ -307,7 +307,7 @@ constexpr int WORK_INTS = trk::SL_MAXCHUNK + 8; // per-chunk work counters + the
 
 template <bool EX>
 int launch_shadow_light_t(Ctx &g, const trk::ShadowLightParams &p, unsigned *bar, cudaStream_t st) {
-    const size_t smem = sizeof(sweep::Smem);
+    const size_t smem = sizeof(sweep::SmemT<2>);
     int &ctas_per_sm = g.sl_ctas[EX ? 1 : 0]; // co-resident CTAs: a cooperative launch may not exceed them
     if (!ctas_per_sm) {
         CK_CUDA(cudaFuncSetAttribute(trk::shadow_light_kernel<EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1196,6 +1196,10 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             o2.bundle_cull = 0;
         return tracer_cuda_render_scene(s, cam, W, H, &o2, rgb_out);
     }
+    if (getenv("TRACER_SHADOW_DIAG") && hc.cyc_total)
+        fprintf(stderr, "shadow diag: CTA cycles %.3e total = items %.1f %% + grid barriers %.1f %% + compaction %.1f %% + other %.1f %%; %llu items in %llu runs\n",
+                (double)hc.cyc_total, 100.0 * hc.cyc_items / hc.cyc_total, 100.0 * hc.cyc_barrier / hc.cyc_total, 100.0 * hc.cyc_compact / hc.cyc_total,
+                100.0 * ((double)hc.cyc_total - hc.cyc_items - hc.cyc_barrier - hc.cyc_compact) / hc.cyc_total, hc.n_items, hc.n_runs);
     if (getenv("TRACER_CULL_DIAG"))
         fprintf(stderr, "cull diag (shadow): l0 survivors %llu, tiles with any %llu, fallback tiles %llu, l1 warp-passes %llu, item-tiles %llu\n", hc.cull_l0,
                 hc.cull_tiles_any, hc.cull_tiles_fallback, hc.cull_l1, (unsigned long long)(hc.tests_shadow / 4096 / cull::CTILE));

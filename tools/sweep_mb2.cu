@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(NTH, MINBLK) k_loop(const float4 *tile_g, int 
 template <int R, int MODE, bool ANYHIT, int NTH, int MINBLK>
 __global__ void __launch_bounds__(NTH, MINBLK) k_prod(const float4 *table, int n_tiles, int n_blocks, int *work, float *out, float seed) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    using SmemM = SmemT<Rows<MODE>::N>; // (round 2, span form: MODE_SHAREDQ / MODE_QBAR sweep 32-byte rows)
+    SmemM &sm = *reinterpret_cast<SmemM *>(smem_raw);
     const int tid = threadIdx.x;
     smem_init(sm);
     unsigned gtile = 0, n_swept = 0, acc = 0;
