@@ -715,6 +715,7 @@ struct ShadowLightParams {
     long long many_rays;
     int items_per_cta;            // (ray block, slice) items wanted per resident CTA
     int min_tiles;                // smallest slice, in tiles
+    long long run_pairs;          // longest run of items handed to a CTA at once, in (ray, triangle) pairs
     const float *tri_verts;
     int *list[2];                 // ping-pong ray lists, [0] = the sorted input
     const int *seg_off;           // [F+1] segment starts of this launch's groups (absolute list positions)
@@ -725,6 +726,8 @@ struct ShadowLightParams {
     int n_spheres;
     sweep::Counters *counters;
     int *work;                    // [SL_MAXCHUNK] work counters, zeroed by the host
+    unsigned long long *timeline; // development (TRACER_SHADOW_DIAG=2): [SL_MAXCHUNK][gridDim.x][2] globaltimer ns at which a CTA
+                                  // ran out of sweep items / left the barrier after the sweep, or null
 };
 
 // The reference's own test for the rays (bits of mask) of one thread against triangle tri, shadow rays
@@ -892,11 +895,17 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
         const int want = p.items_per_cta * (int)gridDim.x;
         const int n_slices = max(1, min(total_blocks >= want ? 1 : (want + total_blocks - 1) / total_blocks, max(1, n_tiles / p.min_tiles)));
         const int n_items = total_blocks * n_slices;
+        // Runs are also capped in absolute size.  Guided self-scheduling assumes CTAs of equal speed, and the four CTAs of an
+        // SM are not: the hardware's warp arbiter favours some of them, the starved one is still inside a long run when the
+        // others find the queue empty (measured with TRACER_SHADOW_DIAG=2 at C4: 3/4 of the CTAs waited ~0.7 ms of every
+        // 6 ms chunk for the 4th CTA of each SM).  Short runs bound that tail; each costs one ray set-up (a few us).
+        const long long item_pairs = (long long)(sweep::NT * R) * sweep::TILE * max(1, n_tiles / n_slices);
+        const int g_cap = (int)max(1ll, p.run_pairs / item_pairs);
         // ---- A: sweep --------------------------------------------------------------------------------------
         for (;;) {
             if (tid == 0) {
                 const int seen = *(volatile int *)&p.work[c];
-                const int g = max(1, min((n_items - seen) / (2 * (int)gridDim.x), n_slices));
+                const int g = max(1, min(min((n_items - seen) / (2 * (int)gridDim.x), n_slices), g_cap));
                 const int it = atomicAdd(&p.work[c], g);
                 sm.blk = it < n_items ? it : -1, sm.seg = min(it + g, n_items);
             }
@@ -932,10 +941,20 @@ __global__ void __launch_bounds__(sweep::NT, sweep::MINB) shadow_light_kernel(co
             }
             c_items += clock64() - c_run;
         }
+        if (p.timeline && tid == 0) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            p.timeline[((size_t)c * gridDim.x + blockIdx.x) * 2] = ns;
+        }
         if (c == n_chunks - 1) break; // nothing left to sweep: the lists are not needed compacted
         long long c0 = clock64();
         grid_barrier(bar, epoch);
         c_bar += clock64() - c0, c0 = clock64();
+        if (p.timeline && tid == 0) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            p.timeline[((size_t)c * gridDim.x + blockIdx.x) * 2 + 1] = ns;
+        }
         // ---- B: survivors per compaction block ------------------------------------------------------------------
         for (int cb = blockIdx.x; cb < total_cblocks; cb += gridDim.x) {
             const int j = group_of_block(s_cblk_off, F, cb), bx = cb - s_cblk_off[j];

@@ -1069,6 +1069,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         }
         sp.many_rays = (long long)1 << 20;
         sp.items_per_cta = items_per_cta();
+        sp.run_pairs = std::getenv("TRACER_RUN_PAIRS") ? std::max(1ll, std::atoll(std::getenv("TRACER_RUN_PAIRS"))) : 6000000ll;
         sp.min_tiles = std::getenv("TRACER_MIN_TILES") ? std::max(1, std::atoi(std::getenv("TRACER_MIN_TILES"))) : 1;
         sp.allcand = s->allcand_span, sp.table_stride = s->span_stride; // the default sweeps read the span tables
         sp.n_tris = s->n_tris, sp.n_tiles = n_tiles, sp.n_px = n_px, sp.tri_verts = s->tri_verts;
@@ -1102,8 +1103,29 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
             sp.cnt[0] = s->cursor + b0 * trk::NFACE, sp.cnt[1] = s->cnt_b + b0 * trk::NFACE;
             sp.work = s->work;
             CK_CUDA(cudaMemsetAsync(s->work, 0, sizeof(int) * WORK_INTS, st));
+            // development: TRACER_SHADOW_DIAG=2 dumps, for every light, when each CTA ran out of sweep items in each chunk
+            static const bool want_timeline = std::getenv("TRACER_SHADOW_DIAG") && std::atoi(std::getenv("TRACER_SHADOW_DIAG")) >= 2;
+            const size_t tl_n = (size_t)trk::SL_MAXCHUNK * 8 * (size_t)g.n_sms * 2;
+            unsigned long long *tl = nullptr;
+            if (want_timeline) {
+                tl = (unsigned long long *)t_pool->alloc(tl_n * sizeof(unsigned long long));
+                if (tl) CK_CUDA(cudaMemsetAsync(tl, 0, tl_n * sizeof(unsigned long long), st));
+            }
+            sp.timeline = tl;
             if (int rc = launch_shadow_light(g, o.exhaustive_strict != 0, sp, (unsigned *)(s->work + trk::SL_MAXCHUNK), st)) return rc;
             ++launches;
+            if (tl) {
+                std::vector<unsigned long long> h(tl_n);
+                CK_CUDA(cudaMemcpyAsync(h.data(), tl, tl_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CK_CUDA(cudaStreamSynchronize(st));
+                t_pool->release(tl);
+                char name[128];
+                std::snprintf(name, sizeof name, "gpurun_out/shadow_timeline_light%d.bin", k);
+                if (FILE *f = std::fopen(name, "wb")) {
+                    const int hdr[2] = {trk::SL_MAXCHUNK, 8 * g.n_sms};
+                    std::fwrite(hdr, sizeof hdr, 1, f), std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f), std::fclose(f);
+                }
+            }
         }
         CK_CUDA(cudaEventRecord(s->ev_shadow[2 * k + 1], st));
     }
