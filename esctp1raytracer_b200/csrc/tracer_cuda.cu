@@ -357,7 +357,7 @@ int items_per_cta() {
         const char *e = std::getenv("TRACER_ITEMS_PER_CTA");
         return e ? std::atoi(e) : 0;
     }();
-    return forced > 0 ? forced : 48;
+    return forced > 0 ? forced : 96;
 }
 
 Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int extra_blocks, int qmode) {
