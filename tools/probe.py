@@ -32,10 +32,10 @@ for n, W, H, L in cases:
                       shadow_chunks=int(os.environ.get('TRACER_CHUNKS', '0')), bundle_cull=bool(os.environ.get('TRACER_CULL')))
         wall = time.time() - t0
     st = out.stats
-    ffma = 6.0
-    prim = st["tests_primary"] * (st.get("flop_primary") or ffma * 2) / (st["ms_primary"] * 1e-3) / 1e12  # executed flops
-    shad = st["tests_shadow"] * ffma * 2 / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
-    shad_ref = st["tests_shadow_ref"] * ffma * 2 / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
+    fp, fs = st.get("flop_primary") or 0.0, st.get("flop_shadow") or 0.0  # flops the formulation needs per pair (0 in cull mode)
+    prim = st["tests_primary"] * fp / (st["ms_primary"] * 1e-3) / 1e12
+    shad = st["tests_shadow"] * fs / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
+    shad_ref = st["tests_shadow_ref"] * fs / max(st["ms_shadow"], 1e-9) / 1e-3 / 1e12
     rays = st["n_primary_rays"] + st["n_shadow_rays"]
     print(json.dumps(dict(R=os.environ.get("TRACER_RAYS", "auto"), chunks=os.environ.get("TRACER_CHUNKS", "auto"), n_tris=n, W=W, H=H, L=L, wall_s=round(wall, 3), **{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()},
                           primary_tflops=round(prim, 2), shadow_tflops_swept=round(shad, 2), shadow_tflops_ref=round(shad_ref, 2),
