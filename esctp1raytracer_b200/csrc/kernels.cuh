@@ -700,7 +700,9 @@ __global__ void iota_kernel(int *a, int n) {
 // so the pairs actually swept track the reference's own early-exit count (main.cpp:324) and the host is not in
 // the loop at all: block offsets, slice counts, the chunk scheme and the early stop ("every ray has its occluder")
 // are decided on the device.  Round 1 ran A/B/C as 4 launches per chunk with host read-backs in between.
-constexpr int SHADOW_R = 16;    // rays per thread of a full shadow-ray block (blocks of NT * SHADOW_R consecutive list entries)
+constexpr int SHADOW_R = 16;    // rays per thread of a full shadow-ray block (blocks of NT * SHADOW_R consecutive list entries).
+                                // 32 measured slower (C4: 397 vs 330 ms): a thread's strict evaluations serialise over twice the
+                                // rays and the CTAs that hold them are the stragglers of every chunk barrier (23 % waiting)
 constexpr int SL_MAXF = 1022;   // ray groups per launch (the host batches bigger lights: 146 vertices x NFACE)
 constexpr int SL_MAXCHUNK = 64;
 constexpr int CBLK = 1024;      // list entries per compaction block
@@ -734,15 +736,15 @@ struct ShadowLightParams {
 // (occlusion(), main.cpp:314-329): the first accepted face in order ends the ray and leaves t = t2 behind (the
 // multi-light carry).  Origin, direction and length stay in the pixel state and are fetched on demand: only a
 // few rays per work item ever get here.  Ray r of the thread is list entry min(e0 + r, e_last).
-// Returns newly occluded rays (bits 0-15) | evaluations << 16 | filter misses << 24.
-__device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float *__restrict__ tri_verts, const int *__restrict__ list_in,
+// Returns newly occluded rays (bits 0-31) | evaluations << 32 | filter misses << 48.
+__device__ __noinline__ unsigned long long strict_shadow(const PixelState &px, const float *__restrict__ tri_verts, const int *__restrict__ list_in,
                                                int n_px, int e0, int e_last, unsigned mask, int tri, unsigned filt) {
     const float *q = tri_verts + 9 * (size_t)tri;
     const f3 v0 = strict::mk(__ldg(q), __ldg(q + 1), __ldg(q + 2));
     const f3 v1 = strict::mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
     const f3 v2 = strict::mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
     const size_t n = (size_t)n_px;
-    unsigned ret = 0;
+    unsigned long long ret = 0;
     while (mask) {
         const int r = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -750,11 +752,11 @@ __device__ __noinline__ unsigned strict_shadow(const PixelState &px, const float
         const f3 o = strict::mk(px.ro[k], px.ro[n + k], px.ro[2 * n + k]);
         const f3 d = strict::mk(px.rd[k], px.rd[n + k], px.rd[2 * n + k]);
         float t = px.rt[k], v = 0.f; // the ray has no occluder yet, so t is its initial length (main.cpp:764)
-        ret += 1u << 16;
+        ret += 1ull << 32;
         if (strict::intersect_triangle(o, d, v0, v1, v2, t, v)) {
             atomicMin(&px.best_occ[k], ((unsigned long long)(unsigned)tri << 32) | __float_as_uint(t));
-            ret |= 1u << r;
-            if (!((filt >> r) & 1u)) ret += 1u << 24;
+            ret |= 1ull << r;
+            if (!((filt >> r) & 1u)) ret += 1ull << 48;
         }
     }
     return ret;
@@ -790,9 +792,9 @@ __device__ __forceinline__ void shadow_item(sweep::SmemT<2> &sm, const ShadowLig
     unsigned swept = 0;
     sweep::sweep_table<RR, sweep::MODE_QBAR, true, EXHAUSTIVE>(
         sm, tab, lo, hi, p.n_tris, rp, rq, qbar, qdelta, valid, done, gtile, swept, [&](unsigned mask, int tri, unsigned filt) {
-            const unsigned c = strict_shadow(p.px, p.tri_verts, list_in, n, e0, seg_end - 1, mask, tri, filt);
-            n_strict += (c >> 16) & 0xffu, n_miss += c >> 24;
-            return c & 0xffffu;
+            const unsigned long long c = strict_shadow(p.px, p.tri_verts, list_in, n, e0, seg_end - 1, mask, tri, filt);
+            n_strict += (unsigned)(c >> 32) & 0xffffu, n_miss += (unsigned)(c >> 48);
+            return (unsigned)c;
         },
         &n_pipe_err);
     tests += (unsigned long long)swept * sweep::TILE * __popc(valid);

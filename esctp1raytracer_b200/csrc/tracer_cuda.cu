@@ -332,6 +332,7 @@ int launch_primary(int R, bool ex, int qmode, const trk::PrimaryParams &p, int g
         return ex ? launch_primary_q<2, true, OQ>(p, grid, st) : launch_primary_q<2, false, OQ>(p, grid, st);
     }
     if (qmode == QB) {
+        if (R == 32) return ex ? launch_primary_q<32, true, QB>(p, grid, st) : launch_primary_q<32, false, QB>(p, grid, st);
         if (R == 16) return ex ? launch_primary_q<16, true, QB>(p, grid, st) : launch_primary_q<16, false, QB>(p, grid, st);
         if (R == 8) return ex ? launch_primary_q<8, true, QB>(p, grid, st) : launch_primary_q<8, false, QB>(p, grid, st);
         if (R == 4) return ex ? launch_primary_q<4, true, QB>(p, grid, st) : launch_primary_q<4, false, QB>(p, grid, st);
@@ -370,7 +371,7 @@ Decomp pick_decomp(int64_t n_rays, int n_tiles, int n_sms, int forced_R, int ext
     // mean q (jittered samples) 16, 8, 4 or 2; three-row form (own q) 12, 8, 4 or 2
     // (C4 closest-hit sweep on one B200: 997 ms at 16, 944 at 24, 905 at 32)
     const bool own_q = qmode == sweep::MODE_OWNQ;
-    const int big = own_q ? 12 : (qmode == sweep::MODE_QBAR ? 16 : 32), mid = own_q ? 8 : 16;
+    const int big = own_q ? 12 : 32, mid = own_q ? 8 : 16;
     if (forced_R == 2 || forced_R == 4 || forced_R == 8 || forced_R == mid || forced_R == big || (qmode == sweep::MODE_SHAREDQ && forced_R == 24)) {
         d.R = forced_R, d.n_blocks = blocks_for(forced_R);
     } else {
