@@ -530,7 +530,7 @@ def main():
                                   "note": "FP32 flops the sweeps execute per (ray, triangle) pair, all in the FMA pipe (FFMA = 2, FADD = 1).  "
                                           "Span form (csrc/sweep.cuh): for rays that share q the three affine edge rows of a triangle are "
                                           "two lower and two upper bounds of p; per thread and triangle 4 FFMA + 2 FMNMX evaluate them "
-                                          "(closest hit: R = 24 pixels of one image row share q exactly; shadow: 8 FFMA, R = 16 q-sorted rays "
+                                          "(closest hit: R = 32 pixels of one image row share q exactly; shadow: 8 FFMA, R = 16 q-sorted rays "
                                           "share mean q + |B| * spread, still a necessary condition); per PAIR x = sat(S p + ax), "
                                           "y = sat(ay - S p) (2 FADD.SAT = 2 flops) and acc += x*y (half a packed FFMA2 = 2 flops): "
                                           "4 + 8/R resp. 4 + 16/R flops.  No integer/ALU-pipe instruction per pair.  Because half of the "
@@ -561,7 +561,7 @@ def main():
                 "ceiling_note": "the loop is FMA-pipe issue bound: on this part a scalar FMA-pipe instruction costs ~1.3 issue cycles (own "
                                 "microbenchmark: scalar FFMA chains peak at 0.745 per cycle and scheduler = peak_scalar_ffma; only packed FFMA2 "
                                 "reaches 0.92), independent of occupancy; per pair the loop issues 2 FADD.SAT + FFMA2/2, per thread and "
-                                "triangle 4 (shadow: 8) FFMA + 2 FMNMX + 2 LDS.128 (tools/sweep_mb4.cu: 9.3 Tpairs/s at R = 24, "
+                                "triangle 4 (shadow: 8) FFMA + 2 FMNMX + 2 LDS.128 (tools/sweep_mb4.cu: 9.5 Tpairs/s at R = 32, "
                                 "8.2 at R = 16 with shared mean q; profiles/r02_*)",
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": (hbm_gbs / hbm_peak) if hbm_peak else None,
                         "streams": "span tables (32 B/triangle/origin) + vertices (36 B/triangle) + framebuffer (3 B/pixel)"},

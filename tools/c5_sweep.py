@@ -6,9 +6,9 @@ tests/test_gpu_fullsize.py::test_16spp_jittered_parity).
         [--brute 10000,100000,1000000,4000000] [--cull 10000,30000,...] [--width 7680 --height 4320 --spp 16]
 
 One JSON line per (mode, N) on rank 0: ms/frame (max over ranks, CUDA events around the frame incl. the band gather),
-Mrays/s, and for the default (brute-force) mode the FP32 rate of the sweeps: with jitter the 16 rays of a thread (one sample
-of 16 pixels of an image row) share a mean q within their stratum, so the closest-hit sweep runs the span form with
-8 FFMA per thread and triangle: 4 + 16/16 = 5 flops per pair (round 2 before the span form: three rows, own q, 15)."""
+Mrays/s, and for the default (brute-force) mode the FP32 rate of the sweeps: with jitter the 32 rays of a thread (one sample
+of 32 pixels of an image row) share a mean q within their stratum, so the closest-hit sweep runs the span form with
+8 FFMA per thread and triangle: 4 + 16/32 = 4.5 flops per pair (round 2 before the span form: three rows, own q, 15)."""
 import argparse
 import hashlib
 import json
