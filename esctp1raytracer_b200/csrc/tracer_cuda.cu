@@ -865,7 +865,7 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
         p.cam = dc, p.bands = bands, p.table = qmode == sweep::MODE_OWNQ ? s->eye_table : s->eye_span, p.n_tiles = n_tiles, p.n_tris = s->n_tris;
         p.tri_verts = s->tri_verts;
         p.best = s->best, p.counters = s->counters, p.work = s->work;
-        p.n_rows = n_rows, p.n_blocks = 0; // ray blocks = screen tiles of (TX R) x (512 / TX) pixels: least edge waste wins
+        p.n_rows = n_rows, p.n_blocks = 0; // ray blocks = screen tiles of (TX R) x (NT / TX) pixels: least edge waste wins
         for (int lg = 3; lg <= 6; ++lg) {
             const int tw = (1 << lg) * d.R, th = sweep::NT >> lg;
             const int tx = (W + tw - 1) / tw, nb = tx * ((n_rows + th - 1) / th);
@@ -1196,10 +1196,9 @@ int tracer_cuda_render_scene(tracer_scene_dev *s, const tracer_camera *cam, int3
     s->stats.filter_misses = (int64_t)hc.filter_misses;
     s->stats.pipeline_errors = (int64_t)hc.pipeline_errors;
     s->stats.kernel_launches = launches;
-    // shadow sweeps: 6 FFMA per pair, or (6 + 3R) FFMA per R pairs when a thread's R = 8 rays share the q-terms
-    // FP32 flops the sweeps execute per swept pair (all in the FMA pipe; FFMA = 2, FMUL = 1): the three edge rows, plus
-    // the conjunction x'*y'*z' accumulated per pair (FMUL + FFMA = 3).  Shadow sweeps: (6 + 3R) FFMA per R pairs for the
-    // rows when a thread's R = 8 q-sorted rays share one q-term per row.
+    // FP32 flops the sweeps' formulation needs per swept pair (all in the FMA pipe; FFMA = 2, FADD = 1).  Span form: two
+    // saturating adds + one multiply-add per pair, plus the bound FFMAs per thread and triangle: 4 (one exact q) or 8 (mean q
+    // + |B| * spread: shadow sweeps, jittered primary samples) over the R rays of the thread.
     s->stats.flop_primary = cull ? 0.0 : flop_primary, s->stats.flop_shadow = cull ? 0.0 : 4.0 + 16.0 / trk::SHADOW_R;
     // of which multiply-adds that evaluate bounds (the rest is the two saturating adds and the accumulate of each pair)
     s->stats.flop_primary_edges = cull ? 0.0 : (flop_primary >= 15.0 ? 12.0 : flop_primary - 4.0);
