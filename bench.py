@@ -78,8 +78,10 @@ def workload_config(name, scene, W, H, spp, mode):
                         f"{scene.n_lights} lights, brute force over all objects",
             "n_tris": scene.n_tris, "n_spheres": int(len(scene.sphere_cr)), "width": W, "height": H,
             "n_lights": scene.n_lights, "spp": max(1, spp), "mode": mode,
-            "l2_policy": "inputs larger than L2 are not needed: the per-frame working "
-            "set is re-streamed every step and the ray workspace (>=400 MB at 4K) exceeds L2; no cached outputs",
+            "l2_policy": "working set larger than L2, no explicit flush: every step rewrites and re-reads its per-pixel ray "
+            "workspace (~130 B/pixel: >= 1 GB per 4K frame on one GPU, >= 135 MB per GPU at 8) against a 126 MB L2, so "
+            "nothing of step k is still cached at step k+1; the 32 MB span table is L2-resident WITHIN a step by design (it "
+            "is swept by every ray block) and is rebuilt from the vertices every frame in the e2e path; no cached outputs",
             "rng": "counter-based hash (seeded)", "partition": "interleaved 8-row bands, scene replicated",
             "spheres": "analytic spheres are an extension the reference does not have: the GPU arm renders them, the CPU "
                        "reference arm cannot (it renders the same triangles and lights without them)"}

@@ -71,8 +71,11 @@ extern "C" {
 
 int tracer_cuda_abi_version(void) { return TRACER_CUDA_ABI_VERSION; }
 
-// src/scene/camera.h:16-29.  The reference build resolves tan() to the double
-// overload (its result is narrowed), which the oracle pin test confirms.
+// src/scene/camera.h:16-29.  camera.h:20 calls tan() on a float whose value is fixed by the literal vfov = 60.f
+// (main.cpp:549): the optimised reference build folds the call at compile time to the correctly rounded float
+// (0x3f13cd3a), where glibc's run-time tanf — what an -O0 or instrumented build of the same source calls — returns
+// the neighbouring float and moves most pixels by an ulp.  tan in double, narrowed once, gives the folded value;
+// the oracle pin test holds it to the reference's -O3 camera bit for bit.
 void tracer_camera_lookat(const float eye[3], const float look[3], const float vup[3], float vfov_deg, float aspect,
                           tracer_camera *out) {
     const float theta = (float)(vfov_deg * M_PI / 180);

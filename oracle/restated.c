@@ -54,7 +54,7 @@ void rst_cross(const float a[3], const float b[3], float out[3]) {
 /* ---- src/scene/camera.h:16-29 -------------------------------------------- */
 void rst_camera(const float eye[3], const float look[3], const float vup_[3], float vfov, float aspect, float out[12]) {
     float theta = (float)(vfov * M_PI / 180); /* float * double / int, narrowed */
-    float half_height = (float)tan(theta / 2); /* resolves to ::tan(double) in the reference build */
+    float half_height = (float)tan(theta / 2); /* = the value the optimised reference build folds camera.h:20 to (see csrc/tracer_host.cpp) */
     float half_width = aspect * half_height;
     v3 origin = ld3(eye);
     v3 w = norm3(sub3(ld3(eye), ld3(look)));
