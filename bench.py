@@ -94,7 +94,11 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.first = gpu_index, None, [], 0
+
+    def mark(self):
+        """the timed region starts here: only samples that arrive from now on are reported"""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -110,7 +114,7 @@ class ClockSampler:
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, pw, reasons = [], [], [], set()
-        for l in self.lines:
+        for l in (self.lines[self.first:] or self.lines):  # (a region shorter than one sampling period: all samples)
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -355,15 +359,18 @@ def main():
 
     # ---- value: resident scene, frame stays in HBM ------------------------------------------
     rs = upload(scene)
-    for _ in range(args.warmup):
-        render(rs, main_cull)
-    barrier()
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, a few hundred ms during which driver
+    # calls can stall) must not fall into the timed region; only the samples taken inside the region are reported
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        render(rs, main_cull)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     acc = {}
     barrier()
+    sampler.mark()
     t_wall = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
