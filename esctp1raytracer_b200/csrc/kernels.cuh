@@ -105,7 +105,7 @@ struct TableParam {
 // K: the margin for unit directions; K2u: the second margin (same units); returns the scaled float row
 // row3: the same row before the second margin and the scaling, in FP64: a pair the reference could accept satisfies
 // p*row3[0] + q*row3[1] + row3[2] >= 0 in exact arithmetic (input of the span rows, span_rows below)
-__device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K, double K2u, double *row3) {
+__host__ __device__ __forceinline__ float4 project_row(const TableParam &tp, double vx, double vy, double vz, double K, double K2u, double *row3) {
     const double A = tp.U[0] * vx + tp.U[1] * vy + tp.U[2] * vz;
     const double B = tp.V[0] * vx + tp.V[1] * vy + tp.V[2] * vz;
     const double K1 = K2u * tp.dmax;
@@ -202,10 +202,76 @@ __host__ __device__ __forceinline__ void span_rows(const double (&rows)[3][3], f
     }
 }
 
+// The filter rows of ONE triangle (p: its 9 vertex floats) for the origin / parametrisation tp: the 48-byte three-row form
+// (rb, rc, rd) and, if want_span, the 32-byte span row (slo, shi).  Host-callable: tests/test_filter_rows.py checks the
+// construction on the CPU against the reference's own intersection test (tracer__origin_rows in tracer_cuda.cu).
+__host__ __device__ __forceinline__ void origin_rows(const float *__restrict__ p, const TableParam &tp, bool want_span, float4 &rb,
+                                                     float4 &rc, float4 &rd, float4 &slo, float4 &shi) {
+    const double ox = tp.o[0], oy = tp.o[1], oz = tp.o[2], lmax = tp.lmax;
+    double rows[3][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}}; // exact rows behind rb, rc, rd (always true unless set)
+    const double v0x = p[0], v0y = p[1], v0z = p[2];
+    const double e1x = (double)p[3] - v0x, e1y = (double)p[4] - v0y, e1z = (double)p[5] - v0z;
+    const double e2x = (double)p[6] - v0x, e2y = (double)p[7] - v0y, e2z = (double)p[8] - v0z;
+    const double ax = v0x - ox, ay = v0y - oy, az = v0z - oz;
+    // B = a x e2, C = e1 x a, Nn = e2 x e1, D = Nn - B - C
+    const double Bx = ay * e2z - az * e2y, By = az * e2x - ax * e2z, Bz = ax * e2y - ay * e2x;
+    const double Cx = e1y * az - e1z * ay, Cy = e1z * ax - e1x * az, Cz = e1x * ay - e1y * ax;
+    const double Nx = e2y * e1z - e2z * e1y, Ny = e2z * e1x - e2x * e1z, Nz = e2x * e1y - e2y * e1x;
+    const double Dx = Nx - Bx - Cx, Dy = Ny - By - Cy, Dz = Nz - Bz - Cz;
+    const double tprime = e2x * Cx + e2y * Cy + e2z * Cz; // e2 . (tvec x e1), tvec = -a
+    const double la = sqrt(ax * ax + ay * ay + az * az);
+    const double lb = sqrt((ax + e1x) * (ax + e1x) + (ay + e1y) * (ay + e1y) + (az + e1z) * (az + e1z));
+    const double lc = sqrt((ax + e2x) * (ax + e2x) + (ay + e2y) * (ay + e2y) + (az + e2z) * (az + e2z));
+    const double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
+    const double l3 = sqrt((e2x - e1x) * (e2x - e1x) + (e2y - e1y) * (e2y - e1y) + (e2z - e1z) * (e2z - e1z));
+    const double emax = fmax(l1, fmax(l2, l3));
+    const double reach = lmax + la + lb + lc;
+    const double eps = (double)TRC_EPS;
+    const double K = (double)sweep::CK * eps * emax * reach;
+    const double tau = (double)sweep::CK * eps * l1 * l2 * reach;
+    if (!(fabs(tprime) > tau)) {
+        // O lies within the noise of the triangle's plane: the side s is undefined.  A line through
+        // O can then only reach the (noise-dilated) triangle if it runs almost inside that plane:
+        // |d.n| <= (h + delta) / (rho - delta), with h the distance of O from the plane, rho a lower
+        // bound of the distance from O to the triangle and delta the positional noise scaled by the
+        // triangle's aspect.  Two of the three rows encode that slab (+n and -n), the third is
+        // always true.  When O is (nearly) ON the triangle — a light vertex against its own light's
+        // faces — the slab degenerates and the row is "always candidate": the strict path decides.
+        rb = rc = rd = make_float4(0.f, 0.f, 1.f, 0.f);
+        const double area2 = sqrt(Nx * Nx + Ny * Ny + Nz * Nz);
+        if (area2 > 0.0 && emax > 0.0) {
+            const double shape = emax * emax / area2;
+            const double delta = 4.0 * (double)sweep::CK * eps * reach * shape;
+            const double rho = fmax(la, fmax(lb, lc)) - emax;
+            const double h = fabs(tprime) / area2;
+            if (rho > 4.0 * delta) {
+                const double kappa = (h + delta) / (rho - delta) * 1.01 + 8.0 * eps;
+                if (kappa < 1.0) {
+                    // second margin: a fraction of the slab's own width, never below the evaluation noise of a unit row
+                    const double k2 = fmax(kappa / 8.0, 16.0 * eps);
+                    rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37, k2, rows[0]);
+                    rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37, k2, rows[1]);
+                }
+            }
+        }
+    } else {
+        const double s = tprime > 0 ? 1.0 : -1.0;
+        // round K up a little so the float row never under-states it
+        const double Kd = K * 1.0000002 + 1e-37;
+        rb = project_row(tp, s * Bx, s * By, s * Bz, Kd, Kd, rows[0]);
+        rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd, Kd, rows[1]);
+        rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd, Kd, rows[2]);
+    }
+    // rb.w (bundle-cull mode only): a lower bound of the distance from O to any point X of the triangle,
+    // |X - O| >= |V - O| - |X - V| >= max(la, lb, lc) - emax, less a slack far above the float noise of the
+    // reference's own t2.  A shadow ray that ends at O and is shorter than this cannot hit the triangle.
+    if (lmax > 0.0) rb.w = (float)fmax(0.0, (fmax(la, fmax(lb, lc)) - emax - 1e-4 * reach) * 0.999999);
+    if (want_span) span_rows(rows, slo, shi);
+}
+
 // table: the 48-byte three-row table (MODE_OWNQ sweeps, bundle-cull mode) or null; span: the 32-byte span table or null
 __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tris, int n_pad, const TableParam tp,
                                    float4 *__restrict__ table, float4 *__restrict__ span) {
-    const double ox = tp.o[0], oy = tp.o[1], oz = tp.o[2], lmax = tp.lmax;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     float4 rb, rc, rd, slo, shi;
@@ -213,66 +279,7 @@ __global__ void build_origin_table(const float *__restrict__ tri_verts, int n_tr
         rb = rc = rd = make_float4(0.f, 0.f, -1.f, 0.f);
         slo = make_float4(0.f, -sweep::SPAN_OPEN, 0.f, -sweep::SPAN_OPEN), shi = make_float4(0.f, sweep::SPAN_OPEN, 0.f, sweep::SPAN_OPEN);
     } else {
-        double rows[3][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}}; // exact rows behind rb, rc, rd (always true unless set)
-        const float *p = tri_verts + 9 * (size_t)i;
-        const double v0x = p[0], v0y = p[1], v0z = p[2];
-        const double e1x = (double)p[3] - v0x, e1y = (double)p[4] - v0y, e1z = (double)p[5] - v0z;
-        const double e2x = (double)p[6] - v0x, e2y = (double)p[7] - v0y, e2z = (double)p[8] - v0z;
-        const double ax = v0x - ox, ay = v0y - oy, az = v0z - oz;
-        // B = a x e2, C = e1 x a, Nn = e2 x e1, D = Nn - B - C
-        const double Bx = ay * e2z - az * e2y, By = az * e2x - ax * e2z, Bz = ax * e2y - ay * e2x;
-        const double Cx = e1y * az - e1z * ay, Cy = e1z * ax - e1x * az, Cz = e1x * ay - e1y * ax;
-        const double Nx = e2y * e1z - e2z * e1y, Ny = e2z * e1x - e2x * e1z, Nz = e2x * e1y - e2y * e1x;
-        const double Dx = Nx - Bx - Cx, Dy = Ny - By - Cy, Dz = Nz - Bz - Cz;
-        const double tprime = e2x * Cx + e2y * Cy + e2z * Cz; // e2 . (tvec x e1), tvec = -a
-        const double la = sqrt(ax * ax + ay * ay + az * az);
-        const double lb = sqrt((ax + e1x) * (ax + e1x) + (ay + e1y) * (ay + e1y) + (az + e1z) * (az + e1z));
-        const double lc = sqrt((ax + e2x) * (ax + e2x) + (ay + e2y) * (ay + e2y) + (az + e2z) * (az + e2z));
-        const double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
-        const double l3 = sqrt((e2x - e1x) * (e2x - e1x) + (e2y - e1y) * (e2y - e1y) + (e2z - e1z) * (e2z - e1z));
-        const double emax = fmax(l1, fmax(l2, l3));
-        const double reach = lmax + la + lb + lc;
-        const double eps = (double)TRC_EPS;
-        const double K = (double)sweep::CK * eps * emax * reach;
-        const double tau = (double)sweep::CK * eps * l1 * l2 * reach;
-        if (!(fabs(tprime) > tau)) {
-            // O lies within the noise of the triangle's plane: the side s is undefined.  A line through
-            // O can then only reach the (noise-dilated) triangle if it runs almost inside that plane:
-            // |d.n| <= (h + delta) / (rho - delta), with h the distance of O from the plane, rho a lower
-            // bound of the distance from O to the triangle and delta the positional noise scaled by the
-            // triangle's aspect.  Two of the three rows encode that slab (+n and -n), the third is
-            // always true.  When O is (nearly) ON the triangle — a light vertex against its own light's
-            // faces — the slab degenerates and the row is "always candidate": the strict path decides.
-            rb = rc = rd = make_float4(0.f, 0.f, 1.f, 0.f);
-            const double area2 = sqrt(Nx * Nx + Ny * Ny + Nz * Nz);
-            if (area2 > 0.0 && emax > 0.0) {
-                const double shape = emax * emax / area2;
-                const double delta = 4.0 * (double)sweep::CK * eps * reach * shape;
-                const double rho = fmax(la, fmax(lb, lc)) - emax;
-                const double h = fabs(tprime) / area2;
-                if (rho > 4.0 * delta) {
-                    const double kappa = (h + delta) / (rho - delta) * 1.01 + 8.0 * eps;
-                    if (kappa < 1.0) {
-                        // second margin: a fraction of the slab's own width, never below the evaluation noise of a unit row
-                        const double k2 = fmax(kappa / 8.0, 16.0 * eps);
-                        rb = project_row(tp, Nx / area2, Ny / area2, Nz / area2, kappa * 1.0000002 + 1e-37, k2, rows[0]);
-                        rc = project_row(tp, -Nx / area2, -Ny / area2, -Nz / area2, kappa * 1.0000002 + 1e-37, k2, rows[1]);
-                    }
-                }
-            }
-        } else {
-            const double s = tprime > 0 ? 1.0 : -1.0;
-            // round K up a little so the float row never under-states it
-            const double Kd = K * 1.0000002 + 1e-37;
-            rb = project_row(tp, s * Bx, s * By, s * Bz, Kd, Kd, rows[0]);
-            rc = project_row(tp, s * Cx, s * Cy, s * Cz, Kd, Kd, rows[1]);
-            rd = project_row(tp, s * Dx, s * Dy, s * Dz, Kd, Kd, rows[2]);
-        }
-        // rb.w (bundle-cull mode only): a lower bound of the distance from O to any point X of the triangle,
-        // |X - O| >= |V - O| - |X - V| >= max(la, lb, lc) - emax, less a slack far above the float noise of the
-        // reference's own t2.  A shadow ray that ends at O and is shorter than this cannot hit the triangle.
-        if (lmax > 0.0) rb.w = (float)fmax(0.0, (fmax(la, fmax(lb, lc)) - emax - 1e-4 * reach) * 0.999999);
-        if (span) span_rows(rows, slo, shi);
+        origin_rows(tri_verts + 9 * (size_t)i, tp, span != nullptr, rb, rc, rd, slo, shi);
     }
     if (table) {
         table[3 * (size_t)i] = rb;

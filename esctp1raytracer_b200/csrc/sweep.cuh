@@ -179,7 +179,7 @@ __device__ __forceinline__ void smem_init(SmemT<ROWS> &sm) {
 // One 48-byte row triple per triangle: rb = (A,B,C,-) of s*u', rc of s*v', rd of s*w', in SATURATING FORM
 // (kernels.cuh, build_origin_table): a pair the reference could accept evaluates to >= 1 on all three rows.
 // Per-ray test used by the (rare) candidate path: bit clear = some row < 1.
-__device__ __forceinline__ bool edge_pass(const float4 rb, const float4 rc, const float4 rd, float p, float q) {
+__host__ __device__ __forceinline__ bool edge_pass(const float4 rb, const float4 rc, const float4 rd, float p, float q) {
     const float x = fmaf(p, rb.x, fmaf(q, rb.y, rb.z));
     const float y = fmaf(p, rc.x, fmaf(q, rc.y, rc.z));
     const float z = fmaf(p, rd.x, fmaf(q, rd.y, rd.z));

@@ -19,8 +19,8 @@
 
 #include "kernels.cuh"
 
-// Internal (tests only, no GPU needed): the span-row construction of build_origin_table and the sweeps' per-ray span
-// test, compiled for the host from the same source.  rows9 = three exact rows (A, B, C); row8 = lo.xyzw, hi.xyzw.
+// Internal (tests only, no GPU needed): the row construction of build_origin_table and the sweeps' per-ray tests,
+// compiled for the host from the same source.  rows9 = three exact rows (A, B, C); row8 = lo.xyzw, hi.xyzw.
 extern "C" void tracer__span_rows(const double *rows9, float *row8) {
     double rows[3][3];
     for (int i = 0; i < 9; ++i) rows[i / 3][i % 3] = rows9[i];
@@ -36,6 +36,32 @@ extern "C" int tracer__span_pass(const float *row8, float p, float q, float qdel
     float ax, ay;
     sweep::span_terms_qbar(lo, hi, q, qdelta, ax, ay);
     return fminf(ps + ax, ay - ps) >= 1.f ? 1 : 0;
+}
+
+// The whole row construction of build_origin_table for ONE triangle (tri9: its 9 vertex floats).  tp18 = origin[3], U[3], V[3],
+// W[3] of the direction parametrisation d' = p*U + q*V + W, then dmax >= |d'| and lmax (the reach bound of the table).
+// out20 = rb, rc, rd (three-row form), lo, hi (span row).
+extern "C" void tracer__origin_rows(const float *tri9, const double *tp14, float *out20) {
+    trk::TableParam tp{};
+    for (int i = 0; i < 3; ++i) tp.o[i] = tp14[i], tp.U[i] = tp14[3 + i], tp.V[i] = tp14[6 + i], tp.W[i] = tp14[9 + i];
+    tp.dmax = tp14[12], tp.lmax = tp14[13];
+    float4 r[5];
+    trk::origin_rows(tri9, tp, true, r[0], r[1], r[2], r[3], r[4]);
+    for (int i = 0; i < 5; ++i) out20[4 * i] = r[i].x, out20[4 * i + 1] = r[i].y, out20[4 * i + 2] = r[i].z, out20[4 * i + 3] = r[i].w;
+}
+// n rays (p, q) against the rows of one triangle: bit 0 = the three-row test (sweep::edge_pass), bit 1 = the span test with
+// the ray's own q (sweep::span_pass), bit 2 = the span test in the hot loop's shared-q form (q = qbar, bounds widened by
+// |B| * qdelta; only meaningful when |q - qbar| <= qdelta)
+extern "C" void tracer__filter_pass(const float *rows20, int n, const float *p, const float *q, float qbar, float qdelta, unsigned char *out) {
+    float4 rr[5];
+    for (int i = 0; i < 5; ++i) rr[i] = make_float4(rows20[4 * i], rows20[4 * i + 1], rows20[4 * i + 2], rows20[4 * i + 3]);
+    float ax, ay;
+    sweep::span_terms_qbar(rr[3], rr[4], qbar, qdelta, ax, ay);
+    for (int i = 0; i < n; ++i) {
+        const float ps = p[i] * sweep::SPAN_S;
+        out[i] = (unsigned char)((sweep::edge_pass(rr[0], rr[1], rr[2], p[i], q[i]) ? 1 : 0) | (sweep::span_pass(rr[3], rr[4], ps, q[i]) ? 2 : 0) |
+                                 (fminf(ps + ax, ay - ps) >= 1.f ? 4 : 0));
+    }
 }
 
 extern "C" int tracer__mt19937_scan(uint32_t seed, int32_t n_lights, const int32_t *faces_per_light, int64_t n_px,
