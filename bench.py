@@ -518,6 +518,7 @@ def main():
             cpu = cpu_sample(scene, W, H, sample_size(scene, W, H, threads, 12.0), threads, extras=True)
         ms_prim = tot["ms_primary"] / (1 if native else n_gpus)
         ms_shad = tot["ms_shadow"] / (1 if native else n_gpus)
+        prim_tflops = flop_primary * tot["tests_primary"] / n_gpus / (ms_prim * 1e-3) / 1e12 if ms_prim else None
         line = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -563,7 +564,15 @@ def main():
                 "swept_pairs_per_step": swept_pairs / args.steps, "sweep_ms_per_step": sweep_ms_max / args.steps,
                 "executed_tflops": swept_flop / n_gpus / sweep_s / 1e12,
                 "primary_ms_per_step": ms_prim / args.steps, "shadow_ms_per_step": ms_shad / args.steps,
-                "primary_tflops": flop_primary * tot["tests_primary"] / n_gpus / (ms_prim * 1e-3) / 1e12 if ms_prim else None,
+                "primary_tflops": prim_tflops,
+                "dominant_kernel": {
+                    "kernel": "trk::primary_kernel (closest-hit sweep, one launch per frame)",
+                    "achieved": prim_tflops, "unit": "TFLOP/s", "frac": prim_tflops / peak_tflops if prim_tflops else None,
+                    "frac_of_nominal": prim_tflops / nominal if prim_tflops else None,
+                    "share_of_sweep_time": ms_prim / (ms_prim + ms_shad) if (ms_prim + ms_shad) else None,
+                    "note": "the launch the roofline contract names (algorithmic flops of that launch / its duration, CUDA events "
+                            "inside the library).  roofline.frac above is the more conservative figure over BOTH sweeps (this "
+                            "launch + the per-light shadow launches, shadow pairs at the reference's own in-order count)"},
                 "shadow_tflops": flop_shadow * tot["tests_shadow"] / n_gpus / (ms_shad * 1e-3) / 1e12 if ms_shad else None,
                 "pair_rate_tpairs_s": swept_pairs / n_gpus / sweep_s / 1e12,
                 "reference_formulation_tflops": FLOP_PER_PAIR_REF * alg_pairs / n_gpus / sweep_s / 1e12,
