@@ -2,7 +2,7 @@
 v1.0.5, through oracle/_ref): random OBJ text — triangles / quads / polygons, i, i/j, i//k, i/j/k and negative indices, g / o / usemtl
 / s statements in random places, comments, blank lines, CRLF, tabs, trailing blanks, numbers in many spellings — must load to the
 same flat scene bit for bit, or be refused by both.  Needs /root/reference (test infrastructure).
-    python tools/fuzz_loader.py [n_files] [seed]
+    python tests/fuzz_loader.py [n_files] [seed]
 """
 import os
 import sys

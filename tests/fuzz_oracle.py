@@ -1,7 +1,7 @@
 """One-off fuzz of the oracle pin: random synthetic scenes (triangle count, geometry count, 1-4 lights, edge lengths, specular,
 normals, camera, frame size, seed) rendered by the UNMODIFIED reference (oracle/_ref: scan_row) and by the restatement (scalar and AVX2
 loops): faceIDs, every float channel of every pixel, t, v and the camera must be bit-equal.  Needs /root/reference (test infrastructure).
-    python tools/fuzz_oracle.py [n_scenes]
+    python tests/fuzz_oracle.py [n_scenes]
 """
 import sys, numpy as np
 import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tests'))

@@ -4,7 +4,7 @@ AddressSanitizer + UndefinedBehaviorSanitizer.  Test infrastructure; needs /root
 
     make -C oracle ref_asan CXX=/usr/bin/g++ CC=/usr/bin/gcc
     LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libstdc++.so)" ASAN_OPTIONS=detect_leaks=0 \
-        python tools/oracle_sanitize.py
+        python tests/oracle_sanitize.py
 
 (libstdc++ is preloaded so that ASan can intercept __cxa_throw — the reference's loader throws on its two
 unloadable models; leak detection is off because the interpreter itself never frees everything)

@@ -123,3 +123,8 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "librestated" not in txt, fn
+    # the development tools are not a side door either: whatever drives the oracle lives under tests/
+    for fn in os.listdir(os.path.join(ROOT, "tools")):
+        if fn.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", fn)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt and "librestated" not in txt and "libref_oracle" not in txt, fn

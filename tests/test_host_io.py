@@ -104,7 +104,7 @@ def test_bench_model_workloads_load_the_reference_models():
 
 
 def test_loader_fuzz_against_the_reference_loader():
-    """tools/fuzz_loader.py: random OBJ/MTL text (polygons, every index form, negative indices, g / o / usemtl / s in random
+    """tests/fuzz_loader.py: random OBJ/MTL text (polygons, every index form, negative indices, g / o / usemtl / s in random
     places, CRLF, tabs, ~45 odd number spellings, shuffled and duplicated materials, d + Tr, several mtllib names) through
     model::loadobj (oracle/_ref, in a forked child: it crashes on input outside its contract) and through ours: equal bit for
     bit, or refused by both; where the reference crashes or indexes obj_materials[-1], ours refuses."""
@@ -114,7 +114,7 @@ def test_loader_fuzz_against_the_reference_loader():
     if not os.path.exists(MODELS):
         pytest.skip("reference tree not present")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_loader.py"), "250", "5"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_loader.py"), "250", "5"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     equal = int(r.stdout.split(" files: ")[1].split(" equal")[0])
     assert equal >= 80  # a good share of the files is loadable, i.e. the bit-for-bit comparison is exercised
