@@ -77,6 +77,29 @@ def test_mt19937_rejection_path(restated):
     assert np.array_equal(a, b) and a.max() == 9
 
 
+def test_mt19937_replay_equals_libstdcxx_for_any_face_count(ref_oracle):
+    """lights of 100-250 faces (not powers of two): tracer_mt19937_faceids against the draws the reference's own scan_row made
+    with std::uniform_int_distribution (libstdc++'s Lemire mapping), generator state equality asserted by the harness"""
+    from conftest import to_flat
+
+    rng = np.random.default_rng(3)
+    seen = set()
+    for _ in range(5):
+        s = scenes.soup_scene(int(rng.integers(300, 2000)), int(rng.integers(6, 14)), 2, seed=int(rng.integers(1, 9999)), edge=(0.05, 0.3))
+        lg = np.array(sorted(rng.choice(s.n_geoms, size=int(rng.integers(1, 4)), replace=False)), np.int32)  # ordinary geometries as lights
+        s2 = Scene(s.geom_tri_offset, s.tri_verts, s.geom_material, lg, tri_normals=s.tri_normals, geom_has_normals=s.geom_has_normals)
+        seen.update(int(f) for f in s2.faces_per_light)
+        W, H, seed = 48, 36, int(rng.integers(1, 2 ** 31))
+        h = ref_oracle.from_flat(to_flat(s2))
+        try:
+            fr, exact = ref_oracle.render_frame(h, W, H, (0, 1, 3), (0, 1, 0), seed=seed)
+        finally:
+            ref_oracle.free(h)
+        assert exact
+        assert np.array_equal(mt19937_faceids(s2, W, H, seed, fr["faceid"][:, 0] >= 0), fr["faceid"])
+    assert any(f & (f - 1) for f in seen)  # face counts that are not powers of two were exercised
+
+
 def test_hash_faceids_properties():
     f = hash_faceids(7, 64, 48, [2, 5])
     assert f.shape == (64 * 48, 2) and f[:, 0].max() == 1 and f[:, 1].max() == 4 and f.min() == 0
