@@ -7,92 +7,24 @@ meaningful on the B200: tests/test_gpu_*.py and the committed profiles/ hold tho
 import io
 import json
 import os
+import subprocess
 import sys
-import time
 from contextlib import redirect_stdout
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-PAIRS_PRIMARY, PAIRS_SHADOW, PAIRS_SHADOW_REF = 6_144_000, 2_000_000, 1_900_000
-MS_PRIMARY, MS_SHADOW = 3.0, 1.0
-
-
-class FakeEvent:
-    def __init__(self, enable_timing=True):
-        self.t = None
-
-    def record(self):
-        self.t = time.perf_counter()
-
-    def elapsed_time(self, other):
-        return (other.t - self.t) * 1e3
-
-
-class FakeFrame:
-    def __init__(self, stats, rgb8):
-        self.stats, self.rgb8 = stats, rgb8
-
-
-def make_stats(W, H, L):
-    hit = W * H // 2
-    return {"n_pixels": W * H, "n_primary_rays": W * H, "n_shadow_rays": hit * L, "tests_primary": PAIRS_PRIMARY,
-            "tests_shadow": PAIRS_SHADOW, "tests_shadow_ref": PAIRS_SHADOW_REF, "strict_evals": 12345, "filter_misses": 0,
-            "pipeline_errors": 0, "kernel_launches": 21, "ms_primary": MS_PRIMARY, "ms_shadow": MS_SHADOW, "ms_other": 0.1,
-            "ms_total": MS_PRIMARY + MS_SHADOW + 0.1, "flop_primary": 4.25, "flop_shadow": 5.0, "flop_primary_edges": 0.25,
-            "flop_shadow_edges": 1.0, "n_sms": 148}
-
-
-class FakeResident:
-    def close(self):
-        pass
-
-
-class FakeRenderer:
-    def __init__(self, device=0):
-        self.device = device
-
-    def fp32_peak(self, variant, iters):
-        return {0: 55.0, 1: 68.0, 3: 47.0}[variant], 1.0
-
-    def device_info(self):
-        return {"sm_count": 148, "clock_khz": 1_965_000, "name": "stand-in"}
-
-    def upload(self, scene):
-        return FakeResident()
-
-    def trace(self, scene, cam, W, H, out=None, **kw):
-        if out is not None:
-            out[...] = 7
-        return FakeFrame(make_stats(W, H, 4), out)
+from bench_standins import MS_PRIMARY, MS_SHADOW, PAIRS_PRIMARY, PAIRS_SHADOW, PAIRS_SHADOW_REF, install
 
 
 @pytest.fixture
 def dry_bench(monkeypatch):
-    import torch
-
     import bench
-    import esctp1raytracer_b200 as pkg
-    from esctp1raytracer_b200 import dist as tdist
 
-    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
-    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-    real_tensor, real_empty = torch.tensor, torch.empty
-    monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
-    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
-    monkeypatch.setattr(pkg, "Renderer", FakeRenderer)
-
-    def render_frame(renderer, rs, cam, W, H, **kw):
-        time.sleep(0.002)
-        return torch.full((H, W, 3), 7, dtype=torch.uint8), make_stats(W, H, 4)
-
-    monkeypatch.setattr(tdist, "render_frame", render_frame)
+    install(monkeypatch.setattr)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
 
@@ -173,3 +105,25 @@ def test_bench_flag_combinations_produce_one_line(dry_bench, argv):
         assert d["e2e"] is None
     if "c5" in argv:
         assert d["config"]["spp"] == 16
+
+
+def test_bench_torchrun_path_two_ranks_on_gloo():
+    """the path the driver's scaling runs take (torchrun, one rank per GPU): reductions over ranks, rank 0 prints ONE line"""
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "bench_dryrun_worker.py"), "--gpus", "2", "--steps", "3", "--warmup", "3",
+           "--workload", "small", "--tris", "2000", "--width", "64", "--height", "48", "--no-cpu-baseline"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 3 and "torchrun" in d["multi_gpu_path"]
+    assert d["rays_per_step"] == 64 * 48 + 64 * 48 // 2 * 4          # the two half-frame shares add up to the frame
+    assert d["gpu_launches"] == (21 * 3) * 2 + 3                       # both ranks' kernels + rank 0's assemble per step
+    r_ = d["roofline"]
+    # per-GPU rate: each rank sweeps half of the pairs in half of the time
+    assert r_["achieved"] == pytest.approx((4.25 * PAIRS_PRIMARY + 5.0 * PAIRS_SHADOW_REF) / ((MS_PRIMARY + MS_SHADOW) * 1e-3) / 1e12, rel=1e-3)
+    assert r_["dominant_kernel"]["frac"] == pytest.approx(4.25 * PAIRS_PRIMARY / (MS_PRIMARY * 1e-3) / 1e12 / 68.0, rel=1e-3)
+    assert d["e2e"]["h2d_bytes_per_step"] > 2 * 2000 * 36 and "per rank" in d["e2e"]["path"]
+    assert d["frame_sha256"] and d["optional_bundle_cull_mode"]["frame_identical_to_default_mode"] is True
